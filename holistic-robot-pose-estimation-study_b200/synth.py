@@ -1,0 +1,166 @@
+"""Deterministic synthetic weights and inputs (no network access: no checkpoints, no datasets).
+
+Weights are a reference-format `state_dict` (names/shapes from arch.py) drawn per tensor from numpy PCG64 streams
+seeded by (seed, crc32(name)), so every machine with numpy produces identical bytes. A plain He init in eval mode
+explodes through ~100 residual/fusion additions, so BatchNorm running statistics come from a one-off
+calibration pass over seeded noise images (scripts/make_bn_calib.py, stored in data/bn_calib_v1.npz); BN affine
+parameters, conv biases and head scales are drawn so that every stage of the forward is well-scaled and every fused
+epilogue term (BN fold, conv bias, residual, head bias) is exercised with non-trivial values.
+
+Inputs follow SURVEY.md §8d: images ~ U[0,1) fp32 NCHW (the /255 convention of scripts/test.py:93), pinhole K with
+fx=fy in U(300,650), principal point 128 +- 8, and k_value = sqrt(fx*fy*1e6/area) (lib/core/function.py:107-110).
+"""
+import math
+import os
+import zlib
+
+import numpy as np
+
+from . import arch, consts
+
+CALIB_FILE = os.path.join(consts.DATA_DIR, "bn_calib_v1.npz")
+CALIB_IMAGE_SEED = 7
+CALIB_BATCH = 8
+
+
+def _rng(seed, name):
+    return np.random.Generator(np.random.PCG64([int(seed), zlib.crc32(name.encode())]))
+
+
+def _draw(name, shape, kind, seed, robot):
+    g = _rng(seed, name)
+    f32 = np.float32
+    if kind == "conv_w":
+        cout, cin, kh, kw = shape
+        std = math.sqrt(2.0 / (kh * kw * cout))          # ctor init, full_net.py:178-181
+        if name == "depth_layer.weight":
+            std = 1e-3                                      # full_net.py:185-188
+        elif name.endswith("final_layer.weight"):
+            std = 0.2 if cin == 256 else 0.06               # heatmap logits sigma ~ 2: peaked but not one-hot
+        return (g.standard_normal(shape) * std).astype(f32)
+    if kind == "deconv_w":
+        cin, cout, kh, kw = shape
+        return (g.standard_normal(shape) * math.sqrt(2.0 / (cin * 4))).astype(f32)  # 2x2 taps reach each output
+    if kind == "conv_b":
+        if name == "depth_layer.bias":
+            return np.full(shape, 0.8, f32)                 # depth ~ 0.8*k/1000 m
+        return (g.standard_normal(shape) * 0.05).astype(f32)
+    if kind == "bn_w":
+        return g.uniform(0.6, 1.4, shape).astype(f32)
+    if kind == "bn_b":
+        return (g.standard_normal(shape) * 0.2).astype(f32)
+    if kind == "bn_mean":
+        return np.zeros(shape, f32)
+    if kind == "bn_var":
+        return np.ones(shape, f32)
+    if kind == "bn_nbt":
+        return np.asarray(1, np.int64)
+    if kind == "lin_w":
+        cout, cin = shape
+        if name.startswith("dec"):
+            return (g.standard_normal(shape) * 0.02).astype(f32)   # ~0.1 rad per refinement iteration
+        b = 1.0 / math.sqrt(cin)
+        return g.uniform(-b, b, shape).astype(f32)
+    if kind == "lin_b":
+        return (g.standard_normal(shape) * 0.02).astype(f32)
+    if kind == "buf":
+        if name == "init_pose":
+            return np.asarray([consts.ROBOTS[robot]["init_pose"]], f32)
+        return np.asarray([consts.INIT_ROT6D], f32)
+    raise ValueError(kind)
+
+
+_calib_cache = {}
+
+
+def _calib(backbone):
+    if "z" not in _calib_cache:
+        _calib_cache["z"] = np.load(CALIB_FILE) if os.path.exists(CALIB_FILE) else None
+    return _calib_cache["z"]
+
+
+def make_state_dict(robot, backbone="resnet50", seed=1234, calibrated=True):
+    """Ordered dict name -> numpy array in the reference's state-dict format."""
+    variant = "resnet50" if backbone in ("resnet", "resnet50") else "hrnet32"
+    z = _calib(variant) if calibrated else None
+    if calibrated and z is None:
+        raise FileNotFoundError("%s missing: run scripts/make_bn_calib.py" % CALIB_FILE)
+    sd = {}
+    for name, shape, kind in arch.full_net(robot, backbone):
+        t = _draw(name, shape, kind, seed, robot)
+        if z is not None and kind in ("bn_mean", "bn_var"):
+            key = "%d/%s/%s" % (seed, variant if name.startswith(("reg_backbone", "deconv")) else "rootnet", name)
+            t = z[key].astype(np.float32)
+            assert t.shape == tuple(shape), (name, t.shape, shape)
+        sd[name] = t
+    return sd
+
+
+def make_images(batch, seed):
+    g = np.random.Generator(np.random.PCG64([int(seed), 1]))
+    return g.random((batch, 3, consts.IMAGE_SIZE, consts.IMAGE_SIZE), dtype=np.float32)
+
+
+def make_camera(batch, seed):
+    """(K [B,3,3], k_value [B]) fp32."""
+    g = np.random.Generator(np.random.PCG64([int(seed), 2]))
+    f = g.uniform(300.0, 650.0, batch)
+    cx = 128.0 + g.uniform(-8.0, 8.0, batch)
+    cy = 128.0 + g.uniform(-8.0, 8.0, batch)
+    K = np.zeros((batch, 3, 3), np.float32)
+    K[:, 0, 0] = f
+    K[:, 1, 1] = f
+    K[:, 0, 2] = cx
+    K[:, 1, 2] = cy
+    K[:, 2, 2] = 1.0
+    side = np.maximum(g.uniform(120.0, 256.0, batch), g.uniform(120.0, 256.0, batch))
+    k_value = np.sqrt(f * f * 1000.0 * 1000.0 / (side * side)).astype(np.float32)
+    return K, k_value
+
+
+def make_inputs(batch, seed):
+    """(images [B,3,256,256], K [B,3,3], k_value [B]) fp32 numpy."""
+    K, kv = make_camera(batch, seed)
+    return make_images(batch, seed), K, kv
+
+
+def make_fk_inputs(robot, n, seed):
+    """Pose-sweep inputs: q ~ U(JOINT_BOUNDS), noisy rot6d of a random rotation, trans, K."""
+    spec = consts.ROBOTS[robot]
+    g = np.random.Generator(np.random.PCG64([int(seed), 3]))
+    b = np.asarray(spec["bounds"], np.float64)
+    q = (b[:, 0] + (b[:, 1] - b[:, 0]) * g.random((n, spec["dof"]))).astype(np.float32)
+    a = g.standard_normal((n, 3))
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    c = g.standard_normal((n, 3))
+    c -= (c * a).sum(1, keepdims=True) * a
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    rot6d = (np.concatenate([a, c], 1) + 1e-2 * g.standard_normal((n, 6))).astype(np.float32)
+    trans = np.stack([g.uniform(-0.5, 0.5, n), g.uniform(-0.5, 0.5, n), g.uniform(0.6, 2.0, n)], 1).astype(np.float32)
+    K, _ = make_camera(n, seed + 17)
+    return q, rot6d, trans, K
+
+
+def make_heatmaps(batch, nkpt, seed, mode="blobs"):
+    """Adversarial heatmap logits [B, nkpt*64, 64, 64] fp32 for kernel-level soft-argmax tests."""
+    g = np.random.Generator(np.random.PCG64([int(seed), 4]))
+    D = consts.DEPTH_DIM
+    x = g.standard_normal((batch, nkpt, D, D, D), dtype=np.float32)
+    if mode == "noise":
+        pass
+    elif mode == "blobs":       # Gaussian blob x20 + noise, peaks allowed at the borders
+        ax = np.arange(D, dtype=np.float32)
+        for b in range(batch):
+            for k in range(nkpt):
+                c = g.uniform(-2.0, D + 1.0, 3)
+                s = g.uniform(1.0, 4.0)
+                gz = np.exp(-0.5 * ((ax - c[0]) / s) ** 2)
+                gy = np.exp(-0.5 * ((ax - c[1]) / s) ** 2)
+                gx = np.exp(-0.5 * ((ax - c[2]) / s) ** 2)
+                x[b, k] += 20.0 * gz[:, None, None] * gy[None, :, None] * gx[None, None, :]
+    elif mode == "extreme":     # large-magnitude logits: exercises the max subtraction
+        x *= 30.0
+        x += g.uniform(-80.0, 80.0, (batch, nkpt, 1, 1, 1)).astype(np.float32)
+    else:
+        raise ValueError(mode)
+    return x.reshape(batch, nkpt * D, D, D)
