@@ -1,0 +1,33 @@
+#include "common.h"
+
+namespace hrp {
+
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+}  // namespace hrp
+
+extern "C" const char* hrp_last_error(void) { return hrp::last_error().c_str(); }
+extern "C" const char* hrp_version(void) { return "hrp_b200 0.1 (sm_100a)"; }

@@ -1,0 +1,464 @@
+// fp32 implicit-GEMM convolution (FFMA) + the small non-GEMM layers of the backbones.
+//
+// This is the HRP_PREC_FP32 parity family: the same arithmetic type the reference uses for nn.Conv2d / nn.Linear /
+// nn.ConvTranspose2d (lib/models/backbones/HRnet.py, Resnet.py, full_net.py:214-238), with BatchNorm folded into the
+// weights and the bias / residual-add / ReLU of Bottleneck.forward and BasicBlock.forward (HRnet.py:41-98) applied in
+// the epilogue. The tensor-core families (conv_tc.cu) share the ConvArgs descriptor.
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <vector>
+
+#include "kernels.h"
+
+namespace hrp {
+
+constexpr int CV_THREADS = 256;
+constexpr int CV_BK = 16;
+
+// BM x BN output tile per CTA, 16x16 threads, (BM/16)x(BN/16) outputs per thread.
+// MAJOR_M: adjacent threads own adjacent pixels (coalesced NCHW stores); otherwise adjacent channels (NHWC stores).
+template <int BM, int BN, bool MAJOR_M>
+__global__ void __launch_bounds__(CV_THREADS)
+conv_igemm_f32_kernel(const ConvArgs p) {
+  constexpr int TM = BM / 16, TN = BN / 16;
+  constexpr int A_LD = BM + 4, B_LD = BN + 4;
+  constexpr int A_F4 = BM * CV_BK / 4 / CV_THREADS;            // float4 A loads per thread per k-tile
+  constexpr int B_F4_TOTAL = CV_BK * BN / 4;                   // float4 B loads per CTA per k-tile
+  __shared__ __align__(16) float As[2][CV_BK][A_LD];
+  __shared__ __align__(16) float Bs[2][CV_BK][B_LD];
+
+  const float* __restrict__ in = static_cast<const float*>(p.in);
+  const float* __restrict__ wt = static_cast<const float*>(p.w);
+  const int tid = threadIdx.x;
+  const int tm = MAJOR_M ? (tid & 15) : (tid >> 4);
+  const int tn = MAJOR_M ? (tid >> 4) : (tid & 15);
+  const int M = p.B * p.Ho * p.Wo;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int ktiles = p.KH * p.KW * p.Cin / CV_BK;
+
+  // per-thread A-load coordinates (fixed over the K loop)
+  int a_row[A_F4], a_kq[A_F4], a_iy0[A_F4], a_ix0[A_F4];
+  const float* a_base[A_F4];
+  bool a_ok[A_F4];
+#pragma unroll
+  for (int l = 0; l < A_F4; ++l) {
+    const int idx = tid + l * CV_THREADS;
+    a_row[l] = idx >> 2;
+    a_kq[l] = idx & 3;
+    const int m = m0 + a_row[l];
+    a_ok[l] = m < M;
+    const int mm = a_ok[l] ? m : 0;
+    const int ox = mm % p.Wo, r = mm / p.Wo, oy = r % p.Ho, b = r / p.Ho;
+    a_iy0[l] = oy * p.stride - p.pad_h;
+    a_ix0[l] = ox * p.stride - p.pad_w;
+    a_base[l] = in + (size_t)b * p.Hi * p.Wi * p.Cin;
+  }
+  const int b_row = tid / (BN / 4), b_col = (tid % (BN / 4)) * 4;
+  const bool b_active = tid < B_F4_TOTAL;
+  const bool b_ok = b_active && (n0 + b_col < p.Cout);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  int c0 = 0, fr = 0, fs = 0;  // k-tile -> (channel offset, filter row, filter col)
+  float4 a_reg[A_F4], b_reg;
+
+  auto load_tile = [&](int kt) {
+#pragma unroll
+    for (int l = 0; l < A_F4; ++l) {
+      const int iy = a_iy0[l] + fr, ix = a_ix0[l] + fs;
+      const bool ok = a_ok[l] && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi;
+      a_reg[l] = ok ? __ldg(reinterpret_cast<const float4*>(a_base[l] + ((size_t)iy * p.Wi + ix) * p.Cin + c0 + a_kq[l] * 4))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    b_reg = b_ok ? __ldg(reinterpret_cast<const float4*>(wt + (size_t)(kt * CV_BK + b_row) * p.Cout + n0 + b_col))
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    c0 += CV_BK;
+    if (c0 == p.Cin) { c0 = 0; if (++fs == p.KW) { fs = 0; ++fr; } }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int l = 0; l < A_F4; ++l) {
+      As[buf][a_kq[l] * 4 + 0][a_row[l]] = a_reg[l].x;
+      As[buf][a_kq[l] * 4 + 1][a_row[l]] = a_reg[l].y;
+      As[buf][a_kq[l] * 4 + 2][a_row[l]] = a_reg[l].z;
+      As[buf][a_kq[l] * 4 + 3][a_row[l]] = a_reg[l].w;
+    }
+    if (b_active) *reinterpret_cast<float4*>(&Bs[buf][b_row][b_col]) = b_reg;
+  };
+
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kt = 0; kt < ktiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < ktiles) load_tile(kt + 1);
+#pragma unroll
+    for (int k = 0; k < CV_BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][tm * TM + i]);
+        a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+      }
+      if (TN >= 4) {
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][tn * TN + j]);
+          b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+        }
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(&Bs[buf][k][tn * TN]);
+        b[0] = v.x; b[1] = v.y;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < ktiles) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue: + bias (BN folded) [+ residual] [ReLU]
+  const float* __restrict__ res = static_cast<const float*>(p.res);
+  float* __restrict__ out = static_cast<float*>(p.out);
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + tm * TM + i;
+    if (m >= M) continue;
+    const int ox = m % p.Wo, r = m / p.Wo, oy = r % p.Ho, b = r / p.Ho;
+    const int y = oy * p.out_sy + p.out_oy, x = ox * p.out_sx + p.out_ox;
+    const size_t pix = ((size_t)b * p.Ho_full + y) * p.Wo_full + x;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tn * TN + j;
+      if (n >= p.Cout) continue;
+      float v = acc[i][j] + __ldg(p.bias + n);
+      if (p.out_nchw) {
+        const size_t o = (((size_t)b * p.Cout + n) * p.Ho_full + y) * p.Wo_full + x;
+        if (res && !p.res_after_act) v += __ldg(res + o);
+        if (p.relu) v = fmaxf(v, 0.f);
+        if (res && p.res_after_act) v += __ldg(res + o);
+        out[o] = v;
+      } else {
+        const size_t o = pix * p.ld_out + p.out_coff + n;
+        if (res && !p.res_after_act) v += __ldg(res + o);
+        if (p.relu) v = fmaxf(v, 0.f);
+        if (res && p.res_after_act) v += __ldg(res + o);
+        out[o] = v;
+      }
+    }
+  }
+}
+
+int conv_f32_launch(const ConvArgs& a, cudaStream_t s) {
+  if (a.Cin % CV_BK != 0) return fail(HRP_ERR_INVALID, "conv_f32: Cin=%d must be a multiple of %d", a.Cin, CV_BK);
+  if (a.Cout % 4 != 0 && a.Cout > 4) return fail(HRP_ERR_INVALID, "conv_f32: Cout=%d must be a multiple of 4", a.Cout);
+  const int M = a.B * a.Ho * a.Wo;
+  if (M <= 0) return HRP_OK;
+  if (a.out_nchw) {
+    dim3 grid(ceil_div(M, 64), ceil_div(a.Cout, 64));
+    conv_igemm_f32_kernel<64, 64, true><<<grid, CV_THREADS, 0, s>>>(a);
+  } else if (a.Cout <= 32) {
+    dim3 grid(ceil_div(M, 128), ceil_div(a.Cout, 32));
+    conv_igemm_f32_kernel<128, 32, false><<<grid, CV_THREADS, 0, s>>>(a);
+  } else if (M >= 128 * 2 * sm_count()) {
+    dim3 grid(ceil_div(M, 128), ceil_div(a.Cout, 64));
+    conv_igemm_f32_kernel<128, 64, false><<<grid, CV_THREADS, 0, s>>>(a);
+  } else {
+    dim3 grid(ceil_div(M, 64), ceil_div(a.Cout, 64));
+    conv_igemm_f32_kernel<64, 64, false><<<grid, CV_THREADS, 0, s>>>(a);
+  }
+  HRP_CHECK_LAUNCH("conv_igemm_f32_kernel");
+  return HRP_OK;
+}
+
+// ---- stem: Cin = 3 straight from the NCHW input image --------------------------------------------------------------------
+// HRnet.py:500-502 (3x3 s2 p1) and Resnet.py:58-60 (7x7 s2 p3). K = 27 / 147 is too thin for a tensor-core tile; the
+// layer is 0.06 / 0.31 GFLOP per frame. 64 pixels x 4 channel groups per CTA, weights broadcast from shared memory.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                 OutT* __restrict__ out, int B, int Hi, int Wi, int Ho, int Wo, int KH, int KW, int pad) {
+  extern __shared__ __align__(16) float sw[];  // [3*KH*KW][64]
+  const int K = 3 * KH * KW;
+  for (int i = threadIdx.x; i < K * 16; i += 256)
+    reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  __syncthreads();
+  const int g = threadIdx.x >> 6;
+  const long long pix = (long long)blockIdx.x * 64 + (threadIdx.x & 63);
+  const long long total = (long long)B * Ho * Wo;
+  if (pix >= total) return;
+  const int ox = (int)(pix % Wo);
+  const int oy = (int)((pix / Wo) % Ho);
+  const int b = (int)(pix / ((long long)Wo * Ho));
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = __ldg(bias + g * 16 + j);
+  const int iy0 = oy * 2 - pad, ix0 = ox * 2 - pad;
+  int k = 0;
+  for (int c = 0; c < 3; ++c) {
+    const float* ip = in + ((size_t)b * 3 + c) * Hi * Wi;
+    for (int r = 0; r < KH; ++r) {
+      const int iy = iy0 + r;
+      for (int s = 0; s < KW; ++s, ++k) {
+        const int ix = ix0 + s;
+        const float v = (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) ? __ldg(ip + (size_t)iy * Wi + ix) : 0.f;
+        const float4* wk = reinterpret_cast<const float4*>(sw + k * 64 + g * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 ww = wk[j];
+          acc[j * 4 + 0] = fmaf(v, ww.x, acc[j * 4 + 0]);
+          acc[j * 4 + 1] = fmaf(v, ww.y, acc[j * 4 + 1]);
+          acc[j * 4 + 2] = fmaf(v, ww.z, acc[j * 4 + 2]);
+          acc[j * 4 + 3] = fmaf(v, ww.w, acc[j * 4 + 3]);
+        }
+      }
+    }
+  }
+  OutT* op = out + (size_t)pix * 64 + g * 16;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float v = fmaxf(acc[j], 0.f);
+    if constexpr (sizeof(OutT) == 4) op[j] = v; else op[j] = __float2bfloat16_rn(v);
+  }
+}
+
+int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, void* out, int B, int Hi, int Wi,
+                     int Ho, int Wo, int KH, int KW, int pad, int out_bf16, cudaStream_t s) {
+  const long long total = (long long)B * Ho * Wo;
+  if (total <= 0) return HRP_OK;
+  const size_t smem = (size_t)3 * KH * KW * 64 * sizeof(float);
+  const unsigned blocks = (unsigned)ceil_div64(total, 64);
+  if (out_bf16) {
+    stem_conv_kernel<__nv_bfloat16><<<blocks, 256, smem, s>>>(in_nchw, w, bias, static_cast<__nv_bfloat16*>(out), B, Hi, Wi, Ho, Wo, KH, KW, pad);
+  } else {
+    stem_conv_kernel<float><<<blocks, 256, smem, s>>>(in_nchw, w, bias, static_cast<float*>(out), B, Hi, Wi, Ho, Wo, KH, KW, pad);
+  }
+  HRP_CHECK_LAUNCH("stem_conv_kernel");
+  return HRP_OK;
+}
+
+// ---- element-wise layers: 4 channels per thread, NHWC ---------------------------------------------------------------------
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+};
+
+// nn.MaxPool2d(3, 2, 1), Resnet.py:22,61
+template <typename T>
+__global__ void maxpool3x3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int Hi, int Wi, int Ho,
+                                    int Wo, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4 = C >> 2;
+  const long long total = (long long)B * Ho * Wo * c4;
+  if (i >= total) return;
+  const int c = (int)(i % c4) * 4;
+  long long r = i / c4;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int iy = oy * 2 - 1 + dy;
+    if (iy < 0 || iy >= Hi) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int ix = ox * 2 - 1 + dx;
+      if (ix < 0 || ix >= Wi) continue;
+      const float4 v = Vec4<T>::ld(in + (((size_t)b * Hi + iy) * Wi + ix) * C + c);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  Vec4<T>::st(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c, m);
+}
+
+int maxpool3x3s2_launch(const void* in, void* out, int B, int Hi, int Wi, int C, int bf16, cudaStream_t s) {
+  const int Ho = (Hi + 2 - 3) / 2 + 1, Wo = (Wi + 2 - 3) / 2 + 1;
+  const long long total = (long long)B * Ho * Wo * (C / 4);
+  if (total <= 0) return HRP_OK;
+  const unsigned blocks = (unsigned)ceil_div64(total, 256);
+  if (bf16) maxpool3x3s2_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), B, Hi, Wi, Ho, Wo, C);
+  else maxpool3x3s2_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(in), static_cast<float*>(out), B, Hi, Wi, Ho, Wo, C);
+  HRP_CHECK_LAUNCH("maxpool3x3s2_kernel");
+  return HRP_OK;
+}
+
+// HighResolutionModule.forward fusion sum (HRnet.py:256-263): same-resolution terms plus nearest-upsampled
+// low-resolution terms (nn.Upsample(scale_factor=2^(j-i), mode='nearest'), HRnet.py:206), then ReLU.
+template <typename T>
+__global__ void fuse_sum_kernel(const FuseArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4 = a.C >> 2;
+  const long long total = (long long)a.B * a.H * a.W * c4;
+  if (i >= total) return;
+  const int c = (int)(i % c4) * 4;
+  long long r = i / c4;
+  const int x = (int)(r % a.W); r /= a.W;
+  const int y = (int)(r % a.H);
+  const int b = (int)(r / a.H);
+  const size_t o = (((size_t)b * a.H + y) * a.W + x) * a.C + c;
+  float4 acc = Vec4<T>::ld(static_cast<const T*>(a.same[0]) + o);
+  for (int k = 1; k < a.n_same; ++k) {
+    const float4 v = Vec4<T>::ld(static_cast<const T*>(a.same[k]) + o);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  for (int k = 0; k < a.n_low; ++k) {
+    const int sh = a.shift[k];
+    const int h = a.H >> sh, w = a.W >> sh;
+    const float4 v = Vec4<T>::ld(static_cast<const T*>(a.low[k]) + (((size_t)b * h + (y >> sh)) * w + (x >> sh)) * a.C + c);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (a.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+  Vec4<T>::st(static_cast<T*>(a.out) + o, acc);
+}
+
+int fuse_sum_launch(const FuseArgs& a, int bf16, cudaStream_t s) {
+  const long long total = (long long)a.B * a.H * a.W * (a.C / 4);
+  if (total <= 0) return HRP_OK;
+  const unsigned blocks = (unsigned)ceil_div64(total, 256);
+  if (bf16) fuse_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(a);
+  else fuse_sum_kernel<float><<<blocks, 256, 0, s>>>(a);
+  HRP_CHECK_LAUNCH("fuse_sum_kernel");
+  return HRP_OK;
+}
+
+// global average pool: nn.AvgPool2d(8) on [B,2048,8,8] (full_net.py:82,350) and F.avg_pool2d over the whole map
+// (HRnet.py:567). One thread per (frame, channel), channels adjacent across the warp.
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int HW, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int c = i % C, b = i / C;
+  const T* p = in + (size_t)b * HW * C + c;
+  float s = 0.f;
+  for (int k = 0; k < HW; ++k) {
+    if constexpr (sizeof(T) == 4) s += __ldg(p + (size_t)k * C); else s += __bfloat162float(p[(size_t)k * C]);
+  }
+  out[i] = s / (float)HW;
+}
+
+int avgpool_launch(const void* in, float* out, int B, int HW, int C, int bf16, cudaStream_t s) {
+  if (B * C <= 0) return HRP_OK;
+  if (bf16) avgpool_kernel<__nv_bfloat16><<<ceil_div(B * C, 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in), out, B, HW, C);
+  else avgpool_kernel<float><<<ceil_div(B * C, 256), 256, 0, s>>>(static_cast<const float*>(in), out, B, HW, C);
+  HRP_CHECK_LAUNCH("avgpool_kernel");
+  return HRP_OK;
+}
+
+// ---- heads --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+depth_head_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
+                  const float* __restrict__ k_value, float* __restrict__ depth, int C) {
+  const int b = blockIdx.x;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) s = fmaf(__ldg(feat + (size_t)b * C + c), __ldg(w + c), s);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += ws[i];
+    const float gamma = t + bias[0];                       // depth_layer, full_net.py:315
+    depth[b] = gamma * k_value[b] / 1000.0f;               // full_net.py:334-336
+  }
+}
+
+int depth_head_launch(const float* feat, const float* w, const float* bias, const float* k_value, float* depth, int B,
+                      int C, cudaStream_t s) {
+  if (B <= 0) return HRP_OK;
+  depth_head_kernel<<<B, 256, 0, s>>>(feat, w, bias, k_value, depth, C);
+  HRP_CHECK_LAUNCH("depth_head_kernel");
+  return HRP_OK;
+}
+
+__global__ void mlp_rank_kernel(float* __restrict__ h1, const float* __restrict__ xc1, int ld,
+                                const float* __restrict__ state, int state_stride, const float* __restrict__ W1b,
+                                int B, int N, int dof) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int n = i % N, b = i / N;
+  float v = xc1[(size_t)b * ld + n];
+  const float* st = state + (size_t)b * state_stride;
+  const float* wr = W1b + (size_t)n * dof;
+  for (int j = 0; j < dof; ++j) v = fmaf(st[j], __ldg(wr + j), v);
+  h1[i] = v;
+}
+
+int mlp_rank_launch(float* h1, const float* xc1, int ld, const float* state, int state_stride, const float* W1b, int B,
+                    int N, int dof, cudaStream_t s) {
+  if (B <= 0) return HRP_OK;
+  mlp_rank_kernel<<<ceil_div(B * N, 256), 256, 0, s>>>(h1, xc1, ld, state, state_stride, W1b, B, N, dof);
+  HRP_CHECK_LAUNCH("mlp_rank_kernel");
+  return HRP_OK;
+}
+
+__global__ void mlp_dec_kernel(float* __restrict__ state_out, const float* __restrict__ state_in, int state_stride,
+                               const float* __restrict__ h2, const float* __restrict__ Wd, const float* __restrict__ bd,
+                               int B, int N, int dof) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= B * dof) return;
+  const int j = wid % dof, b = wid / dof;
+  float s = 0.f;
+  for (int n = lane; n < N; n += 32) s = fmaf(h2[(size_t)b * N + n], __ldg(Wd + (size_t)j * N + n), s);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) state_out[(size_t)b * dof + j] = (s + bd[j]) + state_in[(size_t)b * state_stride + j];   // full_net.py:394
+}
+
+int mlp_dec_launch(float* state_out, const float* state_in, int state_stride, const float* h2, const float* Wd,
+                   const float* bd, int B, int N, int dof, cudaStream_t s) {
+  if (B <= 0) return HRP_OK;
+  mlp_dec_kernel<<<ceil_div(B * dof * 32, 256), 256, 0, s>>>(state_out, state_in, state_stride, h2, Wd, bd, B, N, dof);
+  HRP_CHECK_LAUNCH("mlp_dec_kernel");
+  return HRP_OK;
+}
+
+// ---- host-side packing ------------------------------------------------------------------------------------------------------
+void pack_conv_f32(const float* w, const float* conv_bias, const float* bn_w, const float* bn_b, const float* bn_mean,
+                   const float* bn_var, int Cout, int Cin, int KH, int KW, float* w_out, float* bias_out) {
+  std::vector<double> scale(Cout, 1.0);
+  for (int o = 0; o < Cout; ++o) {
+    double b = conv_bias ? (double)conv_bias[o] : 0.0;
+    if (bn_w) {
+      scale[o] = (double)bn_w[o] / std::sqrt((double)bn_var[o] + 1e-5);   // eps: nn.BatchNorm2d default
+      b = (double)bn_b[o] + (b - (double)bn_mean[o]) * scale[o];
+    }
+    bias_out[o] = (float)b;
+  }
+  for (int r = 0; r < KH; ++r)
+    for (int s = 0; s < KW; ++s)
+      for (int c = 0; c < Cin; ++c)
+        for (int o = 0; o < Cout; ++o)
+          w_out[((size_t)(r * KW + s) * Cin + c) * Cout + o] =
+              (float)((double)w[(((size_t)o * Cin + c) * KH + r) * KW + s] * scale[o]);
+}
+
+}  // namespace hrp

@@ -1,0 +1,75 @@
+// Internal launch interface between the network executor (network.cu) and the kernels.
+#pragma once
+#include "common.h"
+
+namespace hrp {
+
+// ---- convolution as implicit GEMM over NHWC activations ------------------------------------------------------------
+// M = B*Ho*Wo output pixels, N = Cout, K = KH*KW*Cin. The same descriptor serves plain convs, the four sub-pixel
+// phases of a stride-2 transposed conv (out_s* / out_o* place the phase's pixels on the full-resolution grid) and
+// nn.Linear (H = W = 1).
+struct ConvArgs {
+  const void* in;        // NHWC [B,Hi,Wi,Cin]
+  const void* w;         // packed weights (layout depends on the kernel family)
+  const float* bias;     // [Cout] fp32, BN folded (never null)
+  const void* res;       // residual, same layout/shape as out, or null
+  void* out;             // NHWC [B,Ho_full,Wo_full,Cout]  (or NCHW fp32 when out_nchw)
+  int B, Hi, Wi, Cin, Ho, Wo, Cout;
+  int KH, KW, stride, pad_h, pad_w;
+  int out_sy, out_sx, out_oy, out_ox, Ho_full, Wo_full;
+  int relu;
+  int res_after_act;   // 0: act(acc + bias + res)   1: act(acc + bias) + res   (HRnet.py:539-540)
+  int out_nchw;
+  int ld_out;            // channel stride of one output pixel (>= Cout; lets two GEMMs share one row)
+  int out_coff;          // first output channel inside that row
+};
+
+int conv_f32_launch(const ConvArgs& a, cudaStream_t s);
+
+// Stem: NCHW fp32 [B,3,Hi,Wi] -> NHWC [B,Ho,Wo,64], KxK stride 2, BN folded, ReLU. w packed [(c*KH+r)*KW+s][64].
+int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, void* out, int B, int Hi, int Wi,
+                     int Ho, int Wo, int KH, int KW, int pad, int out_bf16, cudaStream_t s);
+
+int maxpool3x3s2_launch(const void* in, void* out, int B, int Hi, int Wi, int C, int bf16, cudaStream_t s);
+
+// out = relu( sum_i same[i] + sum_j nearest_up(low[j], 2^shift[j]) ), NHWC, up to 4 + 3 terms (HRNet fusion).
+struct FuseArgs {
+  const void* same[4];
+  const void* low[3];
+  int shift[3];
+  int n_same, n_low;
+  void* out;
+  int B, H, W, C;
+  int relu;
+};
+int fuse_sum_launch(const FuseArgs& a, int bf16, cudaStream_t s);
+
+// NHWC [B,HW,C] -> fp32 [B,C] mean over HW.
+int avgpool_launch(const void* in, float* out, int B, int HW, int C, int bf16, cudaStream_t s);
+
+// ---- heads ---------------------------------------------------------------------------------------------------------------
+// depth[b] = (dot(feat[b], w) + bias) * k_value[b] / 1000          full_net.py:312-336
+int depth_head_launch(const float* feat, const float* w, const float* bias, const float* k_value, float* depth, int B,
+                      int C, cudaStream_t s);
+// h1[b,n] = xc1[b*ld + n] + sum_j state[b*state_stride + j] * W1b[n*dof + j]     (the state columns of fc_*_1)
+int mlp_rank_launch(float* h1, const float* xc1, int ld, const float* state, int state_stride, const float* W1b, int B,
+                    int N, int dof, cudaStream_t s);
+// state_out[b,j] = state_in[b*state_stride + j] + bd[j] + sum_n h2[b,n] * Wd[j*N + n]
+int mlp_dec_launch(float* state_out, const float* state_in, int state_stride, const float* h2, const float* Wd,
+                   const float* bd, int B, int N, int dof, cudaStream_t s);
+
+// ---- integral layer / kinematics (softargmax.cu, fk_project.cu) ----------------------------------------------------------
+size_t softargmax_workspace(int B, int K, int D, int H, int W);
+int softargmax_launch(const float* hm, int B, int K, int D, int H, int W, const float* Kmat, const float* root_z,
+                      float depth_factor, float image_size, int rootid, int fixroot, float* uvd, float* xyz, void* ws,
+                      size_t ws_bytes, float* root_uv, float* trans, float* kp2d, cudaStream_t stream, int* launches);
+int fk_launch(const hrp_fk* fk, const float* q, const float* rot6d, const float* trans, const float* Kmat, int64_t N,
+              float* xyz, float* uv, cudaStream_t stream);
+
+// ---- host-side weight packing (fp32 family) --------------------------------------------------------------------------------
+// OIHW (+conv bias, +BN) -> [(r*KW+s)*Cin + c][Cout] with the BN scale folded in; bias_out[Cout].
+void pack_conv_f32(const float* w_oihw, const float* conv_bias, const float* bn_w, const float* bn_b,
+                   const float* bn_mean, const float* bn_var, int Cout, int Cin, int KH, int KW, float* w_out,
+                   float* bias_out);
+
+}  // namespace hrp

@@ -1,0 +1,1015 @@
+// Full-network executor: the graph of RootNetwithRegInt.forward (lib/models/full_net.py:262-466) as a flat op list,
+// built once from the reference-format state dict, planned per batch size (liveness-based workspace, no allocation on
+// the timed path) and replayed as one CUDA graph.
+//
+//   DepthNet      rootnet_backbone (HRNet-W32, HRnet.py:499-570) -> depth_layer -> gamma*k/1000   full_net.py:289-342
+//   keypoints     reg_backbone (ResNet-50, Resnet.py:57-68) -> avgpool, 3x deconv + 1x1 -> integral   348-360
+//                 or reg_backbone (HRNet-W32 with heatmap conv) -> integral                          361-364
+//   heads         4x linear refinement of pose and rot6d                                          376-444
+//   kinematics    FK (+ re-rooting) and both pinhole projections                                  447-450, function.py:140
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.h"
+
+struct hrp_fk;  // fk_project.cu
+
+namespace hrp {
+
+enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_RANK, OP_DEC, OP_SOFTARGMAX, OP_FK };
+enum { CLS_CONV_TC = 0, CLS_CONV_F32 = 1, CLS_STEM = 2, CLS_ELEM = 3, CLS_HEADS = 4, CLS_SOFTARGMAX = 5, CLS_FK = 6 };
+enum TKind { T_WS = 0, T_XREG, T_XROOT, T_KVAL, T_KMAT, T_FIELD, T_CONST };
+
+struct TensorInfo {
+  int64_t elems = 0;     // per frame
+  int esize = 4;
+  TKind kind = T_WS;
+  int field = -1;
+  const void* cptr = nullptr;  // T_CONST: device pointer (weights arena), batch-independent
+  int H = 0, W = 0, C = 0;
+  int last_use = -1, first_def = 1 << 30;
+  bool keep = false;
+  std::string name;
+};
+
+struct Layer {            // device-resident packed conv / linear
+  float* w = nullptr;
+  float* bias = nullptr;
+  int Cout = 0, Cin = 0, KH = 0, KW = 0;
+};
+
+struct OpDesc {
+  OpKind kind;
+  int cls;
+  int in = -1, res = -1, out = -1, in2 = -1, in3 = -1, in4 = -1;
+  int out2 = -1, out3 = -1, out4 = -1, out5 = -1;
+  int layer = -1;
+  int Hi = 1, Wi = 1, Cin = 0, Ho = 1, Wo = 1, Cout = 0, KH = 1, KW = 1, stride = 1, pad_h = 0, pad_w = 0;
+  int out_sy = 1, out_sx = 1, out_oy = 0, out_ox = 0, Ho_full = 1, Wo_full = 1, relu = 0, out_nchw = 0;
+  int res_after_act = 0;
+  int same[4] = {-1, -1, -1, -1}, low[3] = {-1, -1, -1}, shift[3] = {0, 0, 0}, n_same = 0, n_low = 0;
+  int ld = 0, coff = 0, state_stride = 0, dof = 0, N = 0;
+  const float* wptr = nullptr;   // small head weights
+  const float* bptr = nullptr;
+  double flops = 0.0;    // per frame
+};
+
+struct Plan {
+  int B = 0;
+  size_t ws_bytes = 0;
+  char* ws = nullptr;
+  std::vector<size_t> off;
+  size_t io_xreg = 0, io_xroot = 0, io_kv = 0, io_K = 0, io_out = 0, sa_ws = 0, sa_ws_bytes = 0;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};
+};
+
+}  // namespace hrp
+
+using namespace hrp;
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct WeightSpec {
+  std::string name;
+  std::vector<int64_t> shape;
+  bool optional = false;  // num_batches_tracked
+};
+
+struct hrp_handle {
+  hrp_config cfg{};
+  int device = 0;
+  hrp_fk* fk = nullptr;
+  int dof = 0, nkpt = 0, ref_kp = 0;
+  std::vector<WeightSpec> specs;
+  std::unordered_map<std::string, int> spec_index;
+  std::unordered_map<std::string, HostTensor> host;
+  bool finalized = false;
+  bool use_graph = true;
+  std::vector<void*> dev_allocs;
+  std::vector<Layer> layers;
+  std::vector<TensorInfo> tensors;
+  std::vector<OpDesc> ops;
+  std::map<int, std::unique_ptr<Plan>> plans;
+  std::unordered_map<std::string, int> debug;
+  cudaStream_t capture_stream = nullptr;
+  int64_t last_launches = 0;
+  int t_xreg = -1, t_xroot = -1, t_kval = -1, t_kmat = -1, t_field[HRP_NUM_FIELDS];
+  int field_width[HRP_NUM_FIELDS];
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// expected tensors, in the reference's naming (mirrors holistic-robot-pose-estimation-study_b200/arch.py)
+// ---------------------------------------------------------------------------------------------------------------------
+struct SpecBuilder {
+  std::vector<WeightSpec>& v;
+  void add(const std::string& n, std::vector<int64_t> s, bool opt = false) { v.push_back({n, std::move(s), opt}); }
+  void bn(const std::string& p, int c) {
+    add(p + ".weight", {c}); add(p + ".bias", {c}); add(p + ".running_mean", {c}); add(p + ".running_var", {c});
+    add(p + ".num_batches_tracked", {}, true);
+  }
+  void conv(const std::string& p, int cin, int cout, int k, bool bias = false) {
+    add(p + ".weight", {cout, cin, k, k});
+    if (bias) add(p + ".bias", {cout});
+  }
+  void conv_bn(const std::string& pc, const std::string& pb, int cin, int cout, int k, bool bias = false) {
+    conv(pc, cin, cout, k, bias); bn(pb, cout);
+  }
+  void bottleneck(const std::string& p, int cin, int planes, bool down) {
+    conv_bn(p + ".conv1", p + ".bn1", cin, planes, 1);
+    conv_bn(p + ".conv2", p + ".bn2", planes, planes, 3);
+    conv_bn(p + ".conv3", p + ".bn3", planes, planes * 4, 1);
+    if (down) conv_bn(p + ".downsample.0", p + ".downsample.1", cin, planes * 4, 1);
+  }
+  void linear(const std::string& p, int cin, int cout) { add(p + ".weight", {cout, cin}); add(p + ".bias", {cout}); }
+};
+
+const int kResnetBlocks[4] = {3, 4, 6, 3};
+const int kResnetPlanes[4] = {64, 128, 256, 512};
+const int kHrModules[3] = {1, 4, 3};
+const int kHrChannels[4] = {32, 64, 128, 256};
+const int kHrHead[4] = {32, 64, 128, 256};
+
+std::string S(const char* fmt, ...) {
+  char buf[256];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  return buf;
+}
+
+void spec_resnet50(SpecBuilder& sb, const std::string& p) {
+  sb.conv_bn(p + "conv1", p + "bn1", 3, 64, 7);
+  int cin = 64;
+  for (int l = 0; l < 4; ++l)
+    for (int b = 0; b < kResnetBlocks[l]; ++b) {
+      sb.bottleneck(S("%slayer%d.%d", p.c_str(), l + 1, b), cin, kResnetPlanes[l], b == 0);
+      cin = kResnetPlanes[l] * 4;
+    }
+}
+
+void spec_hrnet(SpecBuilder& sb, const std::string& p, int hm_channels) {
+  sb.conv_bn(p + "conv1", p + "bn1", 3, 64, 3);
+  sb.conv_bn(p + "conv2", p + "bn2", 64, 64, 3);
+  for (int b = 0; b < 4; ++b) sb.bottleneck(S("%slayer1.%d", p.c_str(), b), b == 0 ? 64 : 256, 64, b == 0);
+  for (int st = 0; st < 3; ++st) {
+    const int nb = st + 2;
+    const std::string t = S("%stransition%d", p.c_str(), st + 1);
+    if (st == 0) {
+      sb.conv_bn(t + ".0.0", t + ".0.1", 256, 32, 3);
+      sb.conv_bn(t + ".1.0.0", t + ".1.0.1", 256, 64, 3);
+    } else {
+      sb.conv_bn(S("%s.%d.0.0", t.c_str(), nb - 1), S("%s.%d.0.1", t.c_str(), nb - 1), kHrChannels[nb - 2], kHrChannels[nb - 1], 3);
+    }
+    for (int m = 0; m < kHrModules[st]; ++m) {
+      const std::string s = S("%sstage%d.%d", p.c_str(), st + 2, m);
+      for (int bi = 0; bi < nb; ++bi)
+        for (int k = 0; k < 4; ++k) {
+          const std::string q = S("%s.branches.%d.%d", s.c_str(), bi, k);
+          sb.conv_bn(q + ".conv1", q + ".bn1", kHrChannels[bi], kHrChannels[bi], 3);
+          sb.conv_bn(q + ".conv2", q + ".bn2", kHrChannels[bi], kHrChannels[bi], 3);
+        }
+      for (int i = 0; i < nb; ++i)
+        for (int j = 0; j < nb; ++j) {
+          const std::string f = S("%s.fuse_layers.%d.%d", s.c_str(), i, j);
+          if (j > i) sb.conv_bn(f + ".0", f + ".1", kHrChannels[j], kHrChannels[i], 1);
+          else if (j < i)
+            for (int k = 0; k < i - j; ++k)
+              sb.conv_bn(S("%s.%d.0", f.c_str(), k), S("%s.%d.1", f.c_str(), k), kHrChannels[j],
+                         k == i - j - 1 ? kHrChannels[i] : kHrChannels[j], 3);
+        }
+    }
+  }
+  for (int i = 0; i < 4; ++i) sb.bottleneck(S("%sincre_modules.%d.0", p.c_str(), i), kHrChannels[i], kHrHead[i], true);
+  for (int i = 0; i < 3; ++i)
+    sb.conv_bn(S("%sdownsamp_modules.%d.0", p.c_str(), i), S("%sdownsamp_modules.%d.1", p.c_str(), i), kHrHead[i] * 4, kHrHead[i + 1] * 4, 3, true);
+  sb.conv_bn(p + "final_feat_layer.0", p + "final_feat_layer.1", 1024, 2048, 1, true);
+  if (hm_channels) sb.conv(p + "final_layer", 32, hm_channels, 1, true);
+}
+
+void build_specs(hrp_handle* h) {
+  SpecBuilder sb{h->specs};
+  const int hm = h->nkpt * 64;
+  if (h->cfg.backbone == HRP_BACKBONE_RESNET50) {
+    spec_resnet50(sb, "reg_backbone.");
+    int cin = 2048;
+    for (int i = 0; i < 3; ++i) {
+      sb.add(S("deconv_layers.%d.weight", 3 * i), {cin, 256, 4, 4});
+      sb.bn(S("deconv_layers.%d", 3 * i + 1), 256);
+      cin = 256;
+    }
+    sb.conv("final_layer", 256, hm, 1, true);
+  } else {
+    spec_hrnet(sb, "reg_backbone.", hm);
+  }
+  sb.linear("fc_pose_1", 2048 + h->dof, 1024);
+  sb.linear("fc_pose_2", 1024, 1024);
+  sb.linear("decpose", 1024, h->dof);
+  sb.linear("fc_rot_1", 2048 + 6, 1024);
+  sb.linear("fc_rot_2", 1024, 1024);
+  sb.linear("decrot", 1024, 6);
+  spec_hrnet(sb, "rootnet_backbone.", 0);
+  sb.conv("depth_layer", 2048, 1, 1, true);
+  sb.add("init_pose", {1, h->dof});
+  sb.add("init_rot", {1, 6});
+  for (size_t i = 0; i < h->specs.size(); ++i) h->spec_index[h->specs[i].name] = (int)i;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// graph construction
+// ---------------------------------------------------------------------------------------------------------------------
+struct Tn { int id = -1, H = 0, W = 0, C = 0; };
+
+struct GraphBuilder {
+  hrp_handle* h;
+  int status = HRP_OK;
+  int act_esize = 4;
+
+  const float* W(const std::string& name) {
+    auto it = h->host.find(name);
+    if (it == h->host.end()) { if (status == HRP_OK) status = fail(HRP_ERR_WEIGHT, "missing tensor %s", name.c_str()); return nullptr; }
+    return it->second.data.data();
+  }
+  bool has(const std::string& name) { return h->host.count(name) != 0; }
+
+  float* upload(const std::vector<float>& v) {
+    float* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)) != cudaSuccess) {
+      if (status == HRP_OK) status = fail(HRP_ERR_NOMEM, "cudaMalloc of %zu bytes for weights failed", v.size() * sizeof(float));
+      cudaGetLastError();
+      return nullptr;
+    }
+    h->dev_allocs.push_back(d);
+    if (cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      if (status == HRP_OK) status = fail(HRP_ERR_CUDA, "weight upload failed");
+      cudaGetLastError();
+    }
+    return d;
+  }
+
+  Tn new_tensor(int H, int W_, int C, int esize, const char* name = "") {
+    TensorInfo t;
+    t.elems = (int64_t)H * W_ * C; t.esize = esize; t.H = H; t.W = W_; t.C = C; t.name = name;
+    h->tensors.push_back(t);
+    return Tn{(int)h->tensors.size() - 1, H, W_, C};
+  }
+  int special(TKind k, int64_t elems, int field = -1) {
+    TensorInfo t; t.kind = k; t.elems = elems; t.field = field; t.keep = true;
+    h->tensors.push_back(t);
+    return (int)h->tensors.size() - 1;
+  }
+  int constant(const float* dptr) {
+    TensorInfo t; t.kind = T_CONST; t.cptr = dptr; t.keep = true;
+    h->tensors.push_back(t);
+    return (int)h->tensors.size() - 1;
+  }
+
+  // conv (+bias) (+BN) packed for the fp32 family. wname = "<prefix>.weight"; bn prefix may be empty.
+  int make_layer(const std::string& pc, const std::string& pb, int Cin, int Cout, int KH, int KW) {
+    const float* w = W(pc + ".weight");
+    const float* cb = has(pc + ".bias") ? W(pc + ".bias") : nullptr;
+    const float *g = nullptr, *b = nullptr, *m = nullptr, *v = nullptr;
+    if (!pb.empty()) { g = W(pb + ".weight"); b = W(pb + ".bias"); m = W(pb + ".running_mean"); v = W(pb + ".running_var"); }
+    if (status != HRP_OK) return -1;
+    std::vector<float> wp((size_t)KH * KW * Cin * Cout), bp(Cout);
+    pack_conv_f32(w, cb, g, b, m, v, Cout, Cin, KH, KW, wp.data(), bp.data());
+    Layer L; L.Cout = Cout; L.Cin = Cin; L.KH = KH; L.KW = KW;
+    L.w = upload(wp); L.bias = upload(bp);
+    h->layers.push_back(L);
+    return (int)h->layers.size() - 1;
+  }
+
+  Tn conv(const Tn& x, const std::string& pc, const std::string& pb, int Cout, int k, int stride, int pad, int relu,
+          int res = -1, int res_after_act = 0, int out_nchw = 0, int out_esize = -1, const char* name = "") {
+    OpDesc op{};
+    op.kind = OP_CONV; op.cls = CLS_CONV_F32;
+    op.layer = make_layer(pc, pb, x.C, Cout, k, k);
+    op.Hi = x.H; op.Wi = x.W; op.Cin = x.C; op.Cout = Cout; op.KH = op.KW = k; op.stride = stride; op.pad_h = op.pad_w = pad;
+    op.Ho = (x.H + 2 * pad - k) / stride + 1; op.Wo = (x.W + 2 * pad - k) / stride + 1;
+    op.Ho_full = op.Ho; op.Wo_full = op.Wo; op.relu = relu; op.res = res; op.res_after_act = res_after_act; op.out_nchw = out_nchw;
+    Tn y = new_tensor(op.Ho, op.Wo, Cout, out_esize > 0 ? out_esize : act_esize, name);
+    op.in = x.id; op.out = y.id; op.ld = Cout;
+    op.flops = 2.0 * op.Ho * op.Wo * Cout * k * k * x.C;
+    h->ops.push_back(op);
+    return y;
+  }
+
+  Tn stem(int x_ext, const std::string& pc, const std::string& pb, int k, int pad) {
+    // weights packed [(c*KH + r)*KW + s][64]
+    const float* w = W(pc + ".weight");
+    const float *g = W(pb + ".weight"), *b = W(pb + ".bias"), *m = W(pb + ".running_mean"), *v = W(pb + ".running_var");
+    Tn y = new_tensor(128, 128, 64, act_esize);
+    if (status != HRP_OK) return y;
+    std::vector<float> wp((size_t)3 * k * k * 64), bp(64);
+    for (int o = 0; o < 64; ++o) {
+      const double sc = (double)g[o] / std::sqrt((double)v[o] + 1e-5);
+      bp[o] = (float)((double)b[o] - (double)m[o] * sc);
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < k; ++r)
+          for (int s = 0; s < k; ++s)
+            wp[((size_t)(c * k + r) * k + s) * 64 + o] = (float)((double)w[(((size_t)o * 3 + c) * k + r) * k + s] * sc);
+    }
+    Layer L; L.Cout = 64; L.Cin = 3; L.KH = L.KW = k; L.w = upload(wp); L.bias = upload(bp);
+    h->layers.push_back(L);
+    OpDesc op{};
+    op.kind = OP_STEM; op.cls = CLS_STEM; op.layer = (int)h->layers.size() - 1;
+    op.in = x_ext; op.out = y.id; op.Hi = op.Wi = 256; op.Ho = op.Wo = 128; op.KH = op.KW = k; op.pad_h = pad;
+    op.flops = 2.0 * 128 * 128 * 64 * k * k * 3;
+    h->ops.push_back(op);
+    return y;
+  }
+
+  Tn bottleneck(const Tn& x, const std::string& p, int planes, int stride) {
+    Tn y = conv(x, p + ".conv1", p + ".bn1", planes, 1, 1, 0, 1);
+    y = conv(y, p + ".conv2", p + ".bn2", planes, 3, stride, 1, 1);
+    Tn r = x;
+    if (has(p + ".downsample.0.weight")) r = conv(x, p + ".downsample.0", p + ".downsample.1", planes * 4, 1, stride, 0, 0);
+    return conv(y, p + ".conv3", p + ".bn3", planes * 4, 1, 1, 0, 1, r.id);   // relu(bn3(conv3) + residual)
+  }
+
+  Tn basic(const Tn& x, const std::string& p) {
+    Tn y = conv(x, p + ".conv1", p + ".bn1", x.C, 3, 1, 1, 1);
+    return conv(y, p + ".conv2", p + ".bn2", x.C, 3, 1, 1, 1, x.id);
+  }
+
+  std::vector<Tn> hr_module(std::vector<Tn> xs, const std::string& p) {
+    const int n = (int)xs.size();
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 4; ++k) xs[i] = basic(xs[i], S("%s.branches.%d.%d", p.c_str(), i, k));
+    std::vector<Tn> out(n);
+    for (int i = 0; i < n; ++i) {
+      Tn acc = xs[i];
+      const bool has_low = i < n - 1;
+      for (int j = 0; j < i; ++j) {  // strided 3x3 chains from higher resolutions; the last conv adds the running sum
+        Tn t = xs[j];
+        for (int k = 0; k < i - j; ++k) {
+          const bool last = k == i - j - 1;
+          const std::string f = S("%s.fuse_layers.%d.%d.%d", p.c_str(), i, j, k);
+          const int relu = last ? ((j == i - 1 && !has_low) ? 1 : 0) : 1;
+          t = conv(t, f + ".0", f + ".1", last ? xs[i].C : xs[j].C, 3, 2, 1, relu, last ? acc.id : -1);
+        }
+        acc = t;
+      }
+      if (!has_low) { out[i] = acc; continue; }
+      OpDesc op{};
+      op.kind = OP_FUSE; op.cls = CLS_ELEM;
+      op.same[0] = acc.id; op.n_same = 1;
+      for (int j = i + 1; j < n; ++j) {  // 1x1 conv + BN at low resolution, nearest upsample folded into the sum
+        const std::string f = S("%s.fuse_layers.%d.%d", p.c_str(), i, j);
+        Tn t = conv(xs[j], f + ".0", f + ".1", xs[i].C, 1, 1, 0, 0);
+        op.low[op.n_low] = t.id; op.shift[op.n_low] = j - i; ++op.n_low;
+      }
+      Tn y = new_tensor(xs[i].H, xs[i].W, xs[i].C, act_esize);
+      op.out = y.id; op.Ho = y.H; op.Wo = y.W; op.Cout = y.C; op.relu = 1;
+      h->ops.push_back(op);
+      out[i] = y;
+    }
+    return out;
+  }
+
+  // returns feat tensor id (fp32 [2048]); *hm receives the NCHW heatmap tensor when hm_channels > 0
+  Tn hrnet(int x_ext, const std::string& p, int hm_channels, Tn* hm) {
+    Tn x = stem(x_ext, p + "conv1", p + "bn1", 3, 1);
+    x = conv(x, p + "conv2", p + "bn2", 64, 3, 2, 1, 1);
+    for (int b = 0; b < 4; ++b) x = bottleneck(x, S("%slayer1.%d", p.c_str(), b), 64, 1);
+    std::vector<Tn> ys;
+    ys.push_back(conv(x, p + "transition1.0.0", p + "transition1.0.1", 32, 3, 1, 1, 1));
+    ys.push_back(conv(x, p + "transition1.1.0.0", p + "transition1.1.0.1", 64, 3, 2, 1, 1));
+    ys = hr_module(ys, p + "stage2.0");
+    for (int st = 1; st < 3; ++st) {
+      const int nb = st + 2;
+      const std::string t = S("%stransition%d.%d.0", p.c_str(), st + 1, nb - 1);
+      ys.push_back(conv(ys.back(), t + ".0", t + ".1", kHrChannels[nb - 1], 3, 2, 1, 1));   // reads y_list[-1], HRnet.py:519
+      for (int m = 0; m < kHrModules[st]; ++m) ys = hr_module(ys, S("%sstage%d.%d", p.c_str(), st + 2, m));
+    }
+    if (hm_channels) *hm = conv(ys[0], p + "final_layer", "", hm_channels, 1, 1, 0, 0, -1, 0, 1, 4, "logits");
+    Tn y = bottleneck(ys[0], p + "incre_modules.0.0", kHrHead[0], 1);
+    for (int i = 0; i < 3; ++i) {
+      Tn a = bottleneck(ys[i + 1], S("%sincre_modules.%d.0", p.c_str(), i + 1), kHrHead[i + 1], 1);
+      const std::string d = S("%sdownsamp_modules.%d", p.c_str(), i);
+      y = conv(y, d + ".0", d + ".1", kHrHead[i + 1] * 4, 3, 2, 1, 1, a.id, /*res_after_act=*/1);   // incre(x) + relu(bn(conv(y)))
+    }
+    y = conv(y, p + "final_feat_layer.0", p + "final_feat_layer.1", 2048, 1, 1, 0, 1);
+    return avgpool(y);
+  }
+
+  Tn avgpool(const Tn& y) {
+    Tn f = new_tensor(1, 1, y.C, 4);
+    OpDesc op{};
+    op.kind = OP_AVGPOOL; op.cls = CLS_ELEM; op.in = y.id; op.out = f.id; op.Hi = y.H; op.Wi = y.W; op.Cin = y.C;
+    h->ops.push_back(op);
+    return f;
+  }
+
+  Tn resnet50(int x_ext, const std::string& p) {
+    Tn x = stem(x_ext, p + "conv1", p + "bn1", 7, 3);
+    Tn y = new_tensor(64, 64, 64, act_esize);
+    OpDesc op{};
+    op.kind = OP_MAXPOOL; op.cls = CLS_ELEM; op.in = x.id; op.out = y.id; op.Hi = x.H; op.Wi = x.W; op.Cin = 64;
+    h->ops.push_back(op);
+    x = y;
+    for (int l = 0; l < 4; ++l)
+      for (int b = 0; b < kResnetBlocks[l]; ++b)
+        x = bottleneck(x, S("%slayer%d.%d", p.c_str(), l + 1, b), kResnetPlanes[l], (b == 0 && l > 0) ? 2 : 1);
+    return x;
+  }
+
+  // ConvTranspose2d(k=4, s=2, p=1) + BN + ReLU as four 2x2 sub-pixel phase convolutions (full_net.py:214-238)
+  Tn deconv(const Tn& x, int idx, int Cout) {
+    const std::string wn = S("deconv_layers.%d.weight", 3 * idx), pb = S("deconv_layers.%d", 3 * idx + 1);
+    const float* w = W(wn);
+    const float *g = W(pb + ".weight"), *b = W(pb + ".bias"), *m = W(pb + ".running_mean"), *v = W(pb + ".running_var");
+    Tn y = new_tensor(x.H * 2, x.W * 2, Cout, act_esize);
+    if (status != HRP_OK) return y;
+    const int Cin = x.C;
+    std::vector<double> sc(Cout);
+    std::vector<float> bp(Cout);
+    for (int o = 0; o < Cout; ++o) { sc[o] = (double)g[o] / std::sqrt((double)v[o] + 1e-5); bp[o] = (float)((double)b[o] - (double)m[o] * sc[o]); }
+    float* dbias = upload(bp);
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        std::vector<float> wp((size_t)4 * Cin * Cout);
+        for (int ty = 0; ty < 2; ++ty)
+          for (int tx = 0; tx < 2; ++tx) {
+            const int ky = 3 - py - 2 * ty, kx = 3 - px - 2 * tx;
+            for (int c = 0; c < Cin; ++c)
+              for (int o = 0; o < Cout; ++o)
+                wp[((size_t)(ty * 2 + tx) * Cin + c) * Cout + o] = (float)((double)w[(((size_t)c * Cout + o) * 4 + ky) * 4 + kx] * sc[o]);
+          }
+        Layer L; L.Cout = Cout; L.Cin = Cin; L.KH = L.KW = 2; L.w = upload(wp); L.bias = dbias;
+        h->layers.push_back(L);
+        OpDesc op{};
+        op.kind = OP_CONV; op.cls = CLS_CONV_F32; op.layer = (int)h->layers.size() - 1;
+        op.in = x.id; op.out = y.id; op.Hi = x.H; op.Wi = x.W; op.Cin = Cin; op.Cout = Cout; op.KH = op.KW = 2; op.stride = 1;
+        op.pad_h = 1 - py; op.pad_w = 1 - px; op.Ho = x.H; op.Wo = x.W; op.out_sy = op.out_sx = 2; op.out_oy = py; op.out_ox = px;
+        op.Ho_full = y.H; op.Wo_full = y.W; op.relu = 1; op.ld = Cout;
+        op.flops = 2.0 * x.H * x.W * Cout * 4 * Cin;
+        h->ops.push_back(op);
+      }
+    return y;
+  }
+
+  // nn.Linear as a 1x1 conv over a [1,1,C] map (fp32 family)
+  Tn linear_packed(const Tn& x, const std::vector<float>& w_oi, const std::vector<float>& bias, int Cout) {
+    std::vector<float> wp((size_t)x.C * Cout), bp(Cout);
+    pack_conv_f32(w_oi.data(), bias.data(), nullptr, nullptr, nullptr, nullptr, Cout, x.C, 1, 1, wp.data(), bp.data());
+    Layer L; L.Cout = Cout; L.Cin = x.C; L.KH = L.KW = 1; L.w = upload(wp); L.bias = upload(bp);
+    h->layers.push_back(L);
+    OpDesc op{};
+    op.kind = OP_CONV; op.cls = CLS_HEADS; op.layer = (int)h->layers.size() - 1;
+    op.Cin = x.C; op.Cout = Cout; op.ld = Cout;
+    Tn y = new_tensor(1, 1, Cout, 4);
+    op.in = x.id; op.out = y.id; op.flops = 2.0 * x.C * Cout;
+    h->ops.push_back(op);
+    return y;
+  }
+
+  void heads(const Tn& xf) {
+    const int dof = h->dof, F = 2048, Hd = 1024;
+    const char* fc1[2] = {"fc_pose_1", "fc_rot_1"};
+    const char* fc2[2] = {"fc_pose_2", "fc_rot_2"};
+    const char* dec[2] = {"decpose", "decrot"};
+    const char* init[2] = {"init_pose", "init_rot"};
+    const int sd[2] = {dof, 6};
+    const int field[2] = {HRP_F_POSE, HRP_F_ROT};
+    // feature part of both first layers in ONE GEMM (iteration-invariant): xc1 = xf . W1[:, :2048]^T + b1
+    std::vector<float> w1((size_t)2 * Hd * F), b1(2 * Hd);
+    std::vector<float> w1b[2];
+    for (int k = 0; k < 2; ++k) {
+      const float* w = W(std::string(fc1[k]) + ".weight");
+      const float* b = W(std::string(fc1[k]) + ".bias");
+      if (status != HRP_OK) return;
+      w1b[k].resize((size_t)Hd * sd[k]);
+      for (int n = 0; n < Hd; ++n) {
+        std::memcpy(&w1[((size_t)k * Hd + n) * F], w + (size_t)n * (F + sd[k]), F * sizeof(float));
+        std::memcpy(&w1b[k][(size_t)n * sd[k]], w + (size_t)n * (F + sd[k]) + F, sd[k] * sizeof(float));   // state columns are LAST (cat([xf, state]))
+        b1[k * Hd + n] = b[n];
+      }
+    }
+    Tn xc1 = linear_packed(xf, w1, b1, 2 * Hd);
+    int state[2];
+    for (int k = 0; k < 2; ++k) {
+      const float* s0 = W(init[k]);
+      if (status != HRP_OK) return;
+      state[k] = constant(upload(std::vector<float>(s0, s0 + sd[k])));
+    }
+    const float* w2h[2]; const float* b2h[2]; float* dw[2]; float* db[2]; float* dw1b[2];
+    for (int k = 0; k < 2; ++k) {
+      w2h[k] = W(std::string(fc2[k]) + ".weight"); b2h[k] = W(std::string(fc2[k]) + ".bias");
+      const float* wd = W(std::string(dec[k]) + ".weight"); const float* bd = W(std::string(dec[k]) + ".bias");
+      if (status != HRP_OK) return;
+      dw[k] = upload(std::vector<float>(wd, wd + (size_t)sd[k] * Hd));
+      db[k] = upload(std::vector<float>(bd, bd + sd[k]));
+      dw1b[k] = upload(w1b[k]);
+    }
+    // fc2 layers are reused by every iteration: pack once
+    int l2[2];
+    for (int k = 0; k < 2; ++k) {
+      std::vector<float> wp((size_t)Hd * Hd), bp(Hd);
+      pack_conv_f32(w2h[k], b2h[k], nullptr, nullptr, nullptr, nullptr, Hd, Hd, 1, 1, wp.data(), bp.data());
+      Layer L; L.Cout = Hd; L.Cin = Hd; L.KH = L.KW = 1; L.w = upload(wp); L.bias = upload(bp);
+      h->layers.push_back(L);
+      l2[k] = (int)h->layers.size() - 1;
+    }
+    for (int it = 0; it < h->cfg.n_iter; ++it)
+      for (int k = 0; k < 2; ++k) {
+        Tn h1 = new_tensor(1, 1, Hd, 4);
+        OpDesc r{};
+        r.kind = OP_RANK; r.cls = CLS_HEADS; r.in = xc1.id; r.in2 = state[k]; r.out = h1.id; r.ld = 2 * Hd; r.coff = k * Hd;
+        r.state_stride = (it == 0) ? 0 : sd[k]; r.dof = sd[k]; r.N = Hd; r.wptr = dw1b[k];
+        r.flops = 2.0 * Hd * sd[k];
+        h->ops.push_back(r);
+        Tn h2 = new_tensor(1, 1, Hd, 4);
+        OpDesc c{};
+        c.kind = OP_CONV; c.cls = CLS_HEADS; c.layer = l2[k]; c.in = h1.id; c.out = h2.id; c.Cin = Hd; c.Cout = Hd; c.ld = Hd;
+        c.flops = 2.0 * Hd * Hd;
+        h->ops.push_back(c);
+        OpDesc d{};
+        d.kind = OP_DEC; d.cls = CLS_HEADS; d.in = h2.id; d.in2 = state[k]; d.out = h->t_field[field[k]];
+        d.state_stride = r.state_stride; d.dof = sd[k]; d.N = Hd; d.wptr = dw[k]; d.bptr = db[k];
+        d.flops = 2.0 * Hd * sd[k];
+        h->ops.push_back(d);
+        state[k] = h->t_field[field[k]];
+      }
+  }
+
+  int build() {
+    h->tensors.clear(); h->ops.clear();
+    act_esize = 4;
+    const int nk = h->nkpt, dof = h->dof;
+    const int fw[HRP_NUM_FIELDS] = {dof, 6, 3, 2, 1, nk * 3, nk * 3, nk * 3, nk * 2, nk * 2};
+    h->t_xreg = special(T_XREG, 3LL * 256 * 256);
+    h->t_xroot = special(T_XROOT, 3LL * 256 * 256);
+    h->t_kval = special(T_KVAL, 1);
+    h->t_kmat = special(T_KMAT, 9);
+    for (int f = 0; f < HRP_NUM_FIELDS; ++f) { h->field_width[f] = fw[f]; h->t_field[f] = special(T_FIELD, fw[f], f); }
+
+    // DepthNet
+    Tn img_feat = hrnet(h->t_xroot, "rootnet_backbone.", 0, nullptr);
+    h->tensors[img_feat.id].keep = true; h->debug["img_feat"] = img_feat.id;
+    {
+      const float* w = W("depth_layer.weight"); const float* b = W("depth_layer.bias");
+      if (status != HRP_OK) return status;
+      OpDesc op{};
+      op.kind = OP_DEPTH; op.cls = CLS_HEADS; op.in = img_feat.id; op.in2 = h->t_kval; op.out = h->t_field[HRP_F_DEPTH];
+      op.wptr = upload(std::vector<float>(w, w + 2048)); op.bptr = upload(std::vector<float>(b, b + 1)); op.Cin = 2048;
+      op.flops = 2.0 * 2048;
+      h->ops.push_back(op);
+    }
+    // keypoint branch
+    Tn xf, logits;
+    if (h->cfg.backbone == HRP_BACKBONE_RESNET50) {
+      Tn x = resnet50(h->t_xreg, "reg_backbone.");
+      xf = avgpool(x);
+      Tn d = deconv(x, 0, 256);
+      d = deconv(d, 1, 256);
+      d = deconv(d, 2, 256);
+      logits = conv(d, "final_layer", "", nk * 64, 1, 1, 0, 0, -1, 0, /*nchw=*/1, 4, "logits");
+    } else {
+      xf = hrnet(h->t_xreg, "reg_backbone.", nk * 64, &logits);
+    }
+    if (status != HRP_OK) return status;
+    h->tensors[xf.id].keep = true; h->debug["xf"] = xf.id;
+    h->tensors[logits.id].keep = true; h->debug["logits"] = logits.id;
+    {
+      OpDesc op{};
+      op.kind = OP_SOFTARGMAX; op.cls = CLS_SOFTARGMAX; op.in = logits.id; op.in2 = h->t_kmat; op.in3 = h->t_field[HRP_F_DEPTH];
+      op.out = h->t_field[HRP_F_UVD]; op.out2 = h->t_field[HRP_F_XYZ_INT]; op.out3 = h->t_field[HRP_F_ROOT_UV];
+      op.out4 = h->t_field[HRP_F_TRANS]; op.out5 = h->t_field[HRP_F_KP2D_INT];
+      h->ops.push_back(op);
+    }
+    heads(xf);
+    if (status != HRP_OK) return status;
+    {
+      OpDesc op{};
+      op.kind = OP_FK; op.cls = CLS_FK; op.in = h->t_field[HRP_F_POSE]; op.in2 = h->t_field[HRP_F_ROT]; op.in3 = h->t_field[HRP_F_TRANS];
+      op.in4 = h->t_kmat; op.out = h->t_field[HRP_F_XYZ_FK]; op.out2 = h->t_field[HRP_F_KP2D_FK];
+      h->ops.push_back(op);
+    }
+    // liveness
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+      const OpDesc& o = h->ops[i];
+      const int ids[] = {o.in, o.res, o.out, o.in2, o.in3, o.in4, o.out2, o.out3, o.out4, o.out5, o.same[0], o.same[1], o.same[2], o.same[3], o.low[0], o.low[1], o.low[2]};
+      for (int id : ids)
+        if (id >= 0) {
+          h->tensors[id].last_use = std::max(h->tensors[id].last_use, (int)i);
+          h->tensors[id].first_def = std::min(h->tensors[id].first_def, (int)i);
+        }
+    }
+    return status;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// planning and execution
+// ---------------------------------------------------------------------------------------------------------------------
+struct FreeList {   // first-fit with coalescing, offsets in bytes
+  std::map<size_t, size_t> free_;  // offset -> size
+  size_t top = 0;
+  size_t alloc(size_t n) {
+    for (auto it = free_.begin(); it != free_.end(); ++it)
+      if (it->second >= n) {
+        const size_t off = it->first, rest = it->second - n;
+        free_.erase(it);
+        if (rest) free_[off + n] = rest;
+        return off;
+      }
+    // extend the arena (merging with a trailing free block)
+    if (!free_.empty()) {
+      auto last = std::prev(free_.end());
+      if (last->first + last->second == top) {
+        const size_t off = last->first;
+        top = off + n;
+        free_.erase(last);
+        return off;
+      }
+    }
+    const size_t off = top;
+    top += n;
+    return off;
+  }
+  void release(size_t off, size_t n) {
+    auto it = free_.emplace(off, n).first;
+    auto nx = std::next(it);
+    if (nx != free_.end() && it->first + it->second == nx->first) { it->second += nx->second; free_.erase(nx); }
+    if (it != free_.begin()) {
+      auto pv = std::prev(it);
+      if (pv->first + pv->second == it->first) { pv->second += it->second; free_.erase(it); }
+    }
+  }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int64_t record_floats(const hrp_handle* h, int B, int64_t* offs) {
+  int64_t o = 0;
+  for (int f = 0; f < HRP_NUM_FIELDS; ++f) {
+    if (offs) offs[f] = o;
+    o += (int64_t)B * h->field_width[f];
+    o = (o + 3) & ~3LL;   // 16-byte aligned fields
+  }
+  if (offs) offs[HRP_NUM_FIELDS] = o;
+  return o;
+}
+
+int make_plan(hrp_handle* h, int B, Plan** out) {
+  auto it = h->plans.find(B);
+  if (it != h->plans.end()) { *out = it->second.get(); return HRP_OK; }
+  std::unique_ptr<Plan> p(new Plan());
+  p->B = B;
+  p->off.assign(h->tensors.size(), 0);
+  FreeList fl;
+  const size_t A = 256;
+  // static I/O staging (graph replays always read/write these)
+  p->io_xreg = fl.alloc(align_up((size_t)B * 3 * 256 * 256 * 4, A));
+  p->io_xroot = fl.alloc(align_up((size_t)B * 3 * 256 * 256 * 4, A));
+  p->io_kv = fl.alloc(align_up((size_t)B * 4, A));
+  p->io_K = fl.alloc(align_up((size_t)B * 9 * 4, A));
+  p->io_out = fl.alloc(align_up((size_t)record_floats(h, B, nullptr) * 4, A));
+  p->sa_ws_bytes = softargmax_workspace(B, h->nkpt, 64, 64, 64);
+  p->sa_ws = fl.alloc(align_up(p->sa_ws_bytes, A));
+  std::vector<size_t> sz(h->tensors.size(), 0);
+  std::vector<char> live(h->tensors.size(), 0);
+  for (size_t i = 0; i < h->ops.size(); ++i) {
+    for (size_t t = 0; t < h->tensors.size(); ++t) {
+      const TensorInfo& ti = h->tensors[t];
+      if (ti.kind == T_WS && ti.first_def == (int)i && !live[t]) {
+        sz[t] = align_up((size_t)ti.elems * B * ti.esize, A);
+        p->off[t] = fl.alloc(sz[t]);
+        live[t] = 1;
+      }
+    }
+    for (size_t t = 0; t < h->tensors.size(); ++t) {
+      const TensorInfo& ti = h->tensors[t];
+      if (ti.kind == T_WS && live[t] && !ti.keep && ti.last_use == (int)i) { fl.release(p->off[t], sz[t]); live[t] = 2; }
+    }
+  }
+  p->ws_bytes = fl.top;
+  HRP_CUDA(cudaSetDevice(h->device));
+  void* ws = nullptr;
+  if (cudaMalloc(&ws, p->ws_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(HRP_ERR_NOMEM, "cudaMalloc of %zu workspace bytes for batch %d failed", p->ws_bytes, B);
+  }
+  p->ws = static_cast<char*>(ws);
+  *out = p.get();
+  h->plans[B] = std::move(p);
+  return HRP_OK;
+}
+
+struct IoPtrs {
+  const float *x_reg, *x_root, *k_value, *Kmat;
+  float* out;
+};
+
+struct Profile {
+  float* ms; int64_t* launches; double* flops;
+  cudaEvent_t e0, e1;
+};
+
+int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* prof) {
+  const int B = p->B;
+  int64_t offs[HRP_NUM_FIELDS + 1];
+  record_floats(h, B, offs);
+  auto ptr = [&](int id) -> void* {
+    if (id < 0) return nullptr;
+    const TensorInfo& t = h->tensors[id];
+    switch (t.kind) {
+      case T_WS: return p->ws + p->off[id];
+      case T_XREG: return const_cast<float*>(io.x_reg);
+      case T_XROOT: return const_cast<float*>(io.x_root);
+      case T_KVAL: return const_cast<float*>(io.k_value);
+      case T_KMAT: return const_cast<float*>(io.Kmat);
+      case T_FIELD: return io.out + offs[t.field];
+      case T_CONST: return const_cast<void*>(t.cptr);
+    }
+    return nullptr;
+  };
+  int64_t launches = 0;
+  for (const OpDesc& o : h->ops) {
+    if (prof) HRP_CUDA(cudaEventRecord(prof->e0, st));
+    int n_launch = 1;
+    switch (o.kind) {
+      case OP_STEM: {
+        const Layer& L = h->layers[o.layer];
+        HRP_TRY(stem_conv_launch(static_cast<const float*>(ptr(o.in)), L.w, L.bias, ptr(o.out), B, o.Hi, o.Wi, o.Ho, o.Wo, o.KH, o.KW, o.pad_h, 0, st));
+        break;
+      }
+      case OP_CONV: {
+        const Layer& L = h->layers[o.layer];
+        ConvArgs a{};
+        a.in = ptr(o.in); a.w = L.w; a.bias = L.bias; a.res = ptr(o.res); a.out = ptr(o.out);
+        a.B = B; a.Hi = o.Hi; a.Wi = o.Wi; a.Cin = o.Cin; a.Ho = o.Ho; a.Wo = o.Wo; a.Cout = o.Cout;
+        a.KH = o.KH; a.KW = o.KW; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w;
+        a.out_sy = o.out_sy; a.out_sx = o.out_sx; a.out_oy = o.out_oy; a.out_ox = o.out_ox; a.Ho_full = o.Ho_full; a.Wo_full = o.Wo_full;
+        a.relu = o.relu; a.out_nchw = o.out_nchw; a.ld_out = o.ld; a.out_coff = 0; a.res_after_act = o.res_after_act;
+        HRP_TRY(conv_f32_launch(a, st));
+        break;
+      }
+      case OP_MAXPOOL:
+        HRP_TRY(maxpool3x3s2_launch(ptr(o.in), ptr(o.out), B, o.Hi, o.Wi, o.Cin, 0, st));
+        break;
+      case OP_FUSE: {
+        FuseArgs a{};
+        for (int k = 0; k < o.n_same; ++k) a.same[k] = ptr(o.same[k]);
+        for (int k = 0; k < o.n_low; ++k) { a.low[k] = ptr(o.low[k]); a.shift[k] = o.shift[k]; }
+        a.n_same = o.n_same; a.n_low = o.n_low; a.out = ptr(o.out); a.B = B; a.H = o.Ho; a.W = o.Wo; a.C = o.Cout; a.relu = o.relu;
+        HRP_TRY(fuse_sum_launch(a, 0, st));
+        break;
+      }
+      case OP_AVGPOOL:
+        HRP_TRY(avgpool_launch(ptr(o.in), static_cast<float*>(ptr(o.out)), B, o.Hi * o.Wi, o.Cin, 0, st));
+        break;
+      case OP_DEPTH:
+        HRP_TRY(depth_head_launch(static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, static_cast<const float*>(ptr(o.in2)), static_cast<float*>(ptr(o.out)), B, o.Cin, st));
+        break;
+      case OP_RANK:
+        HRP_TRY(mlp_rank_launch(static_cast<float*>(ptr(o.out)), static_cast<const float*>(ptr(o.in)) + o.coff, o.ld, static_cast<const float*>(ptr(o.in2)), o.state_stride, o.wptr, B, o.N, o.dof, st));
+        break;
+      case OP_DEC:
+        HRP_TRY(mlp_dec_launch(static_cast<float*>(ptr(o.out)), static_cast<const float*>(ptr(o.in2)), o.state_stride, static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, B, o.N, o.dof, st));
+        break;
+      case OP_SOFTARGMAX: {
+        int nl = 0;
+        HRP_TRY(softargmax_launch(static_cast<const float*>(ptr(o.in)), B, h->nkpt, 64, 64, 64, static_cast<const float*>(ptr(o.in2)), static_cast<const float*>(ptr(o.in3)),
+                                  h->cfg.depth_factor, h->cfg.image_size, h->ref_kp, h->cfg.fix_root, static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)),
+                                  p->ws + p->sa_ws, p->sa_ws_bytes, static_cast<float*>(ptr(o.out3)), static_cast<float*>(ptr(o.out4)), static_cast<float*>(ptr(o.out5)), st, &nl));
+        n_launch = nl;
+        break;
+      }
+      case OP_FK:
+        HRP_TRY(fk_launch(h->fk, static_cast<const float*>(ptr(o.in)), static_cast<const float*>(ptr(o.in2)), static_cast<const float*>(ptr(o.in3)), static_cast<const float*>(ptr(o.in4)), B,
+                          static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)), st));
+        break;
+    }
+    launches += n_launch;
+    if (prof) {
+      HRP_CUDA(cudaEventRecord(prof->e1, st));
+      HRP_CUDA(cudaEventSynchronize(prof->e1));
+      float ms = 0.f;
+      HRP_CUDA(cudaEventElapsedTime(&ms, prof->e0, prof->e1));
+      prof->ms[o.cls] += ms; prof->launches[o.cls] += n_launch; prof->flops[o.cls] += o.flops * B;
+    }
+  }
+  h->last_launches = launches;
+  return HRP_OK;
+}
+
+int check_forward_args(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat, int B, float* out) {
+  if (!h) return fail(HRP_ERR_INVALID, "hrp_forward: null handle");
+  if (!h->finalized) return fail(HRP_ERR_STATE, "hrp_forward: weights not finalized");
+  if (B <= 0 || B > 4096) return fail(HRP_ERR_INVALID, "hrp_forward: batch %d out of range [1, 4096]", B);
+  if (!x_reg || !x_root || !k_value || !Kmat || !out) return fail(HRP_ERR_INVALID, "hrp_forward: null pointer");
+  return HRP_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int hrp_create(const hrp_config* cfg, const hrp_fk_program* robot, int device, hrp_handle** out) {
+  if (!cfg || !robot || !out) return fail(HRP_ERR_INVALID, "hrp_create: null argument");
+  if (cfg->backbone != HRP_BACKBONE_RESNET50 && cfg->backbone != HRP_BACKBONE_HRNET32)
+    return fail(HRP_ERR_INVALID, "hrp_create: unsupported backbone %d (resnet50 or hrnet32)", cfg->backbone);
+  if (cfg->precision != HRP_PREC_FP32)
+    return fail(HRP_ERR_INVALID, "hrp_create: precision %d not available in this build (fp32 parity family only)", cfg->precision);
+  if (cfg->n_iter < 1 || cfg->n_iter > 16) return fail(HRP_ERR_INVALID, "hrp_create: n_iter %d out of range", cfg->n_iter);
+  if (cfg->image_size != 256.0f) return fail(HRP_ERR_INVALID, "hrp_create: only 256x256 inputs are supported (got %g)", cfg->image_size);
+  std::unique_ptr<hrp_handle> h(new hrp_handle());
+  h->cfg = *cfg;
+  h->device = device;
+  HRP_TRY(hrp_fk_create(robot, &h->fk));
+  h->dof = robot->dof; h->nkpt = robot->nkpt; h->ref_kp = robot->root_kp;
+  const int fw[HRP_NUM_FIELDS] = {h->dof, 6, 3, 2, 1, h->nkpt * 3, h->nkpt * 3, h->nkpt * 3, h->nkpt * 2, h->nkpt * 2};
+  for (int f = 0; f < HRP_NUM_FIELDS; ++f) h->field_width[f] = fw[f];
+  build_specs(h.get());
+  *out = h.release();
+  return HRP_OK;
+}
+
+extern "C" void hrp_destroy(hrp_handle* h) {
+  if (!h) return;
+  for (auto& kv : h->plans) {
+    for (int i = 0; i < 2; ++i) if (kv.second->exec[i]) cudaGraphExecDestroy(kv.second->exec[i]);
+    if (kv.second->ws) cudaFree(kv.second->ws);
+  }
+  for (void* p : h->dev_allocs) cudaFree(p);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+  hrp_fk_destroy(h->fk);
+  delete h;
+}
+
+extern "C" int hrp_num_weights(const hrp_handle* h) { return h ? (int)h->specs.size() : 0; }
+extern "C" const char* hrp_weight_name(const hrp_handle* h, int i) {
+  return (h && i >= 0 && i < (int)h->specs.size()) ? h->specs[i].name.c_str() : nullptr;
+}
+extern "C" int hrp_weight_shape(const hrp_handle* h, int i, int64_t* shape, int* ndim) {
+  if (!h || i < 0 || i >= (int)h->specs.size() || !shape || !ndim) return fail(HRP_ERR_INVALID, "hrp_weight_shape: bad argument");
+  *ndim = (int)h->specs[i].shape.size();
+  for (int k = 0; k < *ndim; ++k) shape[k] = h->specs[i].shape[k];
+  return HRP_OK;
+}
+
+extern "C" int hrp_set_weight(hrp_handle* h, const char* name, const void* host_ptr, const int64_t* shape, int ndim, int dtype) {
+  if (!h || !name) return fail(HRP_ERR_INVALID, "hrp_set_weight: null argument");
+  if (h->finalized) return fail(HRP_ERR_STATE, "hrp_set_weight: weights already finalized");
+  auto it = h->spec_index.find(name);
+  if (it == h->spec_index.end()) return fail(HRP_ERR_WEIGHT, "hrp_set_weight: tensor '%s' is not part of this network", name);
+  const WeightSpec& sp = h->specs[it->second];
+  if (sp.optional) return HRP_OK;  // num_batches_tracked
+  if (dtype != HRP_F32) return fail(HRP_ERR_WEIGHT, "hrp_set_weight: '%s' must be float32", name);
+  if (!host_ptr) return fail(HRP_ERR_INVALID, "hrp_set_weight: null data for '%s'", name);
+  if (ndim != (int)sp.shape.size()) return fail(HRP_ERR_WEIGHT, "hrp_set_weight: '%s' has %d dims, expected %zu", name, ndim, sp.shape.size());
+  int64_t n = 1;
+  for (int k = 0; k < ndim; ++k) {
+    if (shape[k] != sp.shape[k]) return fail(HRP_ERR_WEIGHT, "hrp_set_weight: '%s' dim %d is %lld, expected %lld", name, k, (long long)shape[k], (long long)sp.shape[k]);
+    n *= shape[k];
+  }
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.data.assign(static_cast<const float*>(host_ptr), static_cast<const float*>(host_ptr) + n);
+  h->host[name] = std::move(t);
+  return HRP_OK;
+}
+
+extern "C" int hrp_finalize_weights(hrp_handle* h) {
+  if (!h) return fail(HRP_ERR_INVALID, "hrp_finalize_weights: null handle");
+  if (h->finalized) return fail(HRP_ERR_STATE, "hrp_finalize_weights: already finalized");
+  for (const WeightSpec& sp : h->specs)
+    if (!sp.optional && !h->host.count(sp.name)) return fail(HRP_ERR_WEIGHT, "hrp_finalize_weights: tensor '%s' was never set", sp.name.c_str());
+  HRP_CUDA(cudaSetDevice(h->device));
+  GraphBuilder gb{h};
+  const int st = gb.build();
+  if (st != HRP_OK) return st;
+  HRP_CUDA(cudaDeviceSynchronize());
+  h->host.clear();
+  HRP_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+  h->finalized = true;
+  return HRP_OK;
+}
+
+extern "C" int hrp_output_offsets(const hrp_handle* h, int B, int64_t* offsets) {
+  if (!h || !offsets || B <= 0) return fail(HRP_ERR_INVALID, "hrp_output_offsets: bad argument");
+  record_floats(h, B, offsets);
+  return HRP_OK;
+}
+
+extern "C" size_t hrp_workspace_bytes(hrp_handle* h, int B) {
+  if (!h || !h->finalized || B <= 0) return 0;
+  Plan* p = nullptr;
+  if (make_plan(h, B, &p) != HRP_OK) return 0;
+  return p->ws_bytes;
+}
+
+extern "C" int hrp_set_option(hrp_handle* h, const char* name, int64_t value) {
+  if (!h || !name) return fail(HRP_ERR_INVALID, "hrp_set_option: null argument");
+  if (std::strcmp(name, "cuda_graph") == 0) { h->use_graph = value != 0; return HRP_OK; }
+  return fail(HRP_ERR_INVALID, "hrp_set_option: unknown option '%s'", name);
+}
+
+extern "C" int64_t hrp_launch_count(const hrp_handle* h) { return h ? h->last_launches : 0; }
+
+extern "C" int hrp_forward(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
+                           int B, float* out, void* stream) {
+  HRP_TRY(check_forward_args(h, x_reg, x_root, k_value, Kmat, B, out));
+  HRP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* p = nullptr;
+  HRP_TRY(make_plan(h, B, &p));
+  if (!h->use_graph) return run_ops(h, p, IoPtrs{x_reg, x_root, k_value, Kmat, out}, st, nullptr);
+  // graph path: the graph reads/writes the plan's static staging buffers, so one instantiation serves every call
+  const int same = (x_reg == x_root) ? 1 : 0;
+  float* s_xreg = reinterpret_cast<float*>(p->ws + p->io_xreg);
+  float* s_xroot = same ? s_xreg : reinterpret_cast<float*>(p->ws + p->io_xroot);
+  float* s_kv = reinterpret_cast<float*>(p->ws + p->io_kv);
+  float* s_K = reinterpret_cast<float*>(p->ws + p->io_K);
+  float* s_out = reinterpret_cast<float*>(p->ws + p->io_out);
+  if (!p->exec[same]) {
+    cudaGraph_t g = nullptr;
+    HRP_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+    const int rs = run_ops(h, p, IoPtrs{s_xreg, s_xroot, s_kv, s_K, s_out}, h->capture_stream, nullptr);
+    cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &g);
+    if (rs != HRP_OK) { if (g) cudaGraphDestroy(g); return rs; }
+    if (ce != cudaSuccess) return fail(HRP_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&p->exec[same], g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) return fail(HRP_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ce));
+  }
+  const size_t img = (size_t)B * 3 * 256 * 256 * sizeof(float);
+  HRP_CUDA(cudaMemcpyAsync(s_xreg, x_reg, img, cudaMemcpyDeviceToDevice, st));
+  if (!same) HRP_CUDA(cudaMemcpyAsync(s_xroot, x_root, img, cudaMemcpyDeviceToDevice, st));
+  HRP_CUDA(cudaMemcpyAsync(s_kv, k_value, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  HRP_CUDA(cudaMemcpyAsync(s_K, Kmat, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  HRP_CUDA(cudaGraphLaunch(p->exec[same], st));
+  HRP_CUDA(cudaMemcpyAsync(out, s_out, (size_t)record_floats(h, B, nullptr) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return HRP_OK;
+}
+
+extern "C" int hrp_forward_profile(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value,
+                                   const float* Kmat, int B, float* out, float* ms_by_class, int64_t* launches_by_class,
+                                   double* flops_by_class, void* stream) {
+  HRP_TRY(check_forward_args(h, x_reg, x_root, k_value, Kmat, B, out));
+  if (!ms_by_class || !launches_by_class || !flops_by_class) return fail(HRP_ERR_INVALID, "hrp_forward_profile: null output");
+  HRP_CUDA(cudaSetDevice(h->device));
+  Plan* p = nullptr;
+  HRP_TRY(make_plan(h, B, &p));
+  for (int c = 0; c < HRP_NUM_CLASSES; ++c) { ms_by_class[c] = 0.f; launches_by_class[c] = 0; flops_by_class[c] = 0.0; }
+  Profile prof{ms_by_class, launches_by_class, flops_by_class, nullptr, nullptr};
+  HRP_CUDA(cudaEventCreate(&prof.e0));
+  HRP_CUDA(cudaEventCreate(&prof.e1));
+  const int rs = run_ops(h, p, IoPtrs{x_reg, x_root, k_value, Kmat, out}, (cudaStream_t)stream, &prof);
+  cudaEventDestroy(prof.e0);
+  cudaEventDestroy(prof.e1);
+  return rs;
+}
+
+extern "C" int hrp_debug_tensor(hrp_handle* h, const char* name, int B, float* dst_device, int64_t* numel, void* stream) {
+  if (!h || !name || !numel) return fail(HRP_ERR_INVALID, "hrp_debug_tensor: null argument");
+  auto it = h->debug.find(name);
+  if (it == h->debug.end()) return fail(HRP_ERR_INVALID, "hrp_debug_tensor: unknown tensor '%s' (xf, img_feat, logits)", name);
+  auto pit = h->plans.find(B);
+  if (pit == h->plans.end()) return fail(HRP_ERR_STATE, "hrp_debug_tensor: no forward has run for batch %d", B);
+  const TensorInfo& t = h->tensors[it->second];
+  *numel = t.elems * B;
+  if (dst_device) HRP_CUDA(cudaMemcpyAsync(dst_device, pit->second->ws + pit->second->off[it->second], (size_t)*numel * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return HRP_OK;
+}
+
+// single-layer entry point for parity tests (packs on the fly; synchronises; not a timed path)
+extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias, const float* residual, float* out,
+                               int B, int Hi, int Wi, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu,
+                               int precision, void* stream) {
+  if (!in || !weight_oihw || !out) return fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: null argument");
+  if (precision != HRP_PREC_FP32) return fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: precision %d not available in this build", precision);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nw = (size_t)Cout * Cin * KH * KW;
+  std::vector<float> w(nw), b(Cout, 0.f), wp(nw), bp(Cout);
+  HRP_CUDA(cudaMemcpyAsync(w.data(), weight_oihw, nw * 4, cudaMemcpyDeviceToHost, st));
+  if (bias) HRP_CUDA(cudaMemcpyAsync(b.data(), bias, (size_t)Cout * 4, cudaMemcpyDeviceToHost, st));
+  HRP_CUDA(cudaStreamSynchronize(st));
+  pack_conv_f32(w.data(), b.data(), nullptr, nullptr, nullptr, nullptr, Cout, Cin, KH, KW, wp.data(), bp.data());
+  float *dw = nullptr, *db = nullptr;
+  HRP_CUDA(cudaMalloc(&dw, nw * 4));
+  HRP_CUDA(cudaMalloc(&db, (size_t)Cout * 4));
+  HRP_CUDA(cudaMemcpyAsync(dw, wp.data(), nw * 4, cudaMemcpyHostToDevice, st));
+  HRP_CUDA(cudaMemcpyAsync(db, bp.data(), (size_t)Cout * 4, cudaMemcpyHostToDevice, st));
+  ConvArgs a{};
+  a.in = in; a.w = dw; a.bias = db; a.res = residual; a.out = out;
+  a.B = B; a.Hi = Hi; a.Wi = Wi; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.stride = stride; a.pad_h = a.pad_w = pad;
+  a.Ho = (Hi + 2 * pad - KH) / stride + 1; a.Wo = (Wi + 2 * pad - KW) / stride + 1;
+  a.out_sy = a.out_sx = 1; a.Ho_full = a.Ho; a.Wo_full = a.Wo; a.relu = relu; a.ld_out = Cout;
+  const int rs = conv_f32_launch(a, st);
+  cudaStreamSynchronize(st);
+  cudaFree(dw);
+  cudaFree(db);
+  return rs;
+}

@@ -1,0 +1,302 @@
+"""Host-side mirror of the reference model interface, backed by the CUDA library.
+
+`HoliRobPoseB200` is a drop-in for `RootNetwithRegInt` (lib/models/full_net.py:17-466) on the inference path:
+same constructor intent (robot type + the ctor-relevant config keys), `load_state_dict` with the reference's key names
+(optionally `module.`-prefixed, scripts/fullnet_test.py:193-198), `forward(x_reg, x_root, k_value, K)` returning the same
+8-tuple in the same order / shapes / dtype (fp32 on the inputs' CUDA device), plus the `forward(images, K)` dict
+convenience of BASELINE.json's north_star. PyTorch is used for device memory and streams only.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import arch, capi, consts, urdf
+
+UNSUPPORTED = {  # ctor variants of the reference that no shipped config enables -> explicit error
+    "reg_joint_map": False, "direct_reg_rot": False, "rot_iterative_matmul": False, "add_fc": False,
+    "multi_kp": False, "use_rpmg": False,
+}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class FkRobot:
+    """Drop-in for URDFRobot.get_keypoints / get_keypoints_root (+ projection) on CUDA tensors."""
+
+    def __init__(self, robot_type, urdf_text=None):
+        self.robot_type = robot_type
+        self.parsed, self.program = urdf.load_robot(robot_type, urdf_text)
+        self._struct, self._keep = capi.fk_program_struct(self.program)
+        h = C.c_void_p()
+        capi.check(capi.lib().hrp_fk_create(C.byref(self._struct), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                capi.lib().hrp_fk_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
+
+    def keypoints(self, q, rot6d, trans, K):
+        """q [N,dof], rot6d [N,6], trans [N,3], K [N,3,3] CUDA fp32 -> (xyz [N,nkpt,3], uv [N,nkpt,2])."""
+        n = q.shape[0]
+        for t, w in ((q, self.program.dof), (rot6d, 6), (trans, 3)):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape == (n, w)):
+                raise ValueError("FkRobot.keypoints: expected CUDA fp32 [N,%d], got %s %s" % (w, t.dtype, tuple(t.shape)))
+        if not (K.is_cuda and K.dtype == torch.float32 and K.shape == (n, 3, 3)):
+            raise ValueError("FkRobot.keypoints: K must be CUDA fp32 [N,3,3]")
+        q, rot6d, trans, K = (t.contiguous() for t in (q, rot6d, trans, K))
+        xyz = torch.empty(n, self.program.nkpt, 3, device=q.device, dtype=torch.float32)
+        uv = torch.empty(n, self.program.nkpt, 2, device=q.device, dtype=torch.float32)
+        st = torch.cuda.current_stream(q.device).cuda_stream
+        capi.check(capi.lib().hrp_fk_project(self._h, _ptr(q), _ptr(rot6d), _ptr(trans), _ptr(K), n, _ptr(xyz), _ptr(uv),
+                                             C.c_void_p(st)))
+        return xyz, uv
+
+
+def soft_argmax(heatmap, nkpt, K=None, root_z=None, depth_factor=1.3, image_size=256.0, rootid=0, fixroot=True):
+    """Drop-in for HeatmapIntegralPose.forward (lib/utils/integral.py:102-208).
+
+    heatmap [B, nkpt*D, H, W] CUDA fp32 (reference layout) -> (uvd [B,nkpt,3], xyz [B,nkpt,3] or None)."""
+    if not (heatmap.is_cuda and heatmap.dtype == torch.float32 and heatmap.dim() == 4):
+        raise ValueError("soft_argmax: heatmap must be CUDA fp32 [B, nkpt*D, H, W]")
+    B, CD, H, W = heatmap.shape
+    if nkpt <= 0 or CD % nkpt:
+        raise ValueError("soft_argmax: channel count %d is not a multiple of nkpt=%d" % (CD, nkpt))
+    D = CD // nkpt
+    heatmap = heatmap.contiguous()
+    uvd = torch.empty(B, nkpt, 3, device=heatmap.device, dtype=torch.float32)
+    xyz = None
+    kp = rp = C.c_void_p(0)
+    if K is not None:
+        K = K.contiguous().float()
+        root_z = root_z.contiguous().float().reshape(-1)
+        xyz = torch.empty(B, nkpt, 3, device=heatmap.device, dtype=torch.float32)
+        kp, rp = _ptr(K), _ptr(root_z)
+    L = capi.lib()
+    nbytes = L.hrp_softargmax3d_workspace(B, nkpt, D, H, W)
+    ws = torch.empty(max(nbytes, 16), device=heatmap.device, dtype=torch.uint8)
+    st = torch.cuda.current_stream(heatmap.device).cuda_stream
+    capi.check(L.hrp_softargmax3d(_ptr(heatmap), B, nkpt, D, H, W, kp, rp, depth_factor, image_size, rootid,
+                                  int(bool(fixroot)), _ptr(uvd), _ptr(xyz) if xyz is not None else C.c_void_p(0),
+                                  _ptr(ws), nbytes, C.c_void_p(st)))
+    return uvd, xyz
+
+
+def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, relu=False, precision="fp32"):
+    """Single conv through the library (layer-level parity tests). x NHWC, weight OIHW, CUDA fp32."""
+    B, Hi, Wi, Cin = x.shape
+    Cout, _, KH, KW = weight.shape
+    Ho, Wo = (Hi + 2 * pad - KH) // stride + 1, (Wi + 2 * pad - KW) // stride + 1
+    out = torch.empty(B, Ho, Wo, Cout, device=x.device, dtype=torch.float32)
+    st = torch.cuda.current_stream(x.device).cuda_stream
+    z = C.c_void_p(0)
+    capi.check(capi.lib().hrp_conv2d_nhwc(_ptr(x.contiguous()), _ptr(weight.contiguous()),
+                                          _ptr(bias.contiguous()) if bias is not None else z,
+                                          _ptr(residual.contiguous()) if residual is not None else z, _ptr(out),
+                                          B, Hi, Wi, Cin, Cout, KH, KW, stride, pad, int(relu), capi.PREC[precision],
+                                          C.c_void_p(st)))
+    return out
+
+
+class HoliRobPoseB200(torch.nn.Module):
+    """CUDA drop-in for RootNetwithRegInt (inference forward only)."""
+
+    def __init__(self, robot_type, cfg=None, device=None, precision="fp32", **kw):
+        super().__init__()
+        cfg = dict(cfg or {}, **kw)
+        if robot_type not in consts.ROBOTS:
+            raise ValueError("Robot type %s is not supported." % robot_type)       # full_net.py:55
+        for k, v in UNSUPPORTED.items():
+            if cfg.get(k, v) != v:
+                raise NotImplementedError("config %s=%r is not supported by the B200 path (shipped value: %r)" % (k, cfg[k], v))
+        if int(cfg.get("rotation_dim", 6)) != 6:
+            raise NotImplementedError("rotation_dim=%r: only the 6-D representation is supported" % cfg.get("rotation_dim"))
+        spec = consts.ROBOTS[robot_type]
+        self.robot_type = robot_type
+        self.backbone_name = cfg.get("backbone_name", "resnet50")
+        self.rootnet_backbone_name = cfg.get("rootnet_backbone_name", "hrnet32")
+        if self.backbone_name not in capi.BACKBONE:
+            raise NotImplementedError("backbone_name=%r (supported: resnet50, hrnet32)" % self.backbone_name)
+        if self.rootnet_backbone_name not in ("hrnet", "hrnet32"):
+            raise NotImplementedError("rootnet_backbone_name=%r (supported: hrnet32)" % self.rootnet_backbone_name)
+        if precision not in capi.PREC:
+            raise ValueError("precision must be one of %s" % list(capi.PREC))
+        self.precision = precision
+        self.n_iter = int(cfg.get("n_iter", consts.N_ITER))
+        self.image_size = float(cfg.get("other_image_size", consts.IMAGE_SIZE))
+        self.bbox_3d_shape = tuple(cfg.get("bbox_3d_shape", spec["bbox_3d"]))
+        self.reference_keypoint_id = int(cfg.get("reference_keypoint_id", spec["ref_kp"]))
+        self.fix_root = bool(cfg.get("fix_root", True))
+        self.dof, self.nkpt = spec["dof"], spec["nkpt"]
+        self.num_joints = self.nkpt
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cuda", 0)
+        self.device = torch.device(device)
+        parsed = urdf.Robot(open(consts.urdf_path(robot_type)).read())
+        self.program = urdf.compile_program(parsed, urdf.keypoint_frames(robot_type, parsed), self.reference_keypoint_id,
+                                            spec["joints"])
+        self._prog_struct, self._prog_keep = capi.fk_program_struct(self.program)
+        depth_factor = float(np.float32(self.bbox_3d_shape[2]) * np.float32(1e-3))       # integral.py:96-97
+        self._cfg = capi.Config(capi.BACKBONE[self.backbone_name], capi.PREC[precision], self.n_iter, int(self.fix_root),
+                                self.image_size, depth_factor)
+        h = C.c_void_p()
+        capi.check(capi.lib().hrp_create(C.byref(self._cfg), C.byref(self._prog_struct), self.device.index or 0, C.byref(h)))
+        self._h = h
+        self._finalized = False
+        self._out = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                capi.lib().hrp_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
+
+    # ---- weights ----------------------------------------------------------------------------------------------------
+    def expected_tensors(self):
+        L = capi.lib()
+        out = []
+        shape = (C.c_int64 * 4)()
+        nd = C.c_int()
+        for i in range(L.hrp_num_weights(self._h)):
+            capi.check(L.hrp_weight_shape(self._h, i, shape, C.byref(nd)))
+            out.append((L.hrp_weight_name(self._h, i).decode(), tuple(shape[k] for k in range(nd.value))))
+        return out
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Accepts a reference state dict (tensors or numpy arrays; optional `module.` prefix)."""
+        if self._finalized:
+            raise RuntimeError("weights are already loaded; build a new HoliRobPoseB200 to load another checkpoint")
+        L = capi.lib()
+        expected = dict(self.expected_tensors())
+        seen = set()
+        unexpected = []
+        for k, v in state_dict.items():
+            if k.startswith("module."):
+                k = k[len("module."):]
+            if k not in expected:
+                unexpected.append(k)
+                continue
+            if k.endswith("num_batches_tracked"):
+                seen.add(k)
+                continue
+            a = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            shape = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+            capi.check(L.hrp_set_weight(self._h, k.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim, 0))
+            seen.add(k)
+        missing = [k for k in expected if k not in seen and not k.endswith("num_batches_tracked")]
+        if strict and (missing or unexpected):
+            raise RuntimeError("load_state_dict: missing %s, unexpected %s" % (missing[:5], unexpected[:5]))
+        capi.check(L.hrp_finalize_weights(self._h))
+        self._finalized = True
+        return missing, unexpected
+
+    # ---- forward -----------------------------------------------------------------------------------------------------
+    def _record(self, B, device):
+        key = (B, device)
+        if key not in self._out:
+            offs = (C.c_int64 * (capi.NUM_FIELDS + 1))()
+            capi.check(capi.lib().hrp_output_offsets(self._h, B, offs))
+            self._out[key] = list(offs)
+        return self._out[key]
+
+    def forward_record(self, x_reg, x_root, k_value, K):
+        """Runs the network; returns (flat fp32 record tensor, field offsets)."""
+        if not self._finalized:
+            raise RuntimeError("forward before load_state_dict")
+        B = x_reg.shape[0]
+        for t, shp in ((x_reg, (B, 3, 256, 256)), (x_root, (B, 3, 256, 256)), (K, (B, 3, 3))):
+            if not t.is_cuda or tuple(t.shape) != shp:
+                raise ValueError("expected a CUDA tensor of shape %s, got %s on %s" % (shp, tuple(t.shape), t.device))
+        same = x_root is x_reg or x_root.data_ptr() == x_reg.data_ptr()
+        x_reg = x_reg.float().contiguous()                                   # full_net.py:265-266
+        x_root = x_reg if same else x_root.float().contiguous()
+        k_value = torch.as_tensor(k_value, device=x_reg.device).float().reshape(B).contiguous()
+        K = K.float().contiguous()
+        offs = self._record(B, x_reg.device)
+        rec = torch.empty(offs[-1], device=x_reg.device, dtype=torch.float32)
+        st = torch.cuda.current_stream(x_reg.device).cuda_stream
+        capi.check(capi.lib().hrp_forward(self._h, _ptr(x_reg), _ptr(x_root), _ptr(k_value), _ptr(K), B, _ptr(rec),
+                                          C.c_void_p(st)))
+        return rec, offs
+
+    def _fields(self, rec, offs, B):
+        w = (self.dof, 6, 3, 2, 1, self.nkpt * 3, self.nkpt * 3, self.nkpt * 3, self.nkpt * 2, self.nkpt * 2)
+        out = []
+        for f in range(capi.NUM_FIELDS):
+            t = rec[offs[f]:offs[f] + B * w[f]].view(B, w[f])
+            if f in (5, 6, 7):
+                t = t.view(B, self.nkpt, 3)
+            elif f in (8, 9):
+                t = t.view(B, self.nkpt, 2)
+            out.append(t)
+        return out
+
+    def forward(self, x_reg_input, x_root_input=None, k_value=None, K=None, init_pose=None, init_rot=None,
+                test_fps=False):
+        """Reference signature -> 8-tuple (full_net.py:262, 466). `model(images, K)` / `model(images, K=K)` -> dict."""
+        if init_pose is not None or init_rot is not None or test_fps:
+            raise NotImplementedError("init_pose / init_rot / test_fps are not supported by the B200 path")
+        if K is None and (k_value is None) and x_root_input is not None and x_root_input.dim() == 3:
+            return self.forward_dict(x_reg_input, x_root_input)              # model(images, K)
+        if x_root_input is None:
+            return self.forward_dict(x_reg_input, K, k_value)
+        B = x_reg_input.shape[0]
+        rec, offs = self.forward_record(x_reg_input, x_root_input, k_value, K)
+        f = self._fields(rec, offs, B)
+        return tuple(f[:8])
+
+    def forward_dict(self, images, K, k_value=None):
+        """north_star convenience: dict of 2-D/3-D keypoints, joint angles, root depth and camera-frame pose."""
+        B = images.shape[0]
+        if k_value is None:                                                  # scripts/real_test.py:285-289, full-frame bbox
+            k_value = torch.sqrt(K[:, 0, 0] * K[:, 1, 1] * 1000.0 * 1000.0 / (self.image_size * self.image_size))
+        rec, offs = self.forward_record(images, images, k_value, K)
+        return dict(zip(capi.FIELD_NAMES, self._fields(rec, offs, B)))
+
+    def launch_count(self):
+        return int(capi.lib().hrp_launch_count(self._h))
+
+    def set_option(self, name, value):
+        capi.check(capi.lib().hrp_set_option(self._h, name.encode(), int(value)))
+
+    def debug_tensor(self, name, B):
+        n = C.c_int64()
+        L = capi.lib()
+        capi.check(L.hrp_debug_tensor(self._h, name.encode(), B, C.c_void_p(0), C.byref(n), C.c_void_p(0)))
+        t = torch.empty(n.value, device=self.device, dtype=torch.float32)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        capi.check(L.hrp_debug_tensor(self._h, name.encode(), B, _ptr(t), C.byref(n), C.c_void_p(st)))
+        return t
+
+    def profile(self, x_reg, x_root, k_value, K):
+        """Per-kernel-class device time of one un-graphed forward (CUDA events around every launch)."""
+        B = x_reg.shape[0]
+        offs = self._record(B, x_reg.device)
+        rec = torch.empty(offs[-1], device=x_reg.device, dtype=torch.float32)
+        ms = (C.c_float * capi.NUM_CLASSES)()
+        ln = (C.c_int64 * capi.NUM_CLASSES)()
+        fl = (C.c_double * capi.NUM_CLASSES)()
+        st = torch.cuda.current_stream(x_reg.device).cuda_stream
+        k_value = torch.as_tensor(k_value, device=x_reg.device).float().reshape(B).contiguous()
+        capi.check(capi.lib().hrp_forward_profile(self._h, _ptr(x_reg.contiguous()), _ptr(x_root.contiguous()), _ptr(k_value),
+                                                  _ptr(K.contiguous()), B, _ptr(rec), ms, ln, fl, C.c_void_p(st)))
+        return {capi.CLASS_NAMES[i]: dict(ms=ms[i], launches=ln[i], flops=fl[i]) for i in range(capi.NUM_CLASSES)}
+
+
+def get_rootNetwithRegInt_model(init_param_dict, args, device=None, precision="fp32"):
+    """Factory with the reference's name and arguments (full_net.py:470-505); weights are loaded by the caller."""
+    cfg = dict(args) if isinstance(args, dict) else {k: getattr(args, k) for k in dir(args) if not k.startswith("_")}
+    keys = ("backbone_name", "rootnet_backbone_name", "n_iter", "rotation_dim", "reg_joint_map", "direct_reg_rot",
+            "rot_iterative_matmul", "add_fc", "multi_kp", "use_rpmg", "fix_root", "bbox_3d_shape",
+            "reference_keypoint_id", "other_image_size")
+    return HoliRobPoseB200(init_param_dict["robot_type"], {k: cfg[k] for k in keys if k in cfg}, device, precision)

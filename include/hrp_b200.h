@@ -1,0 +1,176 @@
+/*
+ * hrp_b200.h -- C ABI of libhrp_b200.so: HoliRobPose full-network inference forward on NVIDIA B200 (sm_100a).
+ *
+ * The reference (Grz684/Holistic-Robot-Pose-Estimation-Study) has no FFI layer: its boundary for this path is the
+ * Python call  model(x_reg, x_root, k_value, K)  on an nn.Module (lib/models/full_net.py:262-466, call sites
+ * lib/core/function.py:133-141, scripts/test.py:161, scripts/real_test.py:295) followed by
+ * point_projection_from_3d_tensor(K, xyz) (lib/utils/transforms.py:17-21). This header is the FFI that boundary binds
+ * to when the path is replaced; INTEGRATION.md shows the ctypes stub on the reference side.
+ *
+ * Conventions: plain C, no torch types. Every function returns HRP_OK (0) or a negative hrp_status; the message is in
+ * hrp_last_error() (thread-local). Device pointers are caller-owned and must live on the handle's device; work is
+ * enqueued asynchronously on the caller's stream and no call synchronises the host (the reference's device->host copy
+ * at full_net.py:342 does not exist here). A handle is not re-entrant; use one handle per (device, precision).
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef HRP_B200_H_
+#define HRP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  HRP_OK = 0,
+  HRP_ERR_INVALID = -1,     /* bad argument / unsupported configuration (never a silent fallback) */
+  HRP_ERR_CUDA = -2,        /* CUDA runtime/driver error */
+  HRP_ERR_STATE = -3,       /* call order violated (e.g. forward before finalize) */
+  HRP_ERR_WEIGHT = -4,      /* unknown / missing / mis-shaped tensor */
+  HRP_ERR_NOMEM = -5
+} hrp_status;
+
+typedef enum { HRP_F32 = 0, HRP_I64 = 1 } hrp_dtype;
+
+/* Arithmetic of the conv / linear contractions. Everything else (softmax, kinematics, heads' epilogues) is fp32. */
+typedef enum {
+  HRP_PREC_FP32 = 0,        /* fp32 FFMA implicit GEMM: bit-faithful parity mode */
+  HRP_PREC_TF32 = 1,        /* tcgen05 kind::tf32, operands rounded to nearest TF32, fp32 accumulate in TMEM */
+  HRP_PREC_BF16 = 2         /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+} hrp_precision;
+
+typedef enum { HRP_BACKBONE_RESNET50 = 0, HRP_BACKBONE_HRNET32 = 1 } hrp_backbone;
+
+/* ---- kinematic program: compiled form of a URDF (see holistic-robot-pose-estimation-study_b200/urdf.py) ----------
+ * Replaces URDFRobot.get_keypoints / get_keypoints_root / get_TWL (lib/utils/urdf_robot.py:95-135,193-223) and
+ * URDF.link_fk_batch (lib/utils/urdfpytorch/urdf.py:3064-3167). */
+#define HRP_FK_MAX_STEPS 32
+#define HRP_FK_MAX_KP 32
+#define HRP_FK_MAX_SLOTS 8
+#define HRP_FK_PARENT_BASE (-1)
+#define HRP_FK_PARENT_PREV (-2)
+
+typedef struct {
+  int32_t dof;               /* columns of the joint-configuration matrix */
+  int32_t nkpt;              /* keypoints per pose */
+  int32_t n_steps;           /* movable joints on some keypoint path, chain-contiguous order */
+  int32_t n_slots;           /* saved frames needed by branching trees */
+  int32_t root_kp;           /* 0: keypoints in the base frame; >0: re-root at that keypoint's link frame */
+  int32_t root_step;         /* step whose frame carries the root link (-1: base) */
+  const int32_t* step_type;  /* 1 revolute, 2 prismatic */
+  const int32_t* step_parent;/* HRP_FK_PARENT_BASE, HRP_FK_PARENT_PREV or a slot index */
+  const int32_t* step_save;  /* slot to save this step's frame into, or -1 */
+  const int32_t* step_q;     /* configuration column */
+  const float* step_mul;     /* mimic: q' = mul*q + off */
+  const float* step_off;
+  const float* step_origin;  /* n_steps x 12: parent->joint frame (fixed joints folded), row-major 3x4 */
+  const float* step_axis;    /* n_steps x 3 */
+  const int32_t* kp_step;    /* nkpt, ascending; -1 = base frame */
+  const int32_t* kp_index;   /* output keypoint index */
+  const float* kp_offset;    /* nkpt x 3, in the step frame */
+  const float* root_fixed;   /* 12: step frame -> root link frame */
+} hrp_fk_program;
+
+typedef struct hrp_fk hrp_fk;
+
+int hrp_fk_create(const hrp_fk_program* prog, hrp_fk** out);
+void hrp_fk_destroy(hrp_fk* fk);
+
+/* Batched FK + pinhole projection, one pose per thread.
+ * q [N,dof], rot6d [N,6] (first two ROWS of R, lib/utils/geometries.py:100-132), trans [N,3], Kmat [N,3,3] row-major
+ * -> xyz [N,nkpt,3] (metres, camera frame), uv [N,nkpt,2] (pixels; may be NULL). Replaces urdf_robot.py:95-118 /
+ * 193-223 + transforms.py:17-21. All fp32 device pointers. */
+int hrp_fk_project(const hrp_fk* fk, const float* q, const float* rot6d, const float* trans, const float* Kmat,
+                   int64_t N, float* xyz, float* uv, void* stream);
+
+/* ---- heatmap soft-argmax (integral layer) --------------------------------------------------------------------------
+ * hm [B, K*D, H, W] fp32 logits in the reference layout (channel = k*D + d, lib/utils/integral.py:122,170);
+ * softmax over D*H*W per (b,k), marginal first moments, /size - 0.5, fixroot, then uvd_to_xyz
+ * (lib/utils/transforms.py:33-82) with the inverse pinhole of integral.py:56-73.
+ * Kmat [B,3,3], root_z [B] absolute root depth in metres. uvd [B,K,3]; xyz [B,K,3] (may be NULL, then Kmat/root_z
+ * may be NULL). workspace: hrp_softargmax3d_workspace() bytes of device scratch. */
+size_t hrp_softargmax3d_workspace(int B, int K, int D, int H, int W);
+int hrp_softargmax3d(const float* hm, int B, int K, int D, int H, int W, const float* Kmat, const float* root_z,
+                     float depth_factor, float image_size, int rootid, int fixroot, float* uvd, float* xyz,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- single convolution (layer-level parity tests and micro-benchmarks) ----------------------------------------------
+ * in NHWC [B,Hi,Wi,Cin] fp32; weight in the reference layout OIHW [Cout,Cin,KH,KW] fp32 (packed internally, not on a
+ * timed path); bias [Cout] or NULL; residual NHWC [B,Ho,Wo,Cout] or NULL; out NHWC [B,Ho,Wo,Cout]. All device. */
+int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias, const float* residual, float* out,
+                    int B, int Hi, int Wi, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu,
+                    int precision, void* stream);
+
+/* ---- full network ------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t backbone;          /* hrp_backbone: keypoint-branch backbone; the DepthNet backbone is always HRNet-W32 */
+  int32_t precision;         /* hrp_precision */
+  int32_t n_iter;            /* refinement iterations of the pose / rotation heads (shipped: 4) */
+  int32_t fix_root;          /* zero the root keypoint's d before back-projection (shipped: 1) */
+  float image_size;          /* 256 */
+  float depth_factor;        /* bbox_3d_shape[2] * 1e-3 (shipped: 1.3) */
+} hrp_config;
+
+typedef struct hrp_handle hrp_handle;
+
+/* Replaces get_rootNetwithRegInt_model / RootNetwithRegInt.__init__ (full_net.py:37-212, 470-505). */
+int hrp_create(const hrp_config* cfg, const hrp_fk_program* robot, int device, hrp_handle** out);
+void hrp_destroy(hrp_handle* h);
+
+/* The tensors the handle needs, in the reference's state-dict naming. */
+int hrp_num_weights(const hrp_handle* h);
+const char* hrp_weight_name(const hrp_handle* h, int i);
+int hrp_weight_shape(const hrp_handle* h, int i, int64_t* shape /*[4]*/, int* ndim);
+
+/* Replaces load_state_dict: hand over one HOST tensor (copied; BN folding / repacking happens in finalize).
+ * Unknown names -> HRP_ERR_WEIGHT; `num_batches_tracked` tensors are accepted and ignored. */
+int hrp_set_weight(hrp_handle* h, const char* name, const void* host_ptr, const int64_t* shape, int ndim, int dtype);
+int hrp_finalize_weights(hrp_handle* h);
+
+/* Output record: one flat fp32 device buffer, struct-of-arrays. Field f occupies
+ * [offsets[f], offsets[f+1]) floats; offsets has HRP_NUM_FIELDS+1 entries. */
+enum {
+  HRP_F_POSE = 0,      /* [B,dof]    joint angles                      full_net.py:394 */
+  HRP_F_ROT = 1,       /* [B,6]      rot6d                             full_net.py:444 */
+  HRP_F_TRANS = 2,     /* [B,3]      root translation                  full_net.py:367 */
+  HRP_F_ROOT_UV = 3,   /* [B,2]      root keypoint pixel               full_net.py:360 */
+  HRP_F_DEPTH = 4,     /* [B,1]      root depth (m)                    full_net.py:334-336 */
+  HRP_F_UVD = 5,       /* [B,nkpt,3]                                   integral.py:146-151 */
+  HRP_F_XYZ_INT = 6,   /* [B,nkpt,3] integral keypoints                integral.py:157 */
+  HRP_F_XYZ_FK = 7,    /* [B,nkpt,3] forward-kinematics keypoints      full_net.py:447-450 */
+  HRP_F_KP2D_INT = 8,  /* [B,nkpt,2] projection of XYZ_INT             transforms.py:17-21 */
+  HRP_F_KP2D_FK = 9,   /* [B,nkpt,2] projection of XYZ_FK */
+  HRP_NUM_FIELDS = 10
+};
+int hrp_output_offsets(const hrp_handle* h, int B, int64_t* offsets /*[HRP_NUM_FIELDS+1]*/);
+
+/* Device scratch the handle owns for batch B (allocated on first use, outside any timed region after warm-up). */
+size_t hrp_workspace_bytes(hrp_handle* h, int B);
+
+/* The forward: x_reg, x_root NCHW fp32 [B,3,256,256] in [0,1]; k_value [B]; Kmat [B,3,3]; out: flat record.
+ * Replaces RootNetwithRegInt.forward (full_net.py:262-466) + both caller-side projections (function.py:140-141). */
+int hrp_forward(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
+                int B, float* out, void* stream);
+
+/* Options: "cuda_graph" (0/1, default 1). Unknown option -> HRP_ERR_INVALID. */
+int hrp_set_option(hrp_handle* h, const char* name, int64_t value);
+
+/* Introspection for the bench / tests. */
+int64_t hrp_launch_count(const hrp_handle* h);            /* kernels enqueued by the most recent hrp_forward */
+int hrp_debug_tensor(hrp_handle* h, const char* name, int B, float* dst_device, int64_t* numel, void* stream);
+/* Per-kernel-class device time of one un-graphed forward (CUDA events around every launch; for profiling only).
+ * classes: 0 conv-tensor, 1 conv-fp32, 2 stem, 3 pool/fuse elementwise, 4 heads, 5 softargmax, 6 fk. */
+#define HRP_NUM_CLASSES 7
+int hrp_forward_profile(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value,
+                        const float* Kmat, int B, float* out, float* ms_by_class, int64_t* launches_by_class,
+                        double* flops_by_class, void* stream);
+
+const char* hrp_last_error(void);
+const char* hrp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRP_B200_H_ */

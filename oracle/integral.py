@@ -20,17 +20,27 @@ def inverse_intrinsics(K):
     return inv
 
 
-def soft_argmax_uvd(logits, nkpt, rootid, fixroot, depth_dim=64, hm=64):
-    """[B, nkpt*D, H, W] -> uvd [B, nkpt, 3] in [-0.5, 0.5]; integral.py:116-151."""
+def soft_argmax_uvd(logits, nkpt, rootid, fixroot, depth_dim=64, hm=64, path="resnet50"):
+    """[B, nkpt*D, H, W] -> uvd [B, nkpt, 3] in [-0.5, 0.5].
+
+    path="resnet50": integral.py:116-151 (softmax, explicit re-normalisation by the sum, marginal * arange, sum).
+    path="hrnet32":  integral.py:166-190 (softmax, NO re-normalisation, marginal.matmul(arange)). The two differ by the
+    fp32 rounding of a 262 144-term softmax denominator (~1e-4 in uvd on peaked heatmaps)."""
     B = logits.shape[0]
     p = F.softmax(logits.reshape(B, nkpt, -1), 2)
-    p = p / p.sum(2, keepdim=True)
-    p = p.reshape(B, nkpt, depth_dim, hm, hm)
     r = torch.arange(hm, dtype=torch.float32)
-    x = (p.sum((2, 3)) * r).sum(2, keepdim=True) / float(hm) - 0.5
-    y = (p.sum((2, 4)) * r).sum(2, keepdim=True) / float(hm) - 0.5
-    z = (p.sum((3, 4)) * r).sum(2, keepdim=True) / float(depth_dim) - 0.5
-    uvd = torch.cat((x, y, z), 2)
+    if path == "resnet50":
+        p = p / p.sum(2, keepdim=True)
+        p = p.reshape(B, nkpt, depth_dim, hm, hm)
+        x = (p.sum((2, 3)) * r).sum(2, keepdim=True)
+        y = (p.sum((2, 4)) * r).sum(2, keepdim=True)
+        z = (p.sum((3, 4)) * r).sum(2, keepdim=True)
+    else:
+        p = p.reshape(B, nkpt, depth_dim, hm, hm)
+        x = p.sum((2, 3)).matmul(r.unsqueeze(-1))
+        y = p.sum((2, 4)).matmul(r.unsqueeze(-1))
+        z = p.sum((3, 4)).matmul(r.unsqueeze(-1))
+    uvd = torch.cat((x / float(hm) - 0.5, y / float(hm) - 0.5, z / float(depth_dim) - 0.5), 2)
     if fixroot:
         uvd[:, rootid, 2] = 0.0
     return uvd

@@ -61,7 +61,7 @@ class OracleModel:
             logits = network.deconv_head(x_out, sd, calib)
         else:
             logits, xf = network.hrnet_w32(x_reg, sd, "reg_backbone.", True, calib)
-        uvd = integral.soft_argmax_uvd(logits, self.nkpt, self.ref, self.fix_root)
+        uvd = integral.soft_argmax_uvd(logits, self.nkpt, self.ref, self.fix_root, path=self.backbone)
         xyz_int = integral.uvd_to_xyz(uvd, K, depth[:, 0], self.image_size, self.depth_factor)
         root_uv = (uvd[:, self.ref, :2] + 0.5) * self.image_size
         trans = integral.uvz_to_xyz(root_uv, depth, K)

@@ -1,0 +1,83 @@
+"""CPU: the oracle port reproduces the reference's own outputs (tests/golden/*, made by oracle/refrun/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from hrp_b200 import consts, synth
+from oracle import integral, kinematics
+
+import helpers
+
+
+@pytest.mark.parametrize("robot", ["panda", "kuka", "baxter"])
+def test_fk_matches_reference(robot):
+    g = helpers.load_golden("fk_%s.npz" % robot)
+    seed, n, root = (int(v) for v in g["meta"])
+    q, rot, tr, K = synth.make_fk_inputs(robot, n, seed)
+    om, _ = helpers.oracle_for(robot, "resnet50")
+    assert om.actuated_names == consts.ROBOTS[robot]["joints"]
+    assert [l for l, _ in om.kp_frames] == [str(s) for s in g["link_names"]]
+    np.testing.assert_allclose(np.stack([o for _, o in om.kp_frames]), g["offsets"], atol=1e-7)
+    xyz = kinematics.keypoints(om.kin, om.kp_frames, q, rot, tr, root)
+    assert helpers.maxdiff(xyz, g["xyz"]) < 2e-6
+    xyz0 = kinematics.keypoints(om.kin, om.kp_frames, q, rot, tr, 0)
+    assert helpers.maxdiff(xyz0, g["xyz_base_rooted"]) < 2e-6
+    uv = integral.project(torch.from_numpy(K), torch.from_numpy(xyz)).numpy()
+    ok = np.abs(g["xyz"][..., 2]) > 0.05          # projection is ill-conditioned as z -> 0
+    assert np.max(np.abs(uv - g["uv"])[ok]) < 2e-2
+
+
+@pytest.mark.parametrize("robot", ["panda", "kuka"])
+def test_fk_limb_lengths_known_answer(robot):
+    """In-tree known answers: lib/dataset/const.py:108-124."""
+    q, rot, tr, _ = synth.make_fk_inputs(robot, 64, 5)
+    om, _ = helpers.oracle_for(robot, "resnet50")
+    xyz = kinematics.keypoints(om.kin, om.kp_frames, q, rot, tr, om.ref)
+    d = np.linalg.norm(xyz[:, 1:] - xyz[:, :-1], axis=2)
+    np.testing.assert_allclose(d, np.broadcast_to(consts.LIMB_LENGTH[robot], d.shape), atol=2e-5)
+
+
+def test_rot6d_identity_known_answer():
+    """rot6d(I) = [1,0,0,0,1,0] (full_net.py:205) maps back to the identity."""
+    R = kinematics.rot6d_to_rotmat(np.asarray([consts.INIT_ROT6D], np.float32))
+    np.testing.assert_allclose(R[0], np.eye(3), atol=0)
+
+
+@pytest.mark.parametrize("case", ["resnet50_k7_blobs", "resnet50_k7_extreme", "resnet50_k17_noise",
+                                  "hrnet32_k8_blobs", "hrnet32_k17_extreme"])
+def test_softargmax_matches_reference(case):
+    g = helpers.load_golden("softargmax_%s.npz" % case)
+    seed, B, nkpt = (int(v) for v in g["meta"])
+    mode = case.split("_")[-1]
+    hm = torch.from_numpy(synth.make_heatmaps(B, nkpt, seed, mode))
+    K, _ = synth.make_camera(B, seed)
+    uvd = integral.soft_argmax_uvd(hm, nkpt, 3, True, path=case.split("_")[0])
+    xyz = integral.uvd_to_xyz(uvd, torch.from_numpy(K), torch.from_numpy(g["root_z"]), 256.0, 1.3)
+    assert helpers.maxdiff(uvd, g["uvd"]) < 2e-6
+    assert helpers.maxdiff(xyz, g["xyz"]) < 5e-6
+
+
+@pytest.mark.parametrize("robot,backbone", helpers.FULLNET_CASES)
+def test_fullnet_matches_reference(robot, backbone):
+    g = helpers.load_golden("fullnet_%s_%s.npz" % (robot, backbone))
+    wseed, seed, B = (int(v) for v in g["meta"])
+    om, _ = helpers.oracle_for(robot, backbone, wseed)
+    img, K, kv = helpers.inputs(B, seed)
+    trace = {}
+    out = om.forward(img, img, kv, K, trace=trace)
+    names = ["joint_angles", "rot6d", "trans", "root_uv", "root_depth", "uvd", "kp3d_int", "kp3d_fk"]
+    res = dict(zip(names, out))
+    res["kp2d_int"] = integral.project(K, res["kp3d_int"])
+    res["kp2d_fk"] = integral.project(K, res["kp3d_fk"])
+    tol = dict(joint_angles=1e-5, rot6d=1e-5, trans=1e-5, root_uv=1e-3, root_depth=1e-5, uvd=1e-5, kp3d_int=1e-5,
+               kp3d_fk=1e-5, kp2d_int=5e-3, kp2d_fk=5e-3)
+    for k, t in tol.items():
+        assert tuple(res[k].shape) == g[k].shape, k
+        assert helpers.maxdiff(res[k], g[k]) < t, (k, helpers.maxdiff(res[k], g[k]))
+    s = (37, 5, 7)
+    assert helpers.maxdiff(trace["xf"], g["probe_xf"]) < 1e-4
+    assert helpers.maxdiff(trace["img_feat"], g["probe_img_feat"]) < 1e-4
+    assert helpers.maxdiff(trace["logits"][:, ::s[0], ::s[1], ::s[2]], g["probe_logits_sample"]) < 1e-3
+    # the fixture is non-trivial: peaked-but-not-one-hot heatmaps, metre-scale depths, radians-scale angles
+    assert 1.0 < float(g["probe_logits_std"]) < 5.0
+    assert 0.3 < float(np.abs(g["root_depth"]).max()) < 10.0
