@@ -325,8 +325,10 @@ extern "C" void hrp_fk_destroy(hrp_fk* fk) { delete fk; }
 extern "C" int hrp_fk_project(const hrp_fk* fk, const float* q, const float* rot6d, const float* trans,
                               const float* Kmat, int64_t N, float* xyz, float* uv, void* stream) {
   using namespace hrp;
-  if (!fk || !q || !rot6d || !trans || !Kmat || !xyz) return fail(HRP_ERR_INVALID, "hrp_fk_project: null argument");
+  if (!fk) return fail(HRP_ERR_INVALID, "hrp_fk_project: null handle");
   if (N < 0) return fail(HRP_ERR_INVALID, "hrp_fk_project: negative N");
+  if (N == 0) return HRP_OK;   // empty batch: nothing to do, pointers may be null
+  if (!q || !rot6d || !trans || !Kmat || !xyz) return fail(HRP_ERR_INVALID, "hrp_fk_project: null argument");
   if (fk->smem > 48 * 1024)
     HRP_CUDA(cudaFuncSetAttribute(fk_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk->smem));
   return fk_launch(fk, q, rot6d, trans, Kmat, N, xyz, uv, (cudaStream_t)stream);
