@@ -183,7 +183,7 @@ int conv_f32_launch(const ConvArgs& a, cudaStream_t s) {
 // ---- stem: Cin = 3 straight from the NCHW input image --------------------------------------------------------------------
 // HRnet.py:500-502 (3x3 s2 p1) and Resnet.py:58-60 (7x7 s2 p3). K = 27 / 147 is too thin for a tensor-core tile; the
 // layer is 0.06 / 0.31 GFLOP per frame. 64 pixels x 4 channel groups per CTA, weights broadcast from shared memory.
-template <typename OutT>
+template <typename OutT, bool ROUND_TF32>
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                  OutT* __restrict__ out, int B, int Hi, int Wi, int Ho, int Wo, int KH, int KW, int pad) {
@@ -226,21 +226,24 @@ stem_conv_kernel(const float* __restrict__ in, const float* __restrict__ w, cons
   OutT* op = out + (size_t)pix * 64 + g * 16;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const float v = fmaxf(acc[j], 0.f);
+    float v = fmaxf(acc[j], 0.f);
+    if constexpr (ROUND_TF32) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
     if constexpr (sizeof(OutT) == 4) op[j] = v; else op[j] = __float2bfloat16_rn(v);
   }
 }
 
 int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, void* out, int B, int Hi, int Wi,
-                     int Ho, int Wo, int KH, int KW, int pad, int out_bf16, cudaStream_t s) {
+                     int Ho, int Wo, int KH, int KW, int pad, int out_mode, cudaStream_t s) {
   const long long total = (long long)B * Ho * Wo;
   if (total <= 0) return HRP_OK;
   const size_t smem = (size_t)3 * KH * KW * 64 * sizeof(float);
   const unsigned blocks = (unsigned)ceil_div64(total, 64);
-  if (out_bf16) {
-    stem_conv_kernel<__nv_bfloat16><<<blocks, 256, smem, s>>>(in_nchw, w, bias, static_cast<__nv_bfloat16*>(out), B, Hi, Wi, Ho, Wo, KH, KW, pad);
+  if (out_mode == 1) {
+    stem_conv_kernel<__nv_bfloat16, false><<<blocks, 256, smem, s>>>(in_nchw, w, bias, static_cast<__nv_bfloat16*>(out), B, Hi, Wi, Ho, Wo, KH, KW, pad);
+  } else if (out_mode == 2) {
+    stem_conv_kernel<float, true><<<blocks, 256, smem, s>>>(in_nchw, w, bias, static_cast<float*>(out), B, Hi, Wi, Ho, Wo, KH, KW, pad);
   } else {
-    stem_conv_kernel<float><<<blocks, 256, smem, s>>>(in_nchw, w, bias, static_cast<float*>(out), B, Hi, Wi, Ho, Wo, KH, KW, pad);
+    stem_conv_kernel<float, false><<<blocks, 256, smem, s>>>(in_nchw, w, bias, static_cast<float*>(out), B, Hi, Wi, Ho, Wo, KH, KW, pad);
   }
   HRP_CHECK_LAUNCH("stem_conv_kernel");
   return HRP_OK;
@@ -335,6 +338,13 @@ __global__ void fuse_sum_kernel(const FuseArgs a) {
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   if (a.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+  if (a.round_tf32) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(acc.x)); acc.x = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(acc.y)); acc.y = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(acc.z)); acc.z = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(acc.w)); acc.w = __uint_as_float(r);
+  }
   Vec4<T>::st(static_cast<T*>(a.out) + o, acc);
 }
 

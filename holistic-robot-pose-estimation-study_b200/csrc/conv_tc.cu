@@ -1,0 +1,459 @@
+// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (kind::f16 with bf16 operands, or kind::tf32) with the
+// accumulator in TMEM, weights streamed by the TMA bulk-copy engine, activations gathered (im2col on the fly) with
+// cp.async straight into the 128-byte-swizzled K-major operand layout the MMA reads.
+//
+// Replaces every nn.Conv2d / nn.ConvTranspose2d (+ folded BatchNorm2d, + residual add, + ReLU) the reference runs in
+// the two backbones and the deconv head (lib/models/backbones/HRnet.py:28-98,247-265,499-570; Resnet.py:57-139;
+// lib/models/full_net.py:214-238,353-355) in the HRP_PREC_BF16 / HRP_PREC_TF32 families.
+//
+// GEMM view (same ConvArgs descriptor as the fp32 family): M = B*Ho*Wo output pixels, N = Cout, K = KH*KW*Cin with
+// k = (r*KW + s)*Cin + c. One CTA computes a 128 x BLOCK_N tile:
+//   warps 0-3  producers: thread t owns tile row t (one output pixel); per k-block it issues eight 16-byte cp.async
+//              (zero-filled outside the image) into row t of the A stage, XOR-swizzled; then they become the epilogue
+//              warps (warp w reads TMEM lanes 32w..32w+31): + bias, + residual, ReLU, convert, store.
+//   warp 4     allocates TMEM, then one elected lane issues the tcgen05.mma stream and commits stages back.
+//   warp 5     one lane streams pre-swizzled weight tiles with cp.async.bulk (mbarrier complete_tx).
+// Stages hand over through mbarriers: full[s] (128 producer arrivals + 1 expect_tx arrival), empty[s] (tcgen05.commit).
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+
+namespace hrp {
+namespace {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_ROW_BYTES = 128;                          // one swizzle-128B row of K
+constexpr int TC_A_STAGE = TC_BLOCK_M * TC_ROW_BYTES;      // 16 KB
+constexpr int TC_PRODUCERS = 128;
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 6;
+
+struct TcParams {
+  ConvArgs a;
+  int M;             // B*Ho*Wo
+  int Ktot;          // KH*KW*Cin (elements)
+  int num_kb;        // ceil(Ktot / elements per 128-byte row)
+  int block_n;       // multiple of 16, <= 256, divides Cout
+  int stages;
+  int lag;           // cp.async groups kept in flight per producer thread (< stages)
+  int tmem_cols;     // power of two >= max(32, block_n)
+  int out_f32;       // NHWC output element type: 1 fp32, 0 the activation type of the family
+  int round_tf32;    // round fp32 NHWC outputs to TF32 (nearest, ties away) so the next MMA sees exact operands
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(ignored)=1 | SBO = 1024 B
+// (one 8-row group) | version 1 | layout 2. Stepping K inside the 128-byte row adds bytes>>4 to the start field.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ float round_tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------------------------
+template <bool TF32>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const TcParams p) {
+  constexpr int ESZ = TF32 ? 4 : 2;
+  constexpr int KB = TC_ROW_BYTES / ESZ;     // K elements per k-block (64 bf16 / 32 tf32)
+  constexpr int HALF = KB / 2;               // elements per 64-byte half row (4 chunks of 16 B)
+  constexpr int UK = 32 / ESZ;               // K elements per tcgen05.mma (16 bf16 / 8 tf32)
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int S = p.stages;
+  const int b_stage = p.block_n * TC_ROW_BYTES;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + (uint32_t)S * TC_A_STAGE;
+  const uint32_t sBar = sB + (uint32_t)S * b_stage;       // full[S], empty[S], tmem_full, tmem_ptr
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8u * S, bar_acc = sBar + 16u * S, tmem_slot = bar_acc + 8u;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const ConvArgs& a = p.a;
+  const int m0 = blockIdx.x * TC_BLOCK_M, n0 = blockIdx.y * p.block_n;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8u * s, TC_PRODUCERS + 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    // ===== producers: im2col gather of tile row `tid` ===============================================================
+    const int m = m0 + tid;
+    const bool row_ok = m < p.M;
+    const int mm = row_ok ? m : 0;
+    const int ox = mm % a.Wo, t1 = mm / a.Wo, oy = t1 % a.Ho, b = t1 / a.Ho;
+    const int iy0 = oy * a.stride - a.pad_h, ix0 = ox * a.stride - a.pad_w;
+    const uint8_t* img = static_cast<const uint8_t*>(a.in) + (size_t)b * a.Hi * a.Wi * a.Cin * ESZ;
+    const uint32_t row_off = (uint32_t)tid * TC_ROW_BYTES;
+    const uint32_t sw = (uint32_t)(tid & 7);
+    int c = 0, fr = 0, fs = 0, k = 0;                       // running (channel, filter row, filter col, k) of the next half row
+    const int lag = p.lag;
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int s = kb % S;
+      if (kb >= S) mbar_wait(bar_empty + 8u * s, ((kb / S) & 1) ^ 1);
+      const uint32_t dst_row = sA + (uint32_t)s * TC_A_STAGE + row_off;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (k < p.Ktot) {
+          const int iy = iy0 + fr, ix = ix0 + fs;
+          const bool ok = row_ok && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi;
+          const uint8_t* src = ok ? img + ((size_t)(iy * a.Wi + ix) * a.Cin + c) * ESZ : static_cast<const uint8_t*>(a.in);
+          const uint32_t nbytes = ok ? 16u : 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t chunk = (uint32_t)(h * 4 + j);
+            cp_async16(dst_row + ((chunk ^ sw) << 4), src + j * 16, nbytes);
+          }
+          k += HALF;
+          c += HALF;
+          if (c >= a.Cin) { c = 0; if (++fs == a.KW) { fs = 0; ++fr; } }
+        }
+      }
+      cp_async_commit();
+      if (kb >= lag) {
+        if (lag == 2) cp_async_wait<2>(); else if (lag == 1) cp_async_wait<1>(); else cp_async_wait<0>();
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8u * ((kb - lag) % S));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int kb = max(p.num_kb - lag, 0); kb < p.num_kb; ++kb) mbar_arrive(bar_full + 8u * (kb % S));
+
+    // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> global =======================================
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int y = oy * a.out_sy + a.out_oy, x = ox * a.out_sx + a.out_ox;
+    const size_t pix = ((size_t)b * a.Ho_full + y) * a.Wo_full + x;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool f32_io = TF32;                                // element type of NHWC activations (residual / default output)
+    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      uint32_t v[16];
+      __syncwarp();                                          // .sync.aligned: reconverge lanes that skipped the stores
+      tmem_ld16(t_row + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      const int n = n0 + c0;
+      float f[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n) + q);
+        f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + bq.x;
+        f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + bq.y;
+        f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + bq.z;
+        f[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + bq.w;
+      }
+      float r[16];
+      const bool has_res = a.res != nullptr;
+      if (has_res) {
+        const size_t o = pix * a.ld_out + a.out_coff + n;
+        if (f32_io) {
+          const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(a.res) + o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const float4 t = __ldg(rp + q); r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w; }
+        } else {
+          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res) + o);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint4 t = __ldg(rp + q);
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 ff = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+              r[q * 8 + e * 2] = ff.x; r[q * 8 + e * 2 + 1] = ff.y;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float t = f[e];
+        if (has_res && !a.res_after_act) t += r[e];
+        if (a.relu) t = fmaxf(t, 0.f);
+        if (has_res && a.res_after_act) t += r[e];
+        f[e] = t;
+      }
+      if (a.out_nchw) {                                      // fp32 [B,Cout,Ho,Wo]: lanes hold adjacent pixels
+        float* op = static_cast<float*>(a.out) + (((size_t)b * a.Cout + n) * a.Ho_full + y) * a.Wo_full + x;
+        const size_t cs = (size_t)a.Ho_full * a.Wo_full;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) op[e * cs] = f[e];
+      } else if (f32_io || p.out_f32) {
+        if (p.round_tf32) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) f[e] = round_tf32_rna(f[e]);
+        }
+        float4* op = reinterpret_cast<float4*>(static_cast<float*>(a.out) + pix * a.ld_out + a.out_coff + n);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + pix * a.ld_out + a.out_coff + n);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ===== MMA issuer ===================================================================================================
+    const uint32_t idesc = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                           ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int s = kb % S;
+      mbar_wait(bar_full + 8u * s, (kb / S) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const int kleft = p.Ktot - kb * KB;
+        const int nk = (kleft >= KB ? KB : kleft) / UK;
+        const uint64_t da = umma_desc(sA + (uint32_t)s * TC_A_STAGE), db = umma_desc(sB + (uint32_t)s * b_stage);
+        for (int kk = 0; kk < nk; ++kk) umma<TF32>(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0);
+        umma_commit(bar_empty + 8u * s);                     // frees the stage once these MMAs have read it
+        if (kb == p.num_kb - 1) umma_commit(bar_acc);        // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else if (lane == 0) {
+    // ===== weight loader: [kb][Cout][128 B] pre-swizzled; one bulk copy per k-block ===================================
+    const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)n0 * TC_ROW_BYTES;
+    const size_t kb_stride = (size_t)a.Cout * TC_ROW_BYTES;
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int s = kb % S;
+      if (kb >= S) mbar_wait(bar_empty + 8u * s, ((kb / S) & 1) ^ 1);
+      mbar_arrive_expect_tx(bar_full + 8u * s, (uint32_t)b_stage);
+      bulk_g2s(sB + (uint32_t)s * b_stage, wsrc + kb * kb_stride, (uint32_t)b_stage, bar_full + 8u * s);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = round_tf32_rna(in[i]);
+}
+
+size_t tc_smem_bytes(int stages, int block_n) {
+  return 1024 + (size_t)stages * (TC_A_STAGE + block_n * TC_ROW_BYTES) + 16 * TC_MAX_STAGES + 64;
+}
+
+}  // namespace
+
+bool conv_tc_supported(const ConvArgs& a, int tf32) {
+  const int half = tf32 ? 16 : 32;
+  return a.Cin % half == 0 && a.Cout % 16 == 0 && a.ld_out % 8 == 0 && a.out_coff % 8 == 0;
+}
+
+int conv_tc_launch(const ConvArgs& a, int tf32, int out_f32, int round_tf32, cudaStream_t st) {
+  if (!conv_tc_supported(a, tf32))
+    return fail(HRP_ERR_INVALID, "conv_tc: unsupported shape Cin=%d Cout=%d ld=%d coff=%d", a.Cin, a.Cout, a.ld_out, a.out_coff);
+  TcParams p{};
+  p.a = a;
+  p.M = a.B * a.Ho * a.Wo;
+  if (p.M <= 0) return HRP_OK;
+  const int kb_elems = tf32 ? 32 : 64;
+  p.Ktot = a.KH * a.KW * a.Cin;
+  p.num_kb = ceil_div(p.Ktot, kb_elems);
+  const int mtiles = ceil_div(p.M, TC_BLOCK_M);
+  // widest N tile that still gives every SM about two CTAs; never below 32 columns (one TMEM allocation granule)
+  const int cand[4] = {256, 128, 64, 32};
+  int bn = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (a.Cout % cand[i]) continue;
+    bn = cand[i];
+    if ((long long)mtiles * (a.Cout / cand[i]) >= 2LL * sm_count()) break;
+  }
+  if (bn == 0) bn = 16;                                     // Cout = 16 * odd
+  p.block_n = bn;
+  int tm = 32;
+  while (tm < bn) tm <<= 1;
+  p.tmem_cols = tm;
+  const int smax = bn >= 256 ? 4 : (bn >= 128 ? 3 : 4);
+  p.stages = std::max(1, std::min(p.num_kb, smax));
+  p.lag = std::min(2, p.stages - 1);
+  p.out_f32 = out_f32;
+  p.round_tf32 = round_tf32;
+  const size_t smem = tc_smem_bytes(p.stages, bn);
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[tf32 ? 1 : 0]) {
+    if (tf32) HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done[tf32 ? 1 : 0] = true;
+  }
+  dim3 grid(mtiles, a.Cout / bn);
+  if (tf32) conv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
+  else conv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
+  HRP_CHECK_LAUNCH("conv_tc_kernel");
+  return HRP_OK;
+}
+
+// [K][Cout] fp32 (BN folded, k = (r*KW+s)*Cin + c) -> [num_kb][Cout][128 B] K-major rows, 16-byte chunks XOR-swizzled
+// by (row & 7) exactly as the SWIZZLE_128B operand layout expects; K zero-padded to a whole k-block.
+size_t pack_conv_tc_bytes(int K, int Cout, int tf32) { return (size_t)ceil_div(K, tf32 ? 32 : 64) * Cout * TC_ROW_BYTES; }
+
+void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, void* out) {
+  const int kb_elems = tf32 ? 32 : 64, ce = tf32 ? 4 : 8;
+  const int num_kb = ceil_div(K, kb_elems);
+  uint8_t* o = static_cast<uint8_t*>(out);
+  std::memset(o, 0, pack_conv_tc_bytes(K, Cout, tf32));
+  for (int kb = 0; kb < num_kb; ++kb)
+    for (int n = 0; n < Cout; ++n) {
+      uint8_t* row = o + ((size_t)kb * Cout + n) * TC_ROW_BYTES;
+      for (int j = 0; j < 8; ++j) {
+        uint8_t* chunk = row + ((j ^ (n & 7)) << 4);
+        for (int e = 0; e < ce; ++e) {
+          const int k = kb * kb_elems + j * ce + e;
+          if (k >= K) continue;
+          const float v = w_kn[(size_t)k * Cout + n];
+          if (tf32) {
+            uint32_t u;
+            std::memcpy(&u, &v, 4);
+            if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & ~0x1fffu;     // cvt.rna.tf32
+            std::memcpy(chunk + e * 4, &u, 4);
+          } else {
+            uint32_t u;
+            std::memcpy(&u, &v, 4);
+            if ((u & 0x7f800000u) != 0x7f800000u) u += 0x7fffu + ((u >> 16) & 1u);   // round to nearest even
+            const uint16_t hbits = (uint16_t)(u >> 16);
+            std::memcpy(chunk + e * 2, &hbits, 2);
+          }
+        }
+      }
+    }
+}
+
+int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t st) {
+  if (n == 0) return HRP_OK;
+  cast_f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, static_cast<__nv_bfloat16*>(out), n);
+  HRP_CHECK_LAUNCH("cast_f32_to_bf16_kernel");
+  return HRP_OK;
+}
+int cast_bf16_to_f32_launch(const void* in, float* out, size_t n, cudaStream_t st) {
+  if (n == 0) return HRP_OK;
+  cast_bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), out, n);
+  HRP_CHECK_LAUNCH("cast_bf16_to_f32_kernel");
+  return HRP_OK;
+}
+int round_tf32_launch(const float* in, float* out, size_t n, cudaStream_t st) {
+  if (n == 0) return HRP_OK;
+  round_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+  HRP_CHECK_LAUNCH("round_tf32_kernel");
+  return HRP_OK;
+}
+
+}  // namespace hrp

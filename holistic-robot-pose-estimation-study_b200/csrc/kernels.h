@@ -26,9 +26,21 @@ struct ConvArgs {
 
 int conv_f32_launch(const ConvArgs& a, cudaStream_t s);
 
+// Tensor-core family (conv_tc.cu): tcgen05.mma with bf16 (tf32 = 0) or TF32 (tf32 = 1) operands, fp32 accumulation in
+// TMEM. Activations are NHWC bf16 / fp32; `a.w` is the pack_conv_tc() image. out_f32: write fp32 NHWC from the bf16
+// family; round_tf32: round fp32 NHWC outputs to TF32 (nearest) for the next layer's operands.
+bool conv_tc_supported(const ConvArgs& a, int tf32);
+int conv_tc_launch(const ConvArgs& a, int tf32, int out_f32, int round_tf32, cudaStream_t s);
+size_t pack_conv_tc_bytes(int K, int Cout, int tf32);
+void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, void* out);   // from pack_conv_f32's [K][Cout]
+int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t s);
+int cast_bf16_to_f32_launch(const void* in, float* out, size_t n, cudaStream_t s);
+int round_tf32_launch(const float* in, float* out, size_t n, cudaStream_t s);
+
 // Stem: NCHW fp32 [B,3,Hi,Wi] -> NHWC [B,Ho,Wo,64], KxK stride 2, BN folded, ReLU. w packed [(c*KH+r)*KW+s][64].
+// out_mode: 0 fp32, 1 bf16, 2 fp32 rounded to TF32.
 int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, void* out, int B, int Hi, int Wi,
-                     int Ho, int Wo, int KH, int KW, int pad, int out_bf16, cudaStream_t s);
+                     int Ho, int Wo, int KH, int KW, int pad, int out_mode, cudaStream_t s);
 
 int maxpool3x3s2_launch(const void* in, void* out, int B, int Hi, int Wi, int C, int bf16, cudaStream_t s);
 
@@ -41,6 +53,7 @@ struct FuseArgs {
   void* out;
   int B, H, W, C;
   int relu;
+  int round_tf32;
 };
 int fuse_sum_launch(const FuseArgs& a, int bf16, cudaStream_t s);
 

@@ -39,7 +39,8 @@ struct TensorInfo {
 };
 
 struct Layer {            // device-resident packed conv / linear
-  float* w = nullptr;
+  float* w = nullptr;       // fp32 family: [K][Cout]
+  void* w_tc = nullptr;     // tensor-core families: pack_conv_tc image
   float* bias = nullptr;
   int Cout = 0, Cin = 0, KH = 0, KW = 0;
 };
@@ -232,6 +233,9 @@ struct GraphBuilder {
   hrp_handle* h;
   int status = HRP_OK;
   int act_esize = 4;
+  int prec = HRP_PREC_FP32;
+  bool tc() const { return prec != HRP_PREC_FP32; }
+  bool tf32() const { return prec == HRP_PREC_TF32; }
 
   const float* W(const std::string& name) {
     auto it = h->host.find(name);
@@ -253,6 +257,35 @@ struct GraphBuilder {
       cudaGetLastError();
     }
     return d;
+  }
+
+  void* upload_bytes(const std::vector<uint8_t>& v) {
+    void* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(v.size(), 16)) != cudaSuccess) {
+      if (status == HRP_OK) status = fail(HRP_ERR_NOMEM, "cudaMalloc of %zu bytes for weights failed", v.size());
+      cudaGetLastError();
+      return nullptr;
+    }
+    h->dev_allocs.push_back(d);
+    if (cudaMemcpy(d, v.data(), v.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      if (status == HRP_OK) status = fail(HRP_ERR_CUDA, "weight upload failed");
+      cudaGetLastError();
+    }
+    return d;
+  }
+
+  // finish a backbone conv layer from its fp32 [K][Cout] matrix: the tensor-core families keep only the swizzled image
+  int finish_layer(std::vector<float>& wp, float* dbias, int Cin, int Cout, int KH, int KW) {
+    Layer L; L.Cout = Cout; L.Cin = Cin; L.KH = KH; L.KW = KW; L.bias = dbias;
+    if (tc()) {
+      std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32()));
+      pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32(), img.data());
+      L.w_tc = upload_bytes(img);
+    } else {
+      L.w = upload(wp);
+    }
+    h->layers.push_back(L);
+    return (int)h->layers.size() - 1;
   }
 
   Tn new_tensor(int H, int W_, int C, int esize, const char* name = "") {
@@ -281,16 +314,13 @@ struct GraphBuilder {
     if (status != HRP_OK) return -1;
     std::vector<float> wp((size_t)KH * KW * Cin * Cout), bp(Cout);
     pack_conv_f32(w, cb, g, b, m, v, Cout, Cin, KH, KW, wp.data(), bp.data());
-    Layer L; L.Cout = Cout; L.Cin = Cin; L.KH = KH; L.KW = KW;
-    L.w = upload(wp); L.bias = upload(bp);
-    h->layers.push_back(L);
-    return (int)h->layers.size() - 1;
+    return finish_layer(wp, upload(bp), Cin, Cout, KH, KW);
   }
 
   Tn conv(const Tn& x, const std::string& pc, const std::string& pb, int Cout, int k, int stride, int pad, int relu,
           int res = -1, int res_after_act = 0, int out_nchw = 0, int out_esize = -1, const char* name = "") {
     OpDesc op{};
-    op.kind = OP_CONV; op.cls = CLS_CONV_F32;
+    op.kind = OP_CONV; op.cls = tc() ? CLS_CONV_TC : CLS_CONV_F32;
     op.layer = make_layer(pc, pb, x.C, Cout, k, k);
     op.Hi = x.H; op.Wi = x.W; op.Cin = x.C; op.Cout = Cout; op.KH = op.KW = k; op.stride = stride; op.pad_h = op.pad_w = pad;
     op.Ho = (x.H + 2 * pad - k) / stride + 1; op.Wo = (x.W + 2 * pad - k) / stride + 1;
@@ -444,10 +474,8 @@ struct GraphBuilder {
               for (int o = 0; o < Cout; ++o)
                 wp[((size_t)(ty * 2 + tx) * Cin + c) * Cout + o] = (float)((double)w[(((size_t)c * Cout + o) * 4 + ky) * 4 + kx] * sc[o]);
           }
-        Layer L; L.Cout = Cout; L.Cin = Cin; L.KH = L.KW = 2; L.w = upload(wp); L.bias = dbias;
-        h->layers.push_back(L);
         OpDesc op{};
-        op.kind = OP_CONV; op.cls = CLS_CONV_F32; op.layer = (int)h->layers.size() - 1;
+        op.kind = OP_CONV; op.cls = tc() ? CLS_CONV_TC : CLS_CONV_F32; op.layer = finish_layer(wp, dbias, Cin, Cout, 2, 2);
         op.in = x.id; op.out = y.id; op.Hi = x.H; op.Wi = x.W; op.Cin = Cin; op.Cout = Cout; op.KH = op.KW = 2; op.stride = 1;
         op.pad_h = 1 - py; op.pad_w = 1 - px; op.Ho = x.H; op.Wo = x.W; op.out_sy = op.out_sx = 2; op.out_oy = py; op.out_ox = px;
         op.Ho_full = y.H; op.Wo_full = y.W; op.relu = 1; op.ld = Cout;
@@ -543,7 +571,8 @@ struct GraphBuilder {
 
   int build() {
     h->tensors.clear(); h->ops.clear();
-    act_esize = 4;
+    prec = h->cfg.precision;
+    act_esize = prec == HRP_PREC_BF16 ? 2 : 4;
     const int nk = h->nkpt, dof = h->dof;
     const int fw[HRP_NUM_FIELDS] = {dof, 6, 3, 2, 1, nk * 3, nk * 3, nk * 3, nk * 2, nk * 2};
     h->t_xreg = special(T_XREG, 3LL * 256 * 256);
@@ -734,39 +763,41 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
     return nullptr;
   };
   int64_t launches = 0;
+  const int bf16 = h->cfg.precision == HRP_PREC_BF16 ? 1 : 0, tf32 = h->cfg.precision == HRP_PREC_TF32 ? 1 : 0;
   for (const OpDesc& o : h->ops) {
     if (prof) HRP_CUDA(cudaEventRecord(prof->e0, st));
     int n_launch = 1;
     switch (o.kind) {
       case OP_STEM: {
         const Layer& L = h->layers[o.layer];
-        HRP_TRY(stem_conv_launch(static_cast<const float*>(ptr(o.in)), L.w, L.bias, ptr(o.out), B, o.Hi, o.Wi, o.Ho, o.Wo, o.KH, o.KW, o.pad_h, 0, st));
+        HRP_TRY(stem_conv_launch(static_cast<const float*>(ptr(o.in)), L.w, L.bias, ptr(o.out), B, o.Hi, o.Wi, o.Ho, o.Wo, o.KH, o.KW, o.pad_h, bf16 ? 1 : (tf32 ? 2 : 0), st));
         break;
       }
       case OP_CONV: {
         const Layer& L = h->layers[o.layer];
         ConvArgs a{};
-        a.in = ptr(o.in); a.w = L.w; a.bias = L.bias; a.res = ptr(o.res); a.out = ptr(o.out);
+        a.in = ptr(o.in); a.w = o.cls == CLS_CONV_TC ? L.w_tc : static_cast<const void*>(L.w); a.bias = L.bias; a.res = ptr(o.res); a.out = ptr(o.out);
         a.B = B; a.Hi = o.Hi; a.Wi = o.Wi; a.Cin = o.Cin; a.Ho = o.Ho; a.Wo = o.Wo; a.Cout = o.Cout;
         a.KH = o.KH; a.KW = o.KW; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w;
         a.out_sy = o.out_sy; a.out_sx = o.out_sx; a.out_oy = o.out_oy; a.out_ox = o.out_ox; a.Ho_full = o.Ho_full; a.Wo_full = o.Wo_full;
         a.relu = o.relu; a.out_nchw = o.out_nchw; a.ld_out = o.ld; a.out_coff = 0; a.res_after_act = o.res_after_act;
-        HRP_TRY(conv_f32_launch(a, st));
+        if (o.cls == CLS_CONV_TC) HRP_TRY(conv_tc_launch(a, tf32, 0, tf32 && !o.out_nchw, st));
+        else HRP_TRY(conv_f32_launch(a, st));
         break;
       }
       case OP_MAXPOOL:
-        HRP_TRY(maxpool3x3s2_launch(ptr(o.in), ptr(o.out), B, o.Hi, o.Wi, o.Cin, 0, st));
+        HRP_TRY(maxpool3x3s2_launch(ptr(o.in), ptr(o.out), B, o.Hi, o.Wi, o.Cin, bf16, st));
         break;
       case OP_FUSE: {
         FuseArgs a{};
         for (int k = 0; k < o.n_same; ++k) a.same[k] = ptr(o.same[k]);
         for (int k = 0; k < o.n_low; ++k) { a.low[k] = ptr(o.low[k]); a.shift[k] = o.shift[k]; }
-        a.n_same = o.n_same; a.n_low = o.n_low; a.out = ptr(o.out); a.B = B; a.H = o.Ho; a.W = o.Wo; a.C = o.Cout; a.relu = o.relu;
-        HRP_TRY(fuse_sum_launch(a, 0, st));
+        a.n_same = o.n_same; a.n_low = o.n_low; a.out = ptr(o.out); a.B = B; a.H = o.Ho; a.W = o.Wo; a.C = o.Cout; a.relu = o.relu; a.round_tf32 = tf32;
+        HRP_TRY(fuse_sum_launch(a, bf16, st));
         break;
       }
       case OP_AVGPOOL:
-        HRP_TRY(avgpool_launch(ptr(o.in), static_cast<float*>(ptr(o.out)), B, o.Hi * o.Wi, o.Cin, 0, st));
+        HRP_TRY(avgpool_launch(ptr(o.in), static_cast<float*>(ptr(o.out)), B, o.Hi * o.Wi, o.Cin, bf16, st));
         break;
       case OP_DEPTH:
         HRP_TRY(depth_head_launch(static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, static_cast<const float*>(ptr(o.in2)), static_cast<float*>(ptr(o.out)), B, o.Cin, st));
@@ -820,8 +851,8 @@ extern "C" int hrp_create(const hrp_config* cfg, const hrp_fk_program* robot, in
   if (!cfg || !robot || !out) return fail(HRP_ERR_INVALID, "hrp_create: null argument");
   if (cfg->backbone != HRP_BACKBONE_RESNET50 && cfg->backbone != HRP_BACKBONE_HRNET32)
     return fail(HRP_ERR_INVALID, "hrp_create: unsupported backbone %d (resnet50 or hrnet32)", cfg->backbone);
-  if (cfg->precision != HRP_PREC_FP32)
-    return fail(HRP_ERR_INVALID, "hrp_create: precision %d not available in this build (fp32 parity family only)", cfg->precision);
+  if (cfg->precision != HRP_PREC_FP32 && cfg->precision != HRP_PREC_TF32 && cfg->precision != HRP_PREC_BF16)
+    return fail(HRP_ERR_INVALID, "hrp_create: unknown precision %d (0 fp32, 1 tf32, 2 bf16)", cfg->precision);
   if (cfg->n_iter < 1 || cfg->n_iter > 16) return fail(HRP_ERR_INVALID, "hrp_create: n_iter %d out of range", cfg->n_iter);
   if (cfg->image_size != 256.0f) return fail(HRP_ERR_INVALID, "hrp_create: only 256x256 inputs are supported (got %g)", cfg->image_size);
   std::unique_ptr<hrp_handle> h(new hrp_handle());
@@ -989,7 +1020,8 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
                                int B, int Hi, int Wi, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu,
                                int precision, void* stream) {
   if (!in || !weight_oihw || !out) return fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: null argument");
-  if (precision != HRP_PREC_FP32) return fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: precision %d not available in this build", precision);
+  if (precision != HRP_PREC_FP32 && precision != HRP_PREC_TF32 && precision != HRP_PREC_BF16)
+    return fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: unknown precision %d", precision);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nw = (size_t)Cout * Cin * KH * KW;
   std::vector<float> w(nw), b(Cout, 0.f), wp(nw), bp(Cout);
@@ -997,19 +1029,49 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
   if (bias) HRP_CUDA(cudaMemcpyAsync(b.data(), bias, (size_t)Cout * 4, cudaMemcpyDeviceToHost, st));
   HRP_CUDA(cudaStreamSynchronize(st));
   pack_conv_f32(w.data(), b.data(), nullptr, nullptr, nullptr, nullptr, Cout, Cin, KH, KW, wp.data(), bp.data());
-  float *dw = nullptr, *db = nullptr;
-  HRP_CUDA(cudaMalloc(&dw, nw * 4));
-  HRP_CUDA(cudaMalloc(&db, (size_t)Cout * 4));
-  HRP_CUDA(cudaMemcpyAsync(dw, wp.data(), nw * 4, cudaMemcpyHostToDevice, st));
-  HRP_CUDA(cudaMemcpyAsync(db, bp.data(), (size_t)Cout * 4, cudaMemcpyHostToDevice, st));
   ConvArgs a{};
-  a.in = in; a.w = dw; a.bias = db; a.res = residual; a.out = out;
   a.B = B; a.Hi = Hi; a.Wi = Wi; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.stride = stride; a.pad_h = a.pad_w = pad;
   a.Ho = (Hi + 2 * pad - KH) / stride + 1; a.Wo = (Wi + 2 * pad - KW) / stride + 1;
   a.out_sy = a.out_sx = 1; a.Ho_full = a.Ho; a.Wo_full = a.Wo; a.relu = relu; a.ld_out = Cout;
-  const int rs = conv_f32_launch(a, st);
-  cudaStreamSynchronize(st);
-  cudaFree(dw);
-  cudaFree(db);
+  const size_t n_in = (size_t)B * Hi * Wi * Cin, n_out = (size_t)B * a.Ho * a.Wo * Cout;
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(bytes, 16)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    tmp.push_back(d);
+    return d;
+  };
+  int rs = HRP_OK;
+  float* db = static_cast<float*>(dalloc((size_t)Cout * 4));
+  if (!db) rs = fail(HRP_ERR_NOMEM, "hrp_conv2d_nhwc: out of device memory");
+  if (rs == HRP_OK && cudaMemcpyAsync(db, bp.data(), (size_t)Cout * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: copy failed");
+  a.bias = db;
+  if (rs == HRP_OK && precision == HRP_PREC_FP32) {
+    float* dw = static_cast<float*>(dalloc(nw * 4));
+    if (!dw) rs = fail(HRP_ERR_NOMEM, "hrp_conv2d_nhwc: out of device memory");
+    if (rs == HRP_OK && cudaMemcpyAsync(dw, wp.data(), nw * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: copy failed");
+    a.in = in; a.w = dw; a.res = residual; a.out = out;
+    if (rs == HRP_OK) rs = conv_f32_launch(a, st);
+  } else if (rs == HRP_OK) {
+    // tensor-core families: operands converted to the family's activation type exactly as a producing layer would
+    const int tf32 = precision == HRP_PREC_TF32;
+    if (!conv_tc_supported(a, tf32)) rs = fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: shape not supported by the tensor-core family (Cin %% %d, Cout %% 16)", tf32 ? 16 : 32);
+    std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32));
+    pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32, img.data());
+    void* dw = dalloc(img.size());
+    const size_t es = tf32 ? 4 : 2;
+    void* din = dalloc(n_in * es);
+    void* dres = residual ? dalloc(n_out * es) : nullptr;
+    void* dout = tf32 ? static_cast<void*>(out) : dalloc(n_out * es);
+    if (rs == HRP_OK && (!dw || !din || !dout || (residual && !dres))) rs = fail(HRP_ERR_NOMEM, "hrp_conv2d_nhwc: out of device memory");
+    if (rs == HRP_OK && cudaMemcpyAsync(dw, img.data(), img.size(), cudaMemcpyHostToDevice, st) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: copy failed");
+    if (rs == HRP_OK) rs = tf32 ? round_tf32_launch(in, static_cast<float*>(din), n_in, st) : cast_f32_to_bf16_launch(in, din, n_in, st);
+    if (rs == HRP_OK && residual) rs = tf32 ? round_tf32_launch(residual, static_cast<float*>(dres), n_out, st) : cast_f32_to_bf16_launch(residual, dres, n_out, st);
+    a.in = din; a.w = dw; a.res = dres; a.out = dout;
+    if (rs == HRP_OK) rs = conv_tc_launch(a, tf32, 0, tf32, st);
+    if (rs == HRP_OK && !tf32) rs = cast_bf16_to_f32_launch(dout, out, n_out, st);
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess && rs == HRP_OK) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: %s", cudaGetErrorString(cudaGetLastError()));
+  for (void* d : tmp) cudaFree(d);
   return rs;
 }
