@@ -42,7 +42,8 @@ struct TcParams {
   int stages;
   int lag;           // cp.async groups kept in flight per producer thread (< stages)
   int tmem_cols;     // power of two >= max(32, block_n)
-  int out_f32;       // NHWC output element type: 1 fp32, 0 the activation type of the family
+  int bar_off;       // byte offset of the barrier block (after the operand stages and the epilogue staging tile)
+  int cpr_log;       // log2 of 16-byte chunks per staged tile row (block_n * elem / 16)
   int round_tf32;    // round fp32 NHWC outputs to TF32 (nearest, ties away) so the next MMA sees exact operands
 };
 
@@ -138,12 +139,14 @@ __device__ __forceinline__ float round_tf32_rna(float x) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four epilogue warps
+
 template <bool TF32>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 3)
 conv_tc_kernel(const TcParams p) {
   constexpr int ESZ = TF32 ? 4 : 2;
   constexpr int KB = TC_ROW_BYTES / ESZ;     // K elements per k-block (64 bf16 / 32 tf32)
-  constexpr int HALF = KB / 2;               // elements per 64-byte half row (4 chunks of 16 B)
+  constexpr int CE = 16 / ESZ;               // elements per 16-byte chunk
   constexpr int UK = 32 / ESZ;               // K elements per tcgen05.mma (16 bf16 / 8 tf32)
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -152,8 +155,9 @@ conv_tc_kernel(const TcParams p) {
   const int b_stage = p.block_n * TC_ROW_BYTES;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + (uint32_t)S * TC_A_STAGE;
-  const uint32_t sBar = sB + (uint32_t)S * b_stage;       // full[S], empty[S], tmem_full, tmem_ptr
+  const uint32_t sBar = smem_base + (uint32_t)p.bar_off;  // full[S], empty[S], tmem_full, tmem_ptr, row offsets[128]
   const uint32_t bar_full = sBar, bar_empty = sBar + 8u * S, bar_acc = sBar + 16u * S, tmem_slot = bar_acc + 8u;
+  const uint32_t s_rowoff = sBar + 16u * TC_MAX_STAGES + 16u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const ConvArgs& a = p.a;
@@ -175,126 +179,187 @@ conv_tc_kernel(const TcParams p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp < 4) {
-    // ===== producers: im2col gather of tile row `tid` ===============================================================
+    // ===== producers: im2col gather. One warp instruction covers 4 tile rows x 128 contiguous bytes (lane = 8*row + chunk),
+    // so every request touches 4 cache lines instead of 32; a thread serves chunk `j` of 8 rows of its warp's 32. ==========
+    {
+      const int j = lane & 7, rsub = lane >> 3;
+      int iy0[8], ix0[8], boff[8];
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + warp * 32 + i * 4 + rsub;
+        const bool ok = m < p.M;
+        const int mm = ok ? m : 0;
+        const int ox = mm % a.Wo, t1 = mm / a.Wo, oy = t1 % a.Ho, b = t1 / a.Ho;
+        iy0[i] = oy * a.stride - a.pad_h;
+        ix0[i] = ox * a.stride - a.pad_w;
+        boff[i] = b * a.Hi * a.Wi;
+        okmask |= (ok ? 1u : 0u) << i;
+      }
+      const uint32_t dst0 = (uint32_t)(warp * 32 + rsub) * TC_ROW_BYTES;
+      int c = j * CE, fr = 0, fs = 0, kthr = j * CE;
+      while (c >= a.Cin) { c -= a.Cin; if (++fs == a.KW) { fs = 0; ++fr; } }
+      const uint8_t* in8 = static_cast<const uint8_t*>(a.in);
+      const int lag = p.lag;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % S;
+        if (kb >= S) mbar_wait(bar_empty + 8u * s, ((kb / S) & 1) ^ 1);
+        if (kthr < p.Ktot) {
+          const uint32_t dst_s = sA + (uint32_t)s * TC_A_STAGE + dst0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int iy = iy0[i] + fr, ix = ix0[i] + fs;
+            const bool ok = ((okmask >> i) & 1u) && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi;
+            const uint8_t* src = ok ? in8 + ((size_t)(boff[i] + iy * a.Wi + ix) * a.Cin + c) * ESZ : in8;
+            // row r = warp*32 + i*4 + rsub: r & 7 = ((i & 1) << 2) | rsub
+            cp_async16(dst_s + (uint32_t)i * (4 * TC_ROW_BYTES) + (((uint32_t)j ^ (uint32_t)(((i & 1) << 2) | rsub)) << 4), src, ok ? 16u : 0u);
+          }
+        }
+        kthr += KB;
+        c += KB;
+        while (c >= a.Cin) { c -= a.Cin; if (++fs == a.KW) { fs = 0; ++fr; } }
+        cp_async_commit();
+        if (kb >= lag) {
+          if (lag == 2) cp_async_wait<2>(); else if (lag == 1) cp_async_wait<1>(); else cp_async_wait<0>();
+          fence_proxy_async();
+          mbar_arrive(bar_full + 8u * ((kb - lag) % S));
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      for (int kb = max(p.num_kb - lag, 0); kb < p.num_kb; ++kb) mbar_arrive(bar_full + 8u * (kb % S));
+    }
+
+    // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> global ========================================
+    // thread `tid` owns tile row `tid` (TMEM lane tid)
     const int m = m0 + tid;
     const bool row_ok = m < p.M;
     const int mm = row_ok ? m : 0;
     const int ox = mm % a.Wo, t1 = mm / a.Wo, oy = t1 % a.Ho, b = t1 / a.Ho;
-    const int iy0 = oy * a.stride - a.pad_h, ix0 = ox * a.stride - a.pad_w;
-    const uint8_t* img = static_cast<const uint8_t*>(a.in) + (size_t)b * a.Hi * a.Wi * a.Cin * ESZ;
-    const uint32_t row_off = (uint32_t)tid * TC_ROW_BYTES;
-    const uint32_t sw = (uint32_t)(tid & 7);
-    int c = 0, fr = 0, fs = 0, k = 0;                       // running (channel, filter row, filter col, k) of the next half row
-    const int lag = p.lag;
-    for (int kb = 0; kb < p.num_kb; ++kb) {
-      const int s = kb % S;
-      if (kb >= S) mbar_wait(bar_empty + 8u * s, ((kb / S) & 1) ^ 1);
-      const uint32_t dst_row = sA + (uint32_t)s * TC_A_STAGE + row_off;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (k < p.Ktot) {
-          const int iy = iy0 + fr, ix = ix0 + fs;
-          const bool ok = row_ok && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi;
-          const uint8_t* src = ok ? img + ((size_t)(iy * a.Wi + ix) * a.Cin + c) * ESZ : static_cast<const uint8_t*>(a.in);
-          const uint32_t nbytes = ok ? 16u : 0u;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t chunk = (uint32_t)(h * 4 + j);
-            cp_async16(dst_row + ((chunk ^ sw) << 4), src + j * 16, nbytes);
-          }
-          k += HALF;
-          c += HALF;
-          if (c >= a.Cin) { c = 0; if (++fs == a.KW) { fs = 0; ++fr; } }
-        }
-      }
-      cp_async_commit();
-      if (kb >= lag) {
-        if (lag == 2) cp_async_wait<2>(); else if (lag == 1) cp_async_wait<1>(); else cp_async_wait<0>();
-        fence_proxy_async();
-        mbar_arrive(bar_full + 8u * ((kb - lag) % S));
-      }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int kb = max(p.num_kb - lag, 0); kb < p.num_kb; ++kb) mbar_arrive(bar_full + 8u * (kb % S));
-
-    // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> global =======================================
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
     const int y = oy * a.out_sy + a.out_oy, x = ox * a.out_sx + a.out_ox;
     const size_t pix = ((size_t)b * a.Ho_full + y) * a.Wo_full + x;
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const bool f32_io = TF32;                                // element type of NHWC activations (residual / default output)
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-      uint32_t v[16];
-      __syncwarp();                                          // .sync.aligned: reconverge lanes that skipped the stores
-      tmem_ld16(t_row + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-      const int n = n0 + c0;
-      float f[16];
+    if (a.out_nchw) {
+      // fp32 [B,Cout,Ho,Wo] (heatmap logits for the integral layer): lanes hold adjacent pixels, stores are coalesced
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      float* op = static_cast<float*>(a.out) + (((size_t)b * a.Cout + n0) * a.Ho_full + y) * a.Wo_full + x;
+      const size_t cs = (size_t)a.Ho_full * a.Wo_full;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n) + q);
-        f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + bq.x;
-        f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + bq.y;
-        f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + bq.z;
-        f[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + bq.w;
+        for (int q = 0; q < 4; ++q) {
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
+          float f0 = __uint_as_float(v[q * 4 + 0]) + bq.x, f1 = __uint_as_float(v[q * 4 + 1]) + bq.y;
+          float f2 = __uint_as_float(v[q * 4 + 2]) + bq.z, f3 = __uint_as_float(v[q * 4 + 3]) + bq.w;
+          if (a.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+          op[(size_t)(c0 + q * 4 + 0) * cs] = f0; op[(size_t)(c0 + q * 4 + 1) * cs] = f1;
+          op[(size_t)(c0 + q * 4 + 2) * cs] = f2; op[(size_t)(c0 + q * 4 + 3) * cs] = f3;
+        }
       }
-      float r[16];
+    } else {
+      // NHWC: stage the 128 x BLOCK_N tile in shared memory (the operand stages are free once the accumulator is
+      // complete) so that residual loads and output stores run as 16-byte chunks along the channel axis.
+      const uint32_t pitch = (uint32_t)p.block_n * ESZ + 16u;          // odd multiple of 16 B: conflict-free both ways
+      const uint32_t cpr_log = (uint32_t)p.cpr_log;                     // log2(16-byte chunks per tile row)
+      const uint32_t cpr = 1u << cpr_log;
+      const uint32_t stg = smem_base;
+      {
+        const long long off = row_ok ? (long long)(pix * a.ld_out + a.out_coff + n0) : -1ll;
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(s_rowoff + 8u * tid), "l"(off) : "memory");
+      }
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      epi_barrier();
       const bool has_res = a.res != nullptr;
       if (has_res) {
-        const size_t o = pix * a.ld_out + a.out_coff + n;
-        if (f32_io) {
-          const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(a.res) + o);
+        const uint8_t* res8 = static_cast<const uint8_t*>(a.res);
+        for (uint32_t idx = tid; idx < (128u << cpr_log); idx += 128u) {
+          const uint32_t row = idx >> cpr_log, ch = idx & (cpr - 1u);
+          long long off;
+          asm volatile("ld.shared.b64 %0, [%1];" : "=l"(off) : "r"(s_rowoff + 8u * row));
+          if (off >= 0) cp_async16(stg + row * pitch + (ch << 4), res8 + (size_t)off * ESZ + (ch << 4), 16u);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        epi_barrier();
+      }
+      const uint32_t my = stg + (uint32_t)tid * pitch;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float f[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { const float4 t = __ldg(rp + q); r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w; }
-        } else {
-          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res) + o);
+        for (int q = 0; q < 4; ++q) {
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
+          f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + bq.x;
+          f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + bq.y;
+          f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + bq.z;
+          f[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + bq.w;
+        }
+        float r[16];
+        if (has_res) {
+          if constexpr (TF32) {
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const uint4 t = __ldg(rp + q);
-            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+            for (int q = 0; q < 4; ++q)
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r[q * 4]), "=f"(r[q * 4 + 1]), "=f"(r[q * 4 + 2]), "=f"(r[q * 4 + 3]) : "r"(my + (uint32_t)c0 * 4u + 16u * q));
+          } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 ff = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-              r[q * 8 + e * 2] = ff.x; r[q * 8 + e * 2 + 1] = ff.y;
+            for (int q = 0; q < 2; ++q) {
+              uint32_t w[4];
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(my + (uint32_t)c0 * 2u + 16u * q));
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 ff = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                r[q * 8 + e * 2] = ff.x; r[q * 8 + e * 2 + 1] = ff.y;
+              }
             }
           }
         }
-      }
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        float t = f[e];
-        if (has_res && !a.res_after_act) t += r[e];
-        if (a.relu) t = fmaxf(t, 0.f);
-        if (has_res && a.res_after_act) t += r[e];
-        f[e] = t;
-      }
-      if (a.out_nchw) {                                      // fp32 [B,Cout,Ho,Wo]: lanes hold adjacent pixels
-        float* op = static_cast<float*>(a.out) + (((size_t)b * a.Cout + n) * a.Ho_full + y) * a.Wo_full + x;
-        const size_t cs = (size_t)a.Ho_full * a.Wo_full;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) op[e * cs] = f[e];
-      } else if (f32_io || p.out_f32) {
-        if (p.round_tf32) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) f[e] = round_tf32_rna(f[e]);
+        for (int e = 0; e < 16; ++e) {
+          float t = f[e];
+          if (has_res && !a.res_after_act) t += r[e];
+          if (a.relu) t = fmaxf(t, 0.f);
+          if (has_res && a.res_after_act) t += r[e];
+          f[e] = t;
         }
-        float4* op = reinterpret_cast<float4*>(static_cast<float*>(a.out) + pix * a.ld_out + a.out_coff + n);
+        if constexpr (TF32) {
+          if (p.round_tf32) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-      } else {
-        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + pix * a.ld_out + a.out_coff + n);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
-            w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            for (int e = 0; e < 16; ++e) f[e] = round_tf32_rna(f[e]);
           }
-          op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(my + (uint32_t)c0 * 4u + 16u * q), "f"(f[q * 4]), "f"(f[q * 4 + 1]), "f"(f[q * 4 + 2]), "f"(f[q * 4 + 3]) : "memory");
+        } else {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
+              w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + (uint32_t)c0 * 2u + 16u * q), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          }
+        }
+      }
+      epi_barrier();
+      uint8_t* out8 = static_cast<uint8_t*>(a.out);
+      for (uint32_t idx = tid; idx < (128u << cpr_log); idx += 128u) {
+        const uint32_t row = idx >> cpr_log, ch = idx & (cpr - 1u);
+        long long off;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(off) : "r"(s_rowoff + 8u * row));
+        if (off >= 0) {
+          uint4 t;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(stg + row * pitch + (ch << 4)));
+          *reinterpret_cast<uint4*>(out8 + (size_t)off * ESZ + (ch << 4)) = t;
         }
       }
     }
@@ -348,8 +413,14 @@ __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restric
   if (i < n) out[i] = round_tf32_rna(in[i]);
 }
 
-size_t tc_smem_bytes(int stages, int block_n) {
-  return 1024 + (size_t)stages * (TC_A_STAGE + block_n * TC_ROW_BYTES) + 16 * TC_MAX_STAGES + 64;
+// operand stages and the epilogue staging tile share one region; barriers, the TMEM slot and row offsets follow it
+size_t tc_region_bytes(int stages, int block_n, int esz) {
+  const size_t ops = (size_t)stages * (TC_A_STAGE + block_n * TC_ROW_BYTES);
+  const size_t stg = (size_t)TC_BLOCK_M * (block_n * esz + 16);
+  return (std::max(ops, stg) + 127) / 128 * 128;
+}
+size_t tc_smem_bytes(int stages, int block_n, int esz) {
+  return 1024 + tc_region_bytes(stages, block_n, esz) + 16 * TC_MAX_STAGES + 16 + 8 * TC_BLOCK_M + 64;
 }
 
 }  // namespace
@@ -359,7 +430,7 @@ bool conv_tc_supported(const ConvArgs& a, int tf32) {
   return a.Cin % half == 0 && a.Cout % 16 == 0 && a.ld_out % 8 == 0 && a.out_coff % 8 == 0;
 }
 
-int conv_tc_launch(const ConvArgs& a, int tf32, int out_f32, int round_tf32, cudaStream_t st) {
+int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st) {
   if (!conv_tc_supported(a, tf32))
     return fail(HRP_ERR_INVALID, "conv_tc: unsupported shape Cin=%d Cout=%d ld=%d coff=%d", a.Cin, a.Cout, a.ld_out, a.out_coff);
   TcParams p{};
@@ -386,9 +457,13 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int out_f32, int round_tf32, cud
   const int smax = bn >= 256 ? 4 : (bn >= 128 ? 3 : 4);
   p.stages = std::max(1, std::min(p.num_kb, smax));
   p.lag = std::min(2, p.stages - 1);
-  p.out_f32 = out_f32;
   p.round_tf32 = round_tf32;
-  const size_t smem = tc_smem_bytes(p.stages, bn);
+  const int esz = tf32 ? 4 : 2;
+  p.bar_off = (int)tc_region_bytes(p.stages, bn, esz);
+  int cl = 0;
+  while ((16 << cl) < bn * esz) ++cl;
+  p.cpr_log = cl;
+  const size_t smem = tc_smem_bytes(p.stages, bn, esz);
   static bool attr_done[2] = {false, false};
   if (!attr_done[tf32 ? 1 : 0]) {
     if (tf32) HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -27,10 +27,10 @@ struct ConvArgs {
 int conv_f32_launch(const ConvArgs& a, cudaStream_t s);
 
 // Tensor-core family (conv_tc.cu): tcgen05.mma with bf16 (tf32 = 0) or TF32 (tf32 = 1) operands, fp32 accumulation in
-// TMEM. Activations are NHWC bf16 / fp32; `a.w` is the pack_conv_tc() image. out_f32: write fp32 NHWC from the bf16
-// family; round_tf32: round fp32 NHWC outputs to TF32 (nearest) for the next layer's operands.
+// TMEM. Activations are NHWC bf16 / fp32; `a.w` is the pack_conv_tc() image. round_tf32: round fp32 NHWC outputs to
+// TF32 (nearest) for the next layer's operands.
 bool conv_tc_supported(const ConvArgs& a, int tf32);
-int conv_tc_launch(const ConvArgs& a, int tf32, int out_f32, int round_tf32, cudaStream_t s);
+int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s);
 size_t pack_conv_tc_bytes(int K, int Cout, int tf32);
 void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, void* out);   // from pack_conv_f32's [K][Cout]
 int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t s);

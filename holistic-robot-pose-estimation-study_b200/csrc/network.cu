@@ -9,6 +9,7 @@
 //   kinematics    FK (+ re-rooting) and both pinhole projections                                  447-450, function.py:140
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -742,6 +743,7 @@ struct IoPtrs {
 struct Profile {
   float* ms; int64_t* launches; double* flops;
   cudaEvent_t e0, e1;
+  FILE* dump = nullptr;    // HRP_DUMP_OPS=<path>: one CSV line per op (development / profiles/)
 };
 
 int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* prof) {
@@ -781,7 +783,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         a.KH = o.KH; a.KW = o.KW; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w;
         a.out_sy = o.out_sy; a.out_sx = o.out_sx; a.out_oy = o.out_oy; a.out_ox = o.out_ox; a.Ho_full = o.Ho_full; a.Wo_full = o.Wo_full;
         a.relu = o.relu; a.out_nchw = o.out_nchw; a.ld_out = o.ld; a.out_coff = 0; a.res_after_act = o.res_after_act;
-        if (o.cls == CLS_CONV_TC) HRP_TRY(conv_tc_launch(a, tf32, 0, tf32 && !o.out_nchw, st));
+        if (o.cls == CLS_CONV_TC) HRP_TRY(conv_tc_launch(a, tf32, tf32 && !o.out_nchw, st));
         else HRP_TRY(conv_f32_launch(a, st));
         break;
       }
@@ -828,6 +830,9 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
       float ms = 0.f;
       HRP_CUDA(cudaEventElapsedTime(&ms, prof->e0, prof->e1));
       prof->ms[o.cls] += ms; prof->launches[o.cls] += n_launch; prof->flops[o.cls] += o.flops * B;
+      if (prof->dump)
+        fprintf(prof->dump, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.3f\n", (int)o.kind, o.cls, B, o.Hi, o.Wi, o.Cin, o.Ho, o.Wo, o.Cout, o.KH,
+                o.stride, o.res >= 0 ? 1 : 0, o.out_nchw, ms, ms > 0 ? o.flops * B / (ms * 1e-3) / 1e12 : 0.0);
     }
   }
   h->last_launches = launches;
@@ -997,7 +1002,12 @@ extern "C" int hrp_forward_profile(hrp_handle* h, const float* x_reg, const floa
   Profile prof{ms_by_class, launches_by_class, flops_by_class, nullptr, nullptr};
   HRP_CUDA(cudaEventCreate(&prof.e0));
   HRP_CUDA(cudaEventCreate(&prof.e1));
+  if (const char* path = getenv("HRP_DUMP_OPS")) {
+    prof.dump = fopen(path, "w");
+    if (prof.dump) fprintf(prof.dump, "kind,cls,B,Hi,Wi,Cin,Ho,Wo,Cout,k,stride,res,nchw,ms,tflops\n");
+  }
   const int rs = run_ops(h, p, IoPtrs{x_reg, x_root, k_value, Kmat, out}, (cudaStream_t)stream, &prof);
+  if (prof.dump) fclose(prof.dump);
   cudaEventDestroy(prof.e0);
   cudaEventDestroy(prof.e1);
   return rs;
@@ -1068,7 +1078,7 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
     if (rs == HRP_OK) rs = tf32 ? round_tf32_launch(in, static_cast<float*>(din), n_in, st) : cast_f32_to_bf16_launch(in, din, n_in, st);
     if (rs == HRP_OK && residual) rs = tf32 ? round_tf32_launch(residual, static_cast<float*>(dres), n_out, st) : cast_f32_to_bf16_launch(residual, dres, n_out, st);
     a.in = din; a.w = dw; a.res = dres; a.out = dout;
-    if (rs == HRP_OK) rs = conv_tc_launch(a, tf32, 0, tf32, st);
+    if (rs == HRP_OK) rs = conv_tc_launch(a, tf32, tf32, st);
     if (rs == HRP_OK && !tf32) rs = cast_bf16_to_f32_launch(dout, out, n_out, st);
   }
   if (cudaStreamSynchronize(st) != cudaSuccess && rs == HRP_OK) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: %s", cudaGetErrorString(cudaGetLastError()));

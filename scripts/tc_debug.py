@@ -68,6 +68,11 @@ if __name__ == "__main__":
             (1, 8, 1024, 2048, 1, 1, True, True),
             (5, 17, 64, 80, 3, 2, True, True),       # ragged M, Cout = 16*5
             (2, 64, 256, 448, 1, 1, False, False),   # heatmap conv shape
+            (64, 8, 512, 2048, 1, 1, True, True),    # BLOCK_N = 256
+            (64, 8, 512, 512, 3, 1, True, True),     # K = 4608: many barrier phase wraps
+            (16, 16, 1024, 512, 1, 2, True, True),   # 1x1 stride 2 (ResNet downsample)
+            (64, 16, 256, 256, 3, 2, True, True),
+            (64, 32, 64, 128, 3, 1, True, True),     # BLOCK_N = 128
         ]
         for c in ladder:
             try:

@@ -148,6 +148,33 @@ def test_conv_layer_against_torch_fp32(B, H, Cin, Cout, k, stride, dev):
     assert helpers.maxdiff(out, ref) < 2e-5 * max(1.0, float(ref.abs().max()))
 
 
+def _round_like(x, prec):
+    if prec == "bf16":
+        return x.bfloat16().float()
+    return ((x.view(torch.int32) + 0x1000) & ~0x1fff).view(torch.float32)       # cvt.rna.tf32.f32
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride", [(1, 16, 64, 32, 1, 1), (2, 64, 32, 32, 3, 1), (3, 32, 64, 64, 3, 1),
+                                                    (2, 16, 128, 128, 3, 1), (2, 8, 256, 256, 3, 1), (2, 32, 32, 64, 3, 2),
+                                                    (1, 8, 1024, 2048, 1, 1), (5, 17, 64, 80, 3, 2), (2, 64, 256, 448, 1, 1)])
+def test_conv_layer_tensor_core_families(prec, B, H, Cin, Cout, k, stride, dev):
+    """tcgen05 implicit GEMM (conv_tc.cu) against a float64 conv on operands rounded to the family's type: the only
+    differences left are fp32 accumulation order and the rounding of the stored output (bf16: 2^-8, TF32: 2^-11 rel)."""
+    from hrp_b200.model import conv2d_nhwc
+    g = torch.Generator().manual_seed(B * 1000 + Cin + k)
+    x = _round_like(torch.randn(B, H, H, Cin, generator=g), prec)
+    w = _round_like(torch.randn(Cout, Cin, k, k, generator=g) / (k * k * Cin) ** 0.5, prec)
+    b = torch.randn(Cout, generator=g)
+    pad = k // 2
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride, pad)
+    res = _round_like(torch.randn(ref.shape, generator=g), prec)
+    ref = torch.relu(ref + res.double()).permute(0, 2, 3, 1).contiguous()
+    out = conv2d_nhwc(x.to(dev), w.to(dev), b.to(dev), res.permute(0, 2, 3, 1).contiguous().to(dev), stride, pad, True, prec)
+    tol = (2.0 ** -8 if prec == "bf16" else 2.0 ** -11) * (1.0 + ref.abs()) * 1.01 + 2e-5
+    assert bool(((out.cpu().double() - ref).abs() <= tol).all())
+
+
 # ---------------------------------------------------------------------------------------------------- full network
 _models = {}
 
@@ -223,3 +250,30 @@ def test_fullnet_batch64_frames_are_independent(dev):
     kv2 = torch.sqrt(K[:2, 0, 0] * K[:2, 1, 1] * 1e6 / 256.0 ** 2)
     ref2 = om.forward_dict(img[:2], img[:2], kv2, K[:2])
     check_gates(auto, ref2)
+
+
+# bf16 family: separately stated tolerance (north_star). Measured on B200 against the fp32 reference goldens; the gates
+# below carry ~2x margin over the worst case seen (see DESIGN.md "Precision families").
+BF16_TOL = dict(joint_angles=1e-2, root_depth=1e-2, px=2.0, rot6d=1e-2, uvd=5e-3, m3d=2e-2)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("robot,backbone", helpers.FULLNET_CASES)
+def test_fullnet_tensor_core_families_against_reference_golden(prec, robot, backbone, dev):
+    g = helpers.load_golden("fullnet_%s_%s.npz" % (robot, backbone))
+    wseed, seed, B = (int(v) for v in g["meta"])
+    m = gpu_model(robot, backbone, dev, prec)
+    img, K, kv = helpers.inputs(B, seed)
+    out = m.forward_dict(img.to(dev), K.to(dev), kv.to(dev))
+    names = ["joint_angles", "rot6d", "trans", "root_uv", "root_depth", "uvd", "kp3d_int", "kp3d_fk", "kp2d_int", "kp2d_fk"]
+    d = {k: helpers.maxdiff(out[k], g[k]) for k in names}
+    print(prec, robot, backbone, {k: "%.2e" % v for k, v in d.items()})
+    if prec == "tf32":          # TF32-parity mode: the north_star gates themselves
+        assert d["joint_angles"] < helpers.TOL_RAD and d["root_depth"] < helpers.TOL_DEPTH_M, d
+        assert max(d["kp2d_int"], d["kp2d_fk"], d["root_uv"]) < helpers.TOL_PX, d
+    else:
+        t = BF16_TOL
+        assert d["joint_angles"] < t["joint_angles"] and d["root_depth"] < t["root_depth"] and d["rot6d"] < t["rot6d"], d
+        assert max(d["kp2d_int"], d["kp2d_fk"], d["root_uv"]) < t["px"] and d["uvd"] < t["uvd"], d
+        assert max(d["kp3d_int"], d["kp3d_fk"], d["trans"]) < t["m3d"], d
+    assert m.launch_count() > 300
