@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -30,8 +31,11 @@ constexpr int TC_BLOCK_M = 128;
 constexpr int TC_ROW_BYTES = 128;                          // one swizzle-128B row of K
 constexpr int TC_A_STAGE = TC_BLOCK_M * TC_ROW_BYTES;      // 16 KB
 constexpr int TC_PRODUCERS = 128;
-constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_STAGES = 6;
+// threads: 4 producer warps + MMA warp + weight-loader warp + EPI epilogue warps (4, or 8 = two per TMEM lane quarter)
+constexpr int tc_threads(int epi_warps) { return 192 + 32 * epi_warps; }
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_LAG = 6;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
 
 struct TcParams {
   ConvArgs a;
@@ -42,7 +46,9 @@ struct TcParams {
   int stages;
   int lag;           // cp.async groups kept in flight per producer thread (< stages)
   int tmem_cols;     // power of two >= max(32, block_n)
-  int bar_off;       // byte offset of the barrier block (after the operand stages and the epilogue staging tile)
+  int tiles_n, total_tiles;
+  int stg_off;       // byte offset of the epilogue staging tile (after the operand stages)
+  int bar_off;       // byte offset of the barrier block
   int cpr_log;       // log2 of 16-byte chunks per staged tile row (block_n * elem / 16)
   int round_tf32;    // round fp32 NHWC outputs to TF32 (nearest, ties away) so the next MMA sees exact operands
 };
@@ -73,6 +79,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+// for waiters off the critical path: back off between polls so the spinning warp leaves issue slots to the producers
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -139,10 +150,24 @@ __device__ __forceinline__ float round_tf32_rna(float x) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the four epilogue warps
+template <int EPI>
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory"); }   // the epilogue warps
 
-template <bool TF32>
-__global__ void __launch_bounds__(TC_THREADS, 3)
+template <int N>
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {      // cp.async.wait_group takes an immediate
+  if constexpr (N == 0) {
+    cp_async_wait<0>();
+  } else {
+    if (n >= N) cp_async_wait<N>(); else cp_async_wait_dyn<N - 1>(n);
+  }
+}
+
+// Persistent, warp-specialised: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (N tile fastest, so
+// co-resident CTAs share the activation rows they gather). The operand ring and both pipelines run across tile
+// boundaries: producers are already gathering tile i+1 while the MMA warp finishes tile i and the epilogue warps drain
+// the other TMEM accumulator buffer.
+template <bool TF32, int EPI>
+__global__ void __launch_bounds__(tc_threads(EPI), EPI == 4 ? 2 : 1)
 conv_tc_kernel(const TcParams p) {
   constexpr int ESZ = TF32 ? 4 : 2;
   constexpr int KB = TC_ROW_BYTES / ESZ;     // K elements per k-block (64 bf16 / 32 tf32)
@@ -155,20 +180,20 @@ conv_tc_kernel(const TcParams p) {
   const int b_stage = p.block_n * TC_ROW_BYTES;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + (uint32_t)S * TC_A_STAGE;
-  const uint32_t sBar = smem_base + (uint32_t)p.bar_off;  // full[S], empty[S], tmem_full, tmem_ptr, row offsets[128]
-  const uint32_t bar_full = sBar, bar_empty = sBar + 8u * S, bar_acc = sBar + 16u * S, tmem_slot = bar_acc + 8u;
-  const uint32_t s_rowoff = sBar + 16u * TC_MAX_STAGES + 16u;
+  const uint32_t stg = smem_base + (uint32_t)p.stg_off;   // epilogue staging tile: 128 rows x (block_n*ESZ + 16) bytes
+  const uint32_t sBar = smem_base + (uint32_t)p.bar_off;  // full[S], empty[S], acc_full[2], acc_empty[2], tmem slot, row offsets
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8u * TC_MAX_STAGES, bar_accf = sBar + 16u * TC_MAX_STAGES,
+                 bar_acce = bar_accf + 16u, tmem_slot = bar_acce + 16u, s_rowoff = tmem_slot + 16u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const ConvArgs& a = p.a;
-  const int m0 = blockIdx.x * TC_BLOCK_M, n0 = blockIdx.y * p.block_n;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8u * s, TC_PRODUCERS + 1);
       mbar_init(bar_empty + 8u * s, 1);
     }
-    mbar_init(bar_acc, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8u * i, 1); mbar_init(bar_acce + 8u * i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -180,105 +205,173 @@ conv_tc_kernel(const TcParams p) {
 
   if (warp < 4) {
     // ===== producers: im2col gather. One warp instruction covers 4 tile rows x 128 contiguous bytes (lane = 8*row + chunk),
-    // so every request touches 4 cache lines instead of 32; a thread serves chunk `j` of 8 rows of its warp's 32. ==========
-    {
-      const int j = lane & 7, rsub = lane >> 3;
-      int iy0[8], ix0[8], boff[8];
-      uint32_t okmask = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + warp * 32 + i * 4 + rsub;
+    // so every request touches 4 cache lines instead of 32; a thread serves chunk `j` of 8 rows of its warp's 32.
+    // Per tile, lane l first describes tile row warp*32+l as {byte offset of tap (0,0), bitmask of in-image taps} in
+    // shared memory; the gather loop then costs one AND, one select and one add per 16-byte copy. ======================
+    const int j = lane & 7, rsub = lane >> 3;
+    const uint32_t dst0 = (uint32_t)(warp * 32 + rsub) * TC_ROW_BYTES;
+    const uint32_t sw_even = ((uint32_t)j ^ (uint32_t)rsub) << 4, sw_odd = ((uint32_t)j ^ (uint32_t)(4 | rsub)) << 4;
+    const uint32_t s_info = s_rowoff + 8u * TC_BLOCK_M;       // 128 x {int32 offset, uint32 tap mask}
+    const uint8_t* in8 = static_cast<const uint8_t*>(a.in);
+    const int lag = p.lag;
+    const int hw_o = a.Ho * a.Wo;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.tiles_n) * TC_BLOCK_M;
+      const int b0 = m0 / hw_o;                                // first image this tile touches
+      const uint8_t* tile_base = in8 + (size_t)b0 * a.Hi * a.Wi * a.Cin * ESZ;
+      {
+        const int m = m0 + warp * 32 + lane;
         const bool ok = m < p.M;
-        const int mm = ok ? m : 0;
+        const int mm = ok ? m : m0;
         const int ox = mm % a.Wo, t1 = mm / a.Wo, oy = t1 % a.Ho, b = t1 / a.Ho;
-        iy0[i] = oy * a.stride - a.pad_h;
-        ix0[i] = ox * a.stride - a.pad_w;
-        boff[i] = b * a.Hi * a.Wi;
-        okmask |= (ok ? 1u : 0u) << i;
+        const int iy0 = oy * a.stride - a.pad_h, ix0 = ox * a.stride - a.pad_w;
+        uint32_t xmask = 0, mask = 0;
+        for (int fs = 0; fs < a.KW; ++fs) xmask |= ((ix0 + fs >= 0 && ix0 + fs < a.Wi) ? 1u : 0u) << fs;
+        for (int fr = 0; fr < a.KH; ++fr)
+          if (iy0 + fr >= 0 && iy0 + fr < a.Hi) mask |= xmask << (fr * a.KW);
+        if (!ok) mask = 0;
+        const int off0 = (((b - b0) * a.Hi + iy0) * a.Wi + ix0) * a.Cin * ESZ;
+        __syncwarp();                                          // previous tile's descriptors have been consumed
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_info + 8u * (uint32_t)(warp * 32 + lane)), "r"(off0), "r"(mask) : "memory");
+        __syncwarp();
       }
-      const uint32_t dst0 = (uint32_t)(warp * 32 + rsub) * TC_ROW_BYTES;
+      int off0[8];
+      uint32_t tmask[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(off0[i]), "=r"(tmask[i]) : "r"(s_info + 8u * (uint32_t)(warp * 32 + i * 4 + rsub)));
       int c = j * CE, fr = 0, fs = 0, kthr = j * CE;
       while (c >= a.Cin) { c -= a.Cin; if (++fs == a.KW) { fs = 0; ++fr; } }
-      const uint8_t* in8 = static_cast<const uint8_t*>(a.in);
-      const int lag = p.lag;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % S;
-        if (kb >= S) mbar_wait(bar_empty + 8u * s, ((kb / S) & 1) ^ 1);
+      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int s = it % S;
+        if (it >= S) mbar_wait_relaxed(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
         if (kthr < p.Ktot) {
-          const uint32_t dst_s = sA + (uint32_t)s * TC_A_STAGE + dst0;
+          const uint32_t dst_e = sA + (uint32_t)s * TC_A_STAGE + dst0 + sw_even, dst_o = sA + (uint32_t)s * TC_A_STAGE + dst0 + sw_odd;
+          const uint32_t tapbit = 1u << (fr * a.KW + fs);
+          const int dtap = ((fr * a.Wi + fs) * a.Cin + c) * ESZ;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int iy = iy0[i] + fr, ix = ix0[i] + fs;
-            const bool ok = ((okmask >> i) & 1u) && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi;
-            const uint8_t* src = ok ? in8 + ((size_t)(boff[i] + iy * a.Wi + ix) * a.Cin + c) * ESZ : in8;
-            // row r = warp*32 + i*4 + rsub: r & 7 = ((i & 1) << 2) | rsub
-            cp_async16(dst_s + (uint32_t)i * (4 * TC_ROW_BYTES) + (((uint32_t)j ^ (uint32_t)(((i & 1) << 2) | rsub)) << 4), src, ok ? 16u : 0u);
+            const bool ok = (tmask[i] & tapbit) != 0;
+            const int off = ok ? off0[i] + dtap : 0;
+            cp_async16(((i & 1) ? dst_o : dst_e) + (uint32_t)i * (4 * TC_ROW_BYTES), tile_base + off, ok ? 16u : 0u);
           }
         }
         kthr += KB;
         c += KB;
         while (c >= a.Cin) { c -= a.Cin; if (++fs == a.KW) { fs = 0; ++fr; } }
         cp_async_commit();
-        if (kb >= lag) {
-          if (lag == 2) cp_async_wait<2>(); else if (lag == 1) cp_async_wait<1>(); else cp_async_wait<0>();
+        if (it >= lag) {
+          cp_async_wait_dyn<TC_MAX_LAG>(lag);
           fence_proxy_async();
-          mbar_arrive(bar_full + 8u * ((kb - lag) % S));
+          mbar_arrive(bar_full + 8u * ((it - lag) % S));
         }
       }
-      cp_async_wait<0>();
-      fence_proxy_async();
-      for (int kb = max(p.num_kb - lag, 0); kb < p.num_kb; ++kb) mbar_arrive(bar_full + 8u * (kb % S));
     }
-
-    // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> global ========================================
-    // thread `tid` owns tile row `tid` (TMEM lane tid)
-    const int m = m0 + tid;
-    const bool row_ok = m < p.M;
-    const int mm = row_ok ? m : 0;
-    const int ox = mm % a.Wo, t1 = mm / a.Wo, oy = t1 % a.Ho, b = t1 / a.Ho;
-    const int y = oy * a.out_sy + a.out_oy, x = ox * a.out_sx + a.out_ox;
-    const size_t pix = ((size_t)b * a.Ho_full + y) * a.Wo_full + x;
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    if (a.out_nchw) {
-      // fp32 [B,Cout,Ho,Wo] (heatmap logits for the integral layer): lanes hold adjacent pixels, stores are coalesced
-      mbar_wait(bar_acc, 0);
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int k = max(it - lag, 0); k < it; ++k) mbar_arrive(bar_full + 8u * (k % S));
+  } else if (warp == 4) {
+    // ===== MMA issuer ===================================================================================================
+    const uint32_t idesc = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                           ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    int it = 0, li = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+      const int buf = li & 1;
+      if (li >= 2) mbar_wait(bar_acce + 8u * buf, ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
-      float* op = static_cast<float*>(a.out) + (((size_t)b * a.Cout + n0) * a.Ho_full + y) * a.Wo_full + x;
-      const size_t cs = (size_t)a.Ho_full * a.Wo_full;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t v[16];
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.block_n);
+      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(bar_full + 8u * s, (it / S) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const int kleft = p.Ktot - kb * KB;
+          const int nk = (kleft >= KB ? KB : kleft) / UK;
+          const uint64_t da = umma_desc(sA + (uint32_t)s * TC_A_STAGE), db = umma_desc(sB + (uint32_t)s * b_stage);
+          for (int kk = 0; kk < nk; ++kk) umma<TF32>(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0);
+          umma_commit(bar_empty + 8u * s);                     // frees the stage once these MMAs have read it
+          if (kb == p.num_kb - 1) umma_commit(bar_accf + 8u * buf);   // accumulator complete
+        }
         __syncwarp();
-        tmem_ld16(t_row + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
-          float f0 = __uint_as_float(v[q * 4 + 0]) + bq.x, f1 = __uint_as_float(v[q * 4 + 1]) + bq.y;
-          float f2 = __uint_as_float(v[q * 4 + 2]) + bq.z, f3 = __uint_as_float(v[q * 4 + 3]) + bq.w;
-          if (a.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
-          op[(size_t)(c0 + q * 4 + 0) * cs] = f0; op[(size_t)(c0 + q * 4 + 1) * cs] = f1;
-          op[(size_t)(c0 + q * 4 + 2) * cs] = f2; op[(size_t)(c0 + q * 4 + 3) * cs] = f3;
+      }
+    }
+  } else if (warp == 5) {
+    // ===== weight loader: [kb][Cout][128 B] pre-swizzled; one bulk copy per k-block ===================================
+    if (lane == 0) {
+      const size_t kb_stride = (size_t)a.Cout * TC_ROW_BYTES;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.tiles_n) * p.block_n;
+        const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)n0 * TC_ROW_BYTES;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % S;
+          if (it >= S) mbar_wait_relaxed(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8u * s, (uint32_t)b_stage);
+          bulk_g2s(sB + (uint32_t)s * b_stage, wsrc + kb * kb_stride, (uint32_t)b_stage, bar_full + 8u * s);
         }
       }
-    } else {
-      // NHWC: stage the 128 x BLOCK_N tile in shared memory (the operand stages are free once the accumulator is
-      // complete) so that residual loads and output stores run as 16-byte chunks along the channel axis.
-      const uint32_t pitch = (uint32_t)p.block_n * ESZ + 16u;          // odd multiple of 16 B: conflict-free both ways
-      const uint32_t cpr_log = (uint32_t)p.cpr_log;                     // log2(16-byte chunks per tile row)
-      const uint32_t cpr = 1u << cpr_log;
-      const uint32_t stg = smem_base;
-      {
-        const long long off = row_ok ? (long long)(pix * a.ld_out + a.out_coff + n0) : -1ll;
-        asm volatile("st.shared.b64 [%0], %1;" ::"r"(s_rowoff + 8u * tid), "l"(off) : "memory");
+    }
+  } else {
+    // ===== epilogue warps 6..: TMEM -> registers -> (+bias, +residual, ReLU) -> global ================================
+    // a warp may only touch TMEM lanes 32*(warp%4)..+31; thread (et, eh) owns tile row `et`, column half `eh`
+    constexpr int EPI_T = 32 * EPI, EPI_H = EPI / 4;
+    const int et = (warp & 3) * 32 + lane, eh = (warp - 6) >> 2, eid = eh * 128 + et;
+    const int c_lo = (p.block_n / EPI_H) * eh, c_hi = c_lo + p.block_n / EPI_H;   // block_n / EPI_H is a multiple of 16 (block_n >= 32)
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t pitch = (uint32_t)p.block_n * ESZ + 16u;            // odd multiple of 16 B: conflict-free both ways
+    const uint32_t cpr_log = (uint32_t)p.cpr_log;                       // log2(16-byte chunks per tile row)
+    const uint32_t cpr = 1u << cpr_log;
+    const uint32_t my = stg + (uint32_t)et * pitch;
+    const bool has_res = a.res != nullptr;
+    int li = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+      const int buf = li & 1;
+      const int m0 = (tile / p.tiles_n) * TC_BLOCK_M, n0 = (tile % p.tiles_n) * p.block_n;
+      const int m = m0 + et;
+      const bool row_ok = m < p.M;
+      const int mm = row_ok ? m : 0;
+      const int ox = mm % a.Wo, t1 = mm / a.Wo, oy = t1 % a.Ho, b = t1 / a.Ho;
+      const int y = oy * a.out_sy + a.out_oy, x = ox * a.out_sx + a.out_ox;
+      const size_t pix = ((size_t)b * a.Ho_full + y) * a.Wo_full + x;
+      const uint32_t t_row = t_lane + (uint32_t)(buf * p.block_n);
+      if (a.out_nchw) {
+        // fp32 [B,Cout,Ho,Wo] (heatmap logits for the integral layer): lanes hold adjacent pixels, stores are coalesced
+        mbar_wait_relaxed(bar_accf + 8u * buf, (li >> 1) & 1);
+        tc_fence_after();
+        float* op = static_cast<float*>(a.out) + (((size_t)b * a.Cout + n0) * a.Ho_full + y) * a.Wo_full + x;
+        const size_t cs = (size_t)a.Ho_full * a.Wo_full;
+        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld16(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
+            float f0 = __uint_as_float(v[q * 4 + 0]) + bq.x, f1 = __uint_as_float(v[q * 4 + 1]) + bq.y;
+            float f2 = __uint_as_float(v[q * 4 + 2]) + bq.z, f3 = __uint_as_float(v[q * 4 + 3]) + bq.w;
+            if (a.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+            op[(size_t)(c0 + q * 4 + 0) * cs] = f0; op[(size_t)(c0 + q * 4 + 1) * cs] = f1;
+            op[(size_t)(c0 + q * 4 + 2) * cs] = f2; op[(size_t)(c0 + q * 4 + 3) * cs] = f3;
+          }
+        }
+        tc_fence_before();
+        epi_barrier<EPI>();
+        if (eid == 0) mbar_arrive(bar_acce + 8u * buf);
+        continue;
       }
-      mbar_wait(bar_acc, 0);
-      tc_fence_after();
-      epi_barrier();
-      const bool has_res = a.res != nullptr;
+      // NHWC: the 128 x BLOCK_N tile passes through a shared-memory staging tile so that residual loads and output
+      // stores run as 16-byte chunks along the channel axis; the residual is fetched while the MMAs are still running.
+      if (eh == 0) {
+        const long long off = row_ok ? (long long)(pix * a.ld_out + a.out_coff + n0) : -1ll;
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(s_rowoff + 8u * et), "l"(off) : "memory");
+      }
+      epi_barrier<EPI>();
       if (has_res) {
         const uint8_t* res8 = static_cast<const uint8_t*>(a.res);
-        for (uint32_t idx = tid; idx < (128u << cpr_log); idx += 128u) {
+        for (uint32_t idx = eid; idx < (128u << cpr_log); idx += EPI_T) {
           const uint32_t row = idx >> cpr_log, ch = idx & (cpr - 1u);
           long long off;
           asm volatile("ld.shared.b64 %0, [%1];" : "=l"(off) : "r"(s_rowoff + 8u * row));
@@ -286,10 +379,11 @@ conv_tc_kernel(const TcParams p) {
         }
         cp_async_commit();
         cp_async_wait<0>();
-        epi_barrier();
+        epi_barrier<EPI>();
       }
-      const uint32_t my = stg + (uint32_t)tid * pitch;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      mbar_wait_relaxed(bar_accf + 8u * buf, (li >> 1) & 1);
+      tc_fence_after();
+      for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_row + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -350,9 +444,11 @@ conv_tc_kernel(const TcParams p) {
           }
         }
       }
-      epi_barrier();
+      tc_fence_before();
+      epi_barrier<EPI>();
+      if (eid == 0) mbar_arrive(bar_acce + 8u * buf);         // accumulator buffer may be overwritten by tile li+2
       uint8_t* out8 = static_cast<uint8_t*>(a.out);
-      for (uint32_t idx = tid; idx < (128u << cpr_log); idx += 128u) {
+      for (uint32_t idx = eid; idx < (128u << cpr_log); idx += EPI_T) {
         const uint32_t row = idx >> cpr_log, ch = idx & (cpr - 1u);
         long long off;
         asm volatile("ld.shared.b64 %0, [%1];" : "=l"(off) : "r"(s_rowoff + 8u * row));
@@ -362,37 +458,10 @@ conv_tc_kernel(const TcParams p) {
           *reinterpret_cast<uint4*>(out8 + (size_t)off * ESZ + (ch << 4)) = t;
         }
       }
-    }
-    tc_fence_before();
-  } else if (warp == 4) {
-    // ===== MMA issuer ===================================================================================================
-    const uint32_t idesc = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
-                           ((uint32_t)(TC_BLOCK_M >> 4) << 24);
-    for (int kb = 0; kb < p.num_kb; ++kb) {
-      const int s = kb % S;
-      mbar_wait(bar_full + 8u * s, (kb / S) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const int kleft = p.Ktot - kb * KB;
-        const int nk = (kleft >= KB ? KB : kleft) / UK;
-        const uint64_t da = umma_desc(sA + (uint32_t)s * TC_A_STAGE), db = umma_desc(sB + (uint32_t)s * b_stage);
-        for (int kk = 0; kk < nk; ++kk) umma<TF32>(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0);
-        umma_commit(bar_empty + 8u * s);                     // frees the stage once these MMAs have read it
-        if (kb == p.num_kb - 1) umma_commit(bar_acc);        // accumulator complete
-      }
-      __syncwarp();
-    }
-  } else if (lane == 0) {
-    // ===== weight loader: [kb][Cout][128 B] pre-swizzled; one bulk copy per k-block ===================================
-    const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)n0 * TC_ROW_BYTES;
-    const size_t kb_stride = (size_t)a.Cout * TC_ROW_BYTES;
-    for (int kb = 0; kb < p.num_kb; ++kb) {
-      const int s = kb % S;
-      if (kb >= S) mbar_wait(bar_empty + 8u * s, ((kb / S) & 1) ^ 1);
-      mbar_arrive_expect_tx(bar_full + 8u * s, (uint32_t)b_stage);
-      bulk_g2s(sB + (uint32_t)s * b_stage, wsrc + kb * kb_stride, (uint32_t)b_stage, bar_full + 8u * s);
+      epi_barrier<EPI>();                                           // staging tile and row offsets are reused by the next tile
     }
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
@@ -413,21 +482,23 @@ __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restric
   if (i < n) out[i] = round_tf32_rna(in[i]);
 }
 
-// operand stages and the epilogue staging tile share one region; barriers, the TMEM slot and row offsets follow it
-size_t tc_region_bytes(int stages, int block_n, int esz) {
-  const size_t ops = (size_t)stages * (TC_A_STAGE + block_n * TC_ROW_BYTES);
-  const size_t stg = (size_t)TC_BLOCK_M * (block_n * esz + 16);
-  return (std::max(ops, stg) + 127) / 128 * 128;
-}
+size_t tc_stage_bytes(int block_n) { return (size_t)TC_A_STAGE + (size_t)block_n * TC_ROW_BYTES; }
+size_t tc_staging_bytes(int block_n, int esz) { return ((size_t)TC_BLOCK_M * (block_n * esz + 16) + 127) / 128 * 128; }
+size_t tc_tail_bytes() { return 16 * TC_MAX_STAGES + 16 + 16 + 16 + 8 * TC_BLOCK_M + 8 * TC_BLOCK_M + 64; }
 size_t tc_smem_bytes(int stages, int block_n, int esz) {
-  return 1024 + tc_region_bytes(stages, block_n, esz) + 16 * TC_MAX_STAGES + 16 + 8 * TC_BLOCK_M + 64;
+  return 1024 + stages * tc_stage_bytes(block_n) + tc_staging_bytes(block_n, esz) + tc_tail_bytes();
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
 
 }  // namespace
 
 bool conv_tc_supported(const ConvArgs& a, int tf32) {
   const int half = tf32 ? 16 : 32;
-  return a.Cin % half == 0 && a.Cout % 16 == 0 && a.ld_out % 8 == 0 && a.out_coff % 8 == 0;
+  return a.Cin % half == 0 && a.Cout % 32 == 0 && a.ld_out % 8 == 0 && a.out_coff % 8 == 0 && a.KH * a.KW <= 32;
 }
 
 int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st) {
@@ -437,42 +508,69 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   p.a = a;
   p.M = a.B * a.Ho * a.Wo;
   if (p.M <= 0) return HRP_OK;
+  const int esz = tf32 ? 4 : 2;
   const int kb_elems = tf32 ? 32 : 64;
   p.Ktot = a.KH * a.KW * a.Cin;
   p.num_kb = ceil_div(p.Ktot, kb_elems);
   const int mtiles = ceil_div(p.M, TC_BLOCK_M);
-  // widest N tile that still gives every SM about two CTAs; never below 32 columns (one TMEM allocation granule)
+  const int sms = sm_count();
+  // N tile: every CTA re-gathers its activation rows, so wide tiles cut the gather traffic; take the widest that still
+  // leaves about one tile per SM, else the narrowest. (TF32: <= 128 so the fp32 staging tile fits beside the stages.)
+  static const int force_bn = env_int("HRP_TC_BN", 0), force_stages = env_int("HRP_TC_STAGES", 0), force_ctas = env_int("HRP_TC_CTAS", 0);
   const int cand[4] = {256, 128, 64, 32};
   int bn = 0;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = tf32 ? 1 : 0; i < 4; ++i) {
     if (a.Cout % cand[i]) continue;
     bn = cand[i];
-    if ((long long)mtiles * (a.Cout / cand[i]) >= 2LL * sm_count()) break;
+    if ((long long)mtiles * (a.Cout / cand[i]) >= (sms * 4) / 5) break;
   }
-  if (bn == 0) bn = 16;                                     // Cout = 16 * odd
+  if (bn == 0) return fail(HRP_ERR_INVALID, "conv_tc: Cout=%d must be a multiple of 32", a.Cout);
+  if (force_bn && a.Cout % force_bn == 0 && (!tf32 || force_bn <= 128)) bn = force_bn;
   p.block_n = bn;
+  p.tiles_n = a.Cout / bn;
+  p.total_tiles = mtiles * p.tiles_n;
   int tm = 32;
-  while (tm < bn) tm <<= 1;
+  while (tm < 2 * bn) tm <<= 1;                             // two accumulator buffers
   p.tmem_cols = tm;
-  const int smax = bn >= 256 ? 4 : (bn >= 128 ? 3 : 4);
-  p.stages = std::max(1, std::min(p.num_kb, smax));
-  p.lag = std::min(2, p.stages - 1);
+  // CTAs per SM: two when there are enough tiles and two CTAs' shared memory / TMEM fit, else one with a deep ring
+  // epilogue-heavy tiles (wide N, short K) get eight epilogue warps and the SM to themselves
+  static const int force_epi = env_int("HRP_TC_EPI", 0);
+  int epi = (bn >= 128 && p.num_kb <= 4) ? 8 : 4;
+  if (force_epi == 4 || force_epi == 8) epi = force_epi;
+  int ctas = (epi == 4 && p.total_tiles >= 2 * sms && tm <= 256) ? 2 : 1;
+  if (force_ctas) ctas = (epi == 4 && force_ctas == 2 && tm <= 256) ? 2 : 1;
+  const size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 1024 : 0);
+  const size_t fixed = 1024 + tc_staging_bytes(bn, esz) + tc_tail_bytes();
+  int smax = (int)((budget - fixed) / tc_stage_bytes(bn));
+  smax = std::max(1, std::min(smax, TC_MAX_STAGES));
+  if (force_stages) smax = std::max(1, std::min(force_stages, smax));
+  p.stages = smax;                                          // the ring runs across tiles, so depth is not tied to num_kb
+  if ((long long)p.num_kb * ceil_div(p.total_tiles, sms * ctas) < p.stages) p.stages = std::max(1, p.num_kb * ceil_div(p.total_tiles, sms * ctas));
+  p.lag = std::min(TC_MAX_LAG, p.stages - 1);
   p.round_tf32 = round_tf32;
-  const int esz = tf32 ? 4 : 2;
-  p.bar_off = (int)tc_region_bytes(p.stages, bn, esz);
+  p.stg_off = (int)(p.stages * tc_stage_bytes(bn));
+  p.bar_off = p.stg_off + (int)tc_staging_bytes(bn, esz);
   int cl = 0;
   while ((16 << cl) < bn * esz) ++cl;
   p.cpr_log = cl;
   const size_t smem = tc_smem_bytes(p.stages, bn, esz);
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[tf32 ? 1 : 0]) {
-    if (tf32) HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    else HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done[tf32 ? 1 : 0] = true;
+  if (smem > (size_t)TC_SMEM_LIMIT) return fail(HRP_ERR_INVALID, "conv_tc: %zu bytes of shared memory needed (block_n %d)", smem, bn);
+  static bool attr_done = false;
+  if (!attr_done) {
+    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    attr_done = true;
   }
-  dim3 grid(mtiles, a.Cout / bn);
-  if (tf32) conv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
-  else conv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
+  const int grid = std::min(p.total_tiles, sms * ctas);
+  if (tf32) {
+    if (epi == 8) conv_tc_kernel<true, 8><<<grid, tc_threads(8), smem, st>>>(p);
+    else conv_tc_kernel<true, 4><<<grid, tc_threads(4), smem, st>>>(p);
+  } else {
+    if (epi == 8) conv_tc_kernel<false, 8><<<grid, tc_threads(8), smem, st>>>(p);
+    else conv_tc_kernel<false, 4><<<grid, tc_threads(4), smem, st>>>(p);
+  }
   HRP_CHECK_LAUNCH("conv_tc_kernel");
   return HRP_OK;
 }

@@ -66,7 +66,7 @@ if __name__ == "__main__":
             (2, 8, 256, 256, 3, 1, True, True),
             (2, 32, 32, 64, 3, 2, True, True),
             (1, 8, 1024, 2048, 1, 1, True, True),
-            (5, 17, 64, 80, 3, 2, True, True),       # ragged M, Cout = 16*5
+            (5, 17, 64, 96, 3, 2, True, True),       # ragged M, Cout = 32*3
             (2, 64, 256, 448, 1, 1, False, False),   # heatmap conv shape
             (64, 8, 512, 2048, 1, 1, True, True),    # BLOCK_N = 256
             (64, 8, 512, 512, 3, 1, True, True),     # K = 4608: many barrier phase wraps
