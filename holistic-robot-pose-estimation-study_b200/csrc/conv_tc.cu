@@ -14,6 +14,7 @@
 //   warp 4     allocates TMEM, then one elected lane issues the tcgen05.mma stream and commits stages back.
 //   warp 5     one lane streams pre-swizzled weight tiles with cp.async.bulk (mbarrier complete_tx).
 // Stages hand over through mbarriers: full[s] (128 producer arrivals + 1 expect_tx arrival), empty[s] (tcgen05.commit).
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -38,7 +39,10 @@ constexpr int TC_MAX_LAG = 6;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 
 struct TcParams {
+  alignas(64) unsigned char tmap[128];   // CUtensorMap of the NHWC input (TMA mode)
   ConvArgs a;
+  int tma;           // 1: activations arrive by cp.async.bulk.tensor (one thread), 0: cp.async gather (four warps)
+  int row_bytes;     // bytes of K per operand row: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B, Cin*elem == 64 in TMA mode)
   int M;             // B*Ho*Wo
   int Ktot;          // KH*KW*Cin (elements)
   int num_kb;        // ceil(Ktot / elements per 128-byte row)
@@ -83,10 +87,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // for waiters off the critical path: back off between polls so the spinning warp leaves issue slots to the producers
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+  while (!mbar_try_wait(bar, parity)) __nanosleep(20);
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -139,8 +143,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(ignored)=1 | SBO = 1024 B
 // (one 8-row group) | version 1 | layout 2. Stepping K inside the 128-byte row adds bytes>>4 to the start field.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int row_bytes) {
+  const uint64_t sbo = (uint64_t)(8 * row_bytes) >> 4;       // one 8-row group
+  const uint64_t layout = row_bytes == 128 ? 2ull : 4ull;    // SWIZZLE_128B : SWIZZLE_64B
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
 }
 
 __device__ __forceinline__ float round_tf32_rna(float x) {
@@ -168,7 +180,7 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {      // cp.async.wait
 // the other TMEM accumulator buffer.
 template <bool TF32, int EPI>
 __global__ void __launch_bounds__(tc_threads(EPI), EPI == 4 ? 2 : 1)
-conv_tc_kernel(const TcParams p) {
+conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int ESZ = TF32 ? 4 : 2;
   constexpr int KB = TC_ROW_BYTES / ESZ;     // K elements per k-block (64 bf16 / 32 tf32)
   constexpr int CE = 16 / ESZ;               // elements per 16-byte chunk
@@ -177,9 +189,9 @@ conv_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
-  const int b_stage = p.block_n * TC_ROW_BYTES;
+  const int a_stage = TC_BLOCK_M * p.row_bytes, b_stage = p.block_n * p.row_bytes;
   const uint32_t sA = smem_base;
-  const uint32_t sB = sA + (uint32_t)S * TC_A_STAGE;
+  const uint32_t sB = sA + (uint32_t)(S * a_stage);
   const uint32_t stg = smem_base + (uint32_t)p.stg_off;   // epilogue staging tile: 128 rows x (block_n*ESZ + 16) bytes
   const uint32_t sBar = smem_base + (uint32_t)p.bar_off;  // full[S], empty[S], acc_full[2], acc_empty[2], tmem slot, row offsets
   const uint32_t bar_full = sBar, bar_empty = sBar + 8u * TC_MAX_STAGES, bar_accf = sBar + 16u * TC_MAX_STAGES,
@@ -190,12 +202,13 @@ conv_tc_kernel(const TcParams p) {
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8u * s, TC_PRODUCERS + 1);
+      mbar_init(bar_full + 8u * s, p.tma ? 1 : TC_PRODUCERS + 1);
       mbar_init(bar_empty + 8u * s, 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8u * i, 1); mbar_init(bar_acce + 8u * i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 5 && lane == 0 && p.tma) asm volatile("prefetch.tensormap [%0];" ::"l"(p.tmap) : "memory");
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -204,18 +217,22 @@ conv_tc_kernel(const TcParams p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp < 4) {
+    if (!p.tma) {
     // ===== producers: im2col gather. One warp instruction covers 4 tile rows x 128 contiguous bytes (lane = 8*row + chunk),
     // so every request touches 4 cache lines instead of 32; a thread serves chunk `j` of 8 rows of its warp's 32.
     // Per tile, lane l first describes tile row warp*32+l as {byte offset of tap (0,0), bitmask of in-image taps} in
     // shared memory; the gather loop then costs one AND, one select and one add per 16-byte copy. ======================
     const int j = lane & 7, rsub = lane >> 3;
-    const uint32_t dst0 = (uint32_t)(warp * 32 + rsub) * TC_ROW_BYTES;
+    const uint32_t dst0 = (uint32_t)(warp * 32 + rsub) * TC_ROW_BYTES;               // gather mode: row_bytes == 128
     const uint32_t sw_even = ((uint32_t)j ^ (uint32_t)rsub) << 4, sw_odd = ((uint32_t)j ^ (uint32_t)(4 | rsub)) << 4;
     const uint32_t s_info = s_rowoff + 8u * TC_BLOCK_M;       // 128 x {int32 offset, uint32 tap mask}
     const uint8_t* in8 = static_cast<const uint8_t*>(a.in);
     const int lag = p.lag;
     const int hw_o = a.Ho * a.Wo;
+    const int Cin = a.Cin, KW = a.KW, Wi = a.Wi, Ktot = p.Ktot, num_kb = p.num_kb;
     int it = 0;
+    int s = 0, as = 0;                                         // ring slot being filled / slot whose copies are awaited (lag behind)
+    uint32_t ph = 1;                                           // parity to wait on for empty[s] (first pass: slots start free)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.tiles_n) * TC_BLOCK_M;
       const int b0 = m0 / hw_o;                                // first image this tile touches
@@ -242,14 +259,13 @@ conv_tc_kernel(const TcParams p) {
       for (int i = 0; i < 8; ++i)
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(off0[i]), "=r"(tmask[i]) : "r"(s_info + 8u * (uint32_t)(warp * 32 + i * 4 + rsub)));
       int c = j * CE, fr = 0, fs = 0, kthr = j * CE;
-      while (c >= a.Cin) { c -= a.Cin; if (++fs == a.KW) { fs = 0; ++fr; } }
-      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-        const int s = it % S;
-        if (it >= S) mbar_wait_relaxed(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
-        if (kthr < p.Ktot) {
-          const uint32_t dst_e = sA + (uint32_t)s * TC_A_STAGE + dst0 + sw_even, dst_o = sA + (uint32_t)s * TC_A_STAGE + dst0 + sw_odd;
-          const uint32_t tapbit = 1u << (fr * a.KW + fs);
-          const int dtap = ((fr * a.Wi + fs) * a.Cin + c) * ESZ;
+      while (c >= Cin) { c -= Cin; if (++fs == KW) { fs = 0; ++fr; } }
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        if (it >= S) mbar_wait_relaxed(bar_empty + 8u * s, ph);
+        if (kthr < Ktot) {
+          const uint32_t dst_e = sA + (uint32_t)(s * a_stage) + dst0 + sw_even, dst_o = sA + (uint32_t)(s * a_stage) + dst0 + sw_odd;
+          const uint32_t tapbit = 1u << (fr * KW + fs);
+          const int dtap = ((fr * Wi + fs) * Cin + c) * ESZ;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const bool ok = (tmask[i] & tapbit) != 0;
@@ -259,56 +275,74 @@ conv_tc_kernel(const TcParams p) {
         }
         kthr += KB;
         c += KB;
-        while (c >= a.Cin) { c -= a.Cin; if (++fs == a.KW) { fs = 0; ++fr; } }
+        while (c >= Cin) { c -= Cin; if (++fs == KW) { fs = 0; ++fr; } }
         cp_async_commit();
+        if (++s == S) { s = 0; ph ^= 1u; }
         if (it >= lag) {
           cp_async_wait_dyn<TC_MAX_LAG>(lag);
           fence_proxy_async();
-          mbar_arrive(bar_full + 8u * ((it - lag) % S));
+          mbar_arrive(bar_full + 8u * as);
+          if (++as == S) as = 0;
         }
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (int k = max(it - lag, 0); k < it; ++k) mbar_arrive(bar_full + 8u * (k % S));
+    for (int k = max(it - lag, 0); k < it; ++k) { mbar_arrive(bar_full + 8u * as); if (++as == S) as = 0; }
+    }
   } else if (warp == 4) {
     // ===== MMA issuer ===================================================================================================
     const uint32_t idesc = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                            ((uint32_t)(TC_BLOCK_M >> 4) << 24);
-    int it = 0, li = 0;
+    int li = 0, s = 0;
+    uint32_t ph = 0;
+    const int num_kb = p.num_kb;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
       const int buf = li & 1;
       if (li >= 2) mbar_wait(bar_acce + 8u * buf, ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.block_n);
-      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-        const int s = it % S;
-        mbar_wait(bar_full + 8u * s, (it / S) & 1);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_full + 8u * s, ph);
         tc_fence_after();
         if (lane == 0) {
-          const int kleft = p.Ktot - kb * KB;
-          const int nk = (kleft >= KB ? KB : kleft) / UK;
-          const uint64_t da = umma_desc(sA + (uint32_t)s * TC_A_STAGE), db = umma_desc(sB + (uint32_t)s * b_stage);
+          const int kbe = p.row_bytes / ESZ;                  // K elements per k-block
+          const int kleft = p.Ktot - kb * kbe;
+          const int nk = (kleft >= kbe ? kbe : kleft) / UK;
+          const uint64_t da = umma_desc(sA + (uint32_t)(s * a_stage), p.row_bytes), db = umma_desc(sB + (uint32_t)(s * b_stage), p.row_bytes);
           for (int kk = 0; kk < nk; ++kk) umma<TF32>(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0);
           umma_commit(bar_empty + 8u * s);                     // frees the stage once these MMAs have read it
-          if (kb == p.num_kb - 1) umma_commit(bar_accf + 8u * buf);   // accumulator complete
+          if (kb == num_kb - 1) umma_commit(bar_accf + 8u * buf);   // accumulator complete
         }
         __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 5) {
-    // ===== weight loader: [kb][Cout][128 B] pre-swizzled; one bulk copy per k-block ===================================
+    // ===== loader: weights [kb][Cout][row_bytes] pre-swizzled, one bulk copy per k-block; in TMA mode also the
+    // activation tile: one 4-D tensor copy {channels, Wo-run, rows, images} per k-block, zero-filled outside the image ====
     if (lane == 0) {
-      const size_t kb_stride = (size_t)a.Cout * TC_ROW_BYTES;
-      int it = 0;
+      const size_t kb_stride = (size_t)a.Cout * p.row_bytes;
+      const int kbe = p.row_bytes / ESZ;
+      const uint32_t tx = (uint32_t)b_stage + (p.tma ? (uint32_t)a_stage : 0u);
+      int it = 0, s = 0;
+      uint32_t ph = 1;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.tiles_n) * p.block_n;
-        const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)n0 * TC_ROW_BYTES;
+        const int m0 = (tile / p.tiles_n) * TC_BLOCK_M;
+        const int x0 = (m0 % a.Wo) * a.stride - a.pad_w, t1 = m0 / a.Wo, y0 = (t1 % a.Ho) * a.stride - a.pad_h, b0 = t1 / a.Ho;
+        const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)n0 * p.row_bytes;
+        int c = 0, fr = 0, fs = 0;
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const int s = it % S;
-          if (it >= S) mbar_wait_relaxed(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar_full + 8u * s, (uint32_t)b_stage);
-          bulk_g2s(sB + (uint32_t)s * b_stage, wsrc + kb * kb_stride, (uint32_t)b_stage, bar_full + 8u * s);
+          if (it >= S) mbar_wait(bar_empty + 8u * s, ph);
+          mbar_arrive_expect_tx(bar_full + 8u * s, tx);
+          if (p.tma) {
+            tma_load_4d(sA + (uint32_t)(s * a_stage), p.tmap, c, x0 + fs, y0 + fr, b0, bar_full + 8u * s);
+            c += kbe;
+            if (c >= a.Cin) { c = 0; if (++fs == a.KW) { fs = 0; ++fr; } }
+          }
+          bulk_g2s(sB + (uint32_t)(s * b_stage), wsrc + kb * kb_stride, (uint32_t)b_stage, bar_full + 8u * s);
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -337,7 +371,7 @@ conv_tc_kernel(const TcParams p) {
       const uint32_t t_row = t_lane + (uint32_t)(buf * p.block_n);
       if (a.out_nchw) {
         // fp32 [B,Cout,Ho,Wo] (heatmap logits for the integral layer): lanes hold adjacent pixels, stores are coalesced
-        mbar_wait_relaxed(bar_accf + 8u * buf, (li >> 1) & 1);
+        mbar_wait(bar_accf + 8u * buf, (li >> 1) & 1);
         tc_fence_after();
         float* op = static_cast<float*>(a.out) + (((size_t)b * a.Cout + n0) * a.Ho_full + y) * a.Wo_full + x;
         const size_t cs = (size_t)a.Ho_full * a.Wo_full;
@@ -381,7 +415,7 @@ conv_tc_kernel(const TcParams p) {
         cp_async_wait<0>();
         epi_barrier<EPI>();
       }
-      mbar_wait_relaxed(bar_accf + 8u * buf, (li >> 1) & 1);
+      mbar_wait(bar_accf + 8u * buf, (li >> 1) & 1);
       tc_fence_after();
       for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
         uint32_t v[16];
@@ -482,11 +516,11 @@ __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restric
   if (i < n) out[i] = round_tf32_rna(in[i]);
 }
 
-size_t tc_stage_bytes(int block_n) { return (size_t)TC_A_STAGE + (size_t)block_n * TC_ROW_BYTES; }
+size_t tc_stage_bytes(int block_n, int row_bytes) { return (size_t)(TC_BLOCK_M + block_n) * row_bytes; }
 size_t tc_staging_bytes(int block_n, int esz) { return ((size_t)TC_BLOCK_M * (block_n * esz + 16) + 127) / 128 * 128; }
 size_t tc_tail_bytes() { return 16 * TC_MAX_STAGES + 16 + 16 + 16 + 8 * TC_BLOCK_M + 8 * TC_BLOCK_M + 64; }
-size_t tc_smem_bytes(int stages, int block_n, int esz) {
-  return 1024 + stages * tc_stage_bytes(block_n) + tc_staging_bytes(block_n, esz) + tc_tail_bytes();
+size_t tc_smem_bytes(int stages, int block_n, int esz, int row_bytes) {
+  return 1024 + (stages * tc_stage_bytes(block_n, row_bytes) + 1023) / 1024 * 1024 + tc_staging_bytes(block_n, esz) + tc_tail_bytes();
 }
 
 int env_int(const char* name, int dflt) {
@@ -494,11 +528,61 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {          // resolved through the runtime so the library has no link-time libcuda dependency
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// The 128 pixels of an M tile as a box of the NHWC input: {Wo-run, rows, images}. 0 if the geometry does not tile.
+bool tma_box(const ConvArgs& a, int* bw, int* bh, int* bn_img) {
+  if (a.Wo >= TC_BLOCK_M) {
+    if (a.Wo % TC_BLOCK_M) return false;
+    *bw = TC_BLOCK_M; *bh = 1; *bn_img = 1;
+    return true;
+  }
+  if (TC_BLOCK_M % a.Wo) return false;
+  const int rows = TC_BLOCK_M / a.Wo;
+  if (rows <= a.Ho) {
+    if (a.Ho % rows) return false;
+    *bw = a.Wo; *bh = rows; *bn_img = 1;
+  } else {
+    if (rows % a.Ho) return false;
+    *bw = a.Wo; *bh = a.Ho; *bn_img = rows / a.Ho;
+  }
+  return true;
+}
+
 }  // namespace
 
 bool conv_tc_supported(const ConvArgs& a, int tf32) {
   const int half = tf32 ? 16 : 32;
   return a.Cin % half == 0 && a.Cout % 32 == 0 && a.ld_out % 8 == 0 && a.out_coff % 8 == 0 && a.KH * a.KW <= 32;
+}
+
+// Operand-row width a layer is packed for. TMA mode (one tap per k-block) needs Cin*elem to be 64 bytes or a multiple of
+// 128 and the M tile to be a box of the input; everything else goes through the cp.async gather with 128-byte rows.
+int conv_tc_row_bytes(const ConvArgs& a, int tf32, int* use_tma) {
+  static const int no_tma = env_int("HRP_TC_NO_TMA", 0);
+  const int esz = tf32 ? 4 : 2;
+  int bw, bh, bi;
+  const int cb = a.Cin * esz;
+  bool ok = !no_tma && (cb == 64 || cb % 128 == 0) && tma_box(a, &bw, &bh, &bi) && bw * a.stride <= 256 && bh * a.stride <= 256 &&
+            a.stride <= 8 && encode_tiled() != nullptr;
+  if (use_tma) *use_tma = ok ? 1 : 0;
+  return ok && cb == 64 ? 64 : 128;
 }
 
 int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st) {
@@ -509,12 +593,29 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   p.M = a.B * a.Ho * a.Wo;
   if (p.M <= 0) return HRP_OK;
   const int esz = tf32 ? 4 : 2;
-  const int kb_elems = tf32 ? 32 : 64;
+  p.row_bytes = conv_tc_row_bytes(a, tf32, &p.tma);
+  const int kb_elems = p.row_bytes / esz;
   p.Ktot = a.KH * a.KW * a.Cin;
   p.num_kb = ceil_div(p.Ktot, kb_elems);
+  if (p.tma) {
+    int bw = 0, bh = 0, bi = 0;
+    tma_box(a, &bw, &bh, &bi);
+    CUtensorMap tm;
+    const cuuint64_t gdim[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)a.Cin * esz, (cuuint64_t)a.Wi * a.Cin * esz, (cuuint64_t)a.Hi * a.Wi * a.Cin * esz};
+    const cuuint32_t box[4] = {(cuuint32_t)kb_elems, (cuuint32_t)(bw * a.stride), (cuuint32_t)(bh * a.stride), (cuuint32_t)bi};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1};
+    const CUresult r = encode_tiled()(&tm, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.in),
+                                      gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HRP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for input [%d,%d,%d,%d]", (int)r, a.B, a.Hi, a.Wi, a.Cin);
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    std::memcpy(p.tmap, &tm, 128);
+  }
   const int mtiles = ceil_div(p.M, TC_BLOCK_M);
   const int sms = sm_count();
-  // N tile: every CTA re-gathers its activation rows, so wide tiles cut the gather traffic; take the widest that still
+  // N tile: every CTA re-reads its activation rows, so wide tiles cut that traffic; take the widest that still
   // leaves about one tile per SM, else the narrowest. (TF32: <= 128 so the fp32 staging tile fits beside the stages.)
   static const int force_bn = env_int("HRP_TC_BN", 0), force_stages = env_int("HRP_TC_STAGES", 0), force_ctas = env_int("HRP_TC_CTAS", 0);
   const int cand[4] = {256, 128, 64, 32};
@@ -532,28 +633,28 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   int tm = 32;
   while (tm < 2 * bn) tm <<= 1;                             // two accumulator buffers
   p.tmem_cols = tm;
-  // CTAs per SM: two when there are enough tiles and two CTAs' shared memory / TMEM fit, else one with a deep ring
   // epilogue-heavy tiles (wide N, short K) get eight epilogue warps and the SM to themselves
   static const int force_epi = env_int("HRP_TC_EPI", 0);
-  int epi = (bn >= 128 && p.num_kb <= 4) ? 8 : 4;
+  int epi = (bn >= 128 && p.Ktot <= 256) ? 8 : 4;
   if (force_epi == 4 || force_epi == 8) epi = force_epi;
   int ctas = (epi == 4 && p.total_tiles >= 2 * sms && tm <= 256) ? 2 : 1;
   if (force_ctas) ctas = (epi == 4 && force_ctas == 2 && tm <= 256) ? 2 : 1;
   const size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 1024 : 0);
-  const size_t fixed = 1024 + tc_staging_bytes(bn, esz) + tc_tail_bytes();
-  int smax = (int)((budget - fixed) / tc_stage_bytes(bn));
+  const size_t fixed = 2048 + tc_staging_bytes(bn, esz) + tc_tail_bytes();
+  int smax = (int)((budget - fixed) / tc_stage_bytes(bn, p.row_bytes));
   smax = std::max(1, std::min(smax, TC_MAX_STAGES));
   if (force_stages) smax = std::max(1, std::min(force_stages, smax));
   p.stages = smax;                                          // the ring runs across tiles, so depth is not tied to num_kb
-  if ((long long)p.num_kb * ceil_div(p.total_tiles, sms * ctas) < p.stages) p.stages = std::max(1, p.num_kb * ceil_div(p.total_tiles, sms * ctas));
+  const long long kb_per_cta = (long long)p.num_kb * ceil_div(p.total_tiles, sms * ctas);
+  if (kb_per_cta < p.stages) p.stages = (int)std::max(1LL, kb_per_cta);
   p.lag = std::min(TC_MAX_LAG, p.stages - 1);
   p.round_tf32 = round_tf32;
-  p.stg_off = (int)(p.stages * tc_stage_bytes(bn));
+  p.stg_off = (int)((p.stages * tc_stage_bytes(bn, p.row_bytes) + 1023) / 1024 * 1024);
   p.bar_off = p.stg_off + (int)tc_staging_bytes(bn, esz);
   int cl = 0;
   while ((16 << cl) < bn * esz) ++cl;
   p.cpr_log = cl;
-  const size_t smem = tc_smem_bytes(p.stages, bn, esz);
+  const size_t smem = tc_smem_bytes(p.stages, bn, esz, p.row_bytes);
   if (smem > (size_t)TC_SMEM_LIMIT) return fail(HRP_ERR_INVALID, "conv_tc: %zu bytes of shared memory needed (block_n %d)", smem, bn);
   static bool attr_done = false;
   if (!attr_done) {
@@ -575,20 +676,22 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   return HRP_OK;
 }
 
-// [K][Cout] fp32 (BN folded, k = (r*KW+s)*Cin + c) -> [num_kb][Cout][128 B] K-major rows, 16-byte chunks XOR-swizzled
-// by (row & 7) exactly as the SWIZZLE_128B operand layout expects; K zero-padded to a whole k-block.
-size_t pack_conv_tc_bytes(int K, int Cout, int tf32) { return (size_t)ceil_div(K, tf32 ? 32 : 64) * Cout * TC_ROW_BYTES; }
+// [K][Cout] fp32 (BN folded, k = (r*KW+s)*Cin + c) -> [num_kb][Cout][row_bytes] K-major rows, 16-byte chunks XOR-swizzled
+// exactly as the SWIZZLE_128B (chunk ^ (row & 7)) / SWIZZLE_64B (chunk ^ ((row >> 1) & 3)) operand layouts expect; K
+// zero-padded to a whole k-block.
+size_t pack_conv_tc_bytes(int K, int Cout, int tf32, int row_bytes) { return (size_t)ceil_div(K, row_bytes / (tf32 ? 4 : 2)) * Cout * row_bytes; }
 
-void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, void* out) {
-  const int kb_elems = tf32 ? 32 : 64, ce = tf32 ? 4 : 8;
+void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, void* out) {
+  const int ce = tf32 ? 4 : 8, chunks = row_bytes / 16, kb_elems = chunks * ce;
   const int num_kb = ceil_div(K, kb_elems);
   uint8_t* o = static_cast<uint8_t*>(out);
-  std::memset(o, 0, pack_conv_tc_bytes(K, Cout, tf32));
+  std::memset(o, 0, pack_conv_tc_bytes(K, Cout, tf32, row_bytes));
   for (int kb = 0; kb < num_kb; ++kb)
     for (int n = 0; n < Cout; ++n) {
-      uint8_t* row = o + ((size_t)kb * Cout + n) * TC_ROW_BYTES;
-      for (int j = 0; j < 8; ++j) {
-        uint8_t* chunk = row + ((j ^ (n & 7)) << 4);
+      uint8_t* row = o + ((size_t)kb * Cout + n) * row_bytes;
+      const int sw = row_bytes == 128 ? (n & 7) : ((n >> 1) & 3);
+      for (int j = 0; j < chunks; ++j) {
+        uint8_t* chunk = row + ((j ^ sw) << 4);
         for (int e = 0; e < ce; ++e) {
           const int k = kb * kb_elems + j * ce + e;
           if (k >= K) continue;

@@ -31,8 +31,11 @@ int conv_f32_launch(const ConvArgs& a, cudaStream_t s);
 // TF32 (nearest) for the next layer's operands.
 bool conv_tc_supported(const ConvArgs& a, int tf32);
 int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s);
-size_t pack_conv_tc_bytes(int K, int Cout, int tf32);
-void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, void* out);   // from pack_conv_f32's [K][Cout]
+// Operand-row width (64 / 128 bytes) the layer described by `a` (shape fields only) must be packed for; *use_tma tells
+// whether its activations will arrive by TMA tensor copies or by the cp.async gather.
+int conv_tc_row_bytes(const ConvArgs& a, int tf32, int* use_tma);
+size_t pack_conv_tc_bytes(int K, int Cout, int tf32, int row_bytes);
+void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, void* out);   // from pack_conv_f32's [K][Cout]
 int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t s);
 int cast_bf16_to_f32_launch(const void* in, float* out, size_t n, cudaStream_t s);
 int round_tf32_launch(const float* in, float* out, size_t n, cudaStream_t s);

@@ -276,17 +276,26 @@ struct GraphBuilder {
   }
 
   // finish a backbone conv layer from its fp32 [K][Cout] matrix: the tensor-core families keep only the swizzled image
-  int finish_layer(std::vector<float>& wp, float* dbias, int Cin, int Cout, int KH, int KW) {
+  // (`g`: the shape fields of the op that will use the layer -- they decide the operand-row width it is packed for)
+  int finish_layer(std::vector<float>& wp, float* dbias, int Cin, int Cout, int KH, int KW, const ConvArgs& g) {
     Layer L; L.Cout = Cout; L.Cin = Cin; L.KH = KH; L.KW = KW; L.bias = dbias;
     if (tc()) {
-      std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32()));
-      pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32(), img.data());
+      const int rb = conv_tc_row_bytes(g, tf32(), nullptr);
+      std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32(), rb));
+      pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32(), rb, img.data());
       L.w_tc = upload_bytes(img);
     } else {
       L.w = upload(wp);
     }
     h->layers.push_back(L);
     return (int)h->layers.size() - 1;
+  }
+
+  static ConvArgs shape_of(const OpDesc& o) {
+    ConvArgs g{};
+    g.B = 1; g.Hi = o.Hi; g.Wi = o.Wi; g.Cin = o.Cin; g.Ho = o.Ho; g.Wo = o.Wo; g.Cout = o.Cout; g.KH = o.KH; g.KW = o.KW;
+    g.stride = o.stride; g.pad_h = o.pad_h; g.pad_w = o.pad_w; g.ld_out = o.Cout;
+    return g;
   }
 
   Tn new_tensor(int H, int W_, int C, int esize, const char* name = "") {
@@ -307,7 +316,7 @@ struct GraphBuilder {
   }
 
   // conv (+bias) (+BN) packed for the fp32 family. wname = "<prefix>.weight"; bn prefix may be empty.
-  int make_layer(const std::string& pc, const std::string& pb, int Cin, int Cout, int KH, int KW) {
+  int make_layer(const std::string& pc, const std::string& pb, int Cin, int Cout, int KH, int KW, const ConvArgs& geom) {
     const float* w = W(pc + ".weight");
     const float* cb = has(pc + ".bias") ? W(pc + ".bias") : nullptr;
     const float *g = nullptr, *b = nullptr, *m = nullptr, *v = nullptr;
@@ -315,16 +324,16 @@ struct GraphBuilder {
     if (status != HRP_OK) return -1;
     std::vector<float> wp((size_t)KH * KW * Cin * Cout), bp(Cout);
     pack_conv_f32(w, cb, g, b, m, v, Cout, Cin, KH, KW, wp.data(), bp.data());
-    return finish_layer(wp, upload(bp), Cin, Cout, KH, KW);
+    return finish_layer(wp, upload(bp), Cin, Cout, KH, KW, geom);
   }
 
   Tn conv(const Tn& x, const std::string& pc, const std::string& pb, int Cout, int k, int stride, int pad, int relu,
           int res = -1, int res_after_act = 0, int out_nchw = 0, int out_esize = -1, const char* name = "") {
     OpDesc op{};
     op.kind = OP_CONV; op.cls = tc() ? CLS_CONV_TC : CLS_CONV_F32;
-    op.layer = make_layer(pc, pb, x.C, Cout, k, k);
     op.Hi = x.H; op.Wi = x.W; op.Cin = x.C; op.Cout = Cout; op.KH = op.KW = k; op.stride = stride; op.pad_h = op.pad_w = pad;
     op.Ho = (x.H + 2 * pad - k) / stride + 1; op.Wo = (x.W + 2 * pad - k) / stride + 1;
+    op.layer = make_layer(pc, pb, x.C, Cout, k, k, shape_of(op));
     op.Ho_full = op.Ho; op.Wo_full = op.Wo; op.relu = relu; op.res = res; op.res_after_act = res_after_act; op.out_nchw = out_nchw;
     Tn y = new_tensor(op.Ho, op.Wo, Cout, out_esize > 0 ? out_esize : act_esize, name);
     op.in = x.id; op.out = y.id; op.ld = Cout;
@@ -476,9 +485,10 @@ struct GraphBuilder {
                 wp[((size_t)(ty * 2 + tx) * Cin + c) * Cout + o] = (float)((double)w[(((size_t)c * Cout + o) * 4 + ky) * 4 + kx] * sc[o]);
           }
         OpDesc op{};
-        op.kind = OP_CONV; op.cls = tc() ? CLS_CONV_TC : CLS_CONV_F32; op.layer = finish_layer(wp, dbias, Cin, Cout, 2, 2);
+        op.kind = OP_CONV; op.cls = tc() ? CLS_CONV_TC : CLS_CONV_F32;
         op.in = x.id; op.out = y.id; op.Hi = x.H; op.Wi = x.W; op.Cin = Cin; op.Cout = Cout; op.KH = op.KW = 2; op.stride = 1;
-        op.pad_h = 1 - py; op.pad_w = 1 - px; op.Ho = x.H; op.Wo = x.W; op.out_sy = op.out_sx = 2; op.out_oy = py; op.out_ox = px;
+        op.pad_h = 1 - py; op.pad_w = 1 - px; op.Ho = x.H; op.Wo = x.W;
+        op.layer = finish_layer(wp, dbias, Cin, Cout, 2, 2, shape_of(op)); op.out_sy = op.out_sx = 2; op.out_oy = py; op.out_ox = px;
         op.Ho_full = y.H; op.Wo_full = y.W; op.relu = 1; op.ld = Cout;
         op.flops = 2.0 * x.H * x.W * Cout * 4 * Cin;
         h->ops.push_back(op);
@@ -1066,8 +1076,9 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
     // tensor-core families: operands converted to the family's activation type exactly as a producing layer would
     const int tf32 = precision == HRP_PREC_TF32;
     if (!conv_tc_supported(a, tf32)) rs = fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: shape not supported by the tensor-core family (Cin %% %d, Cout %% 16)", tf32 ? 16 : 32);
-    std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32));
-    pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32, img.data());
+    const int rb = conv_tc_row_bytes(a, tf32, nullptr);
+    std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32, rb));
+    pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32, rb, img.data());
     void* dw = dalloc(img.size());
     const size_t es = tf32 ? 4 : 2;
     void* din = dalloc(n_in * es);
