@@ -60,6 +60,27 @@ def test_fk_limb_lengths_at_scale(robot, dev):
     assert torch.isfinite(uv).all()
 
 
+
+@pytest.mark.parametrize("robot", ["panda", "kuka", "baxter"])
+def test_fk_generated_chain_matches_table_interpreter(robot, dev, monkeypatch):
+    """The URDF-generated straight-line chain (persistent cp.async kernel) against the table interpreter on the same poses:
+    many tiles per CTA, a ragged tail, and input views that are not 16-byte aligned (synchronous staging path)."""
+    from hrp_b200.model import FkRobot
+    n = 148 * 7 * 128 * 2 + 77
+    args = [cu(a, dev) for a in synth.make_fk_inputs(robot, n, 55)]
+    fk = FkRobot(robot)
+    monkeypatch.setenv("HRP_FK_GENERIC", "1")
+    fk_tab = FkRobot(robot)
+    monkeypatch.delenv("HRP_FK_GENERIC")
+    x1, u1 = fk.keypoints(*args)
+    x0, u0 = fk_tab.keypoints(*args)
+    assert helpers.maxdiff(x1, x0) < 2e-6
+    ok = x0[..., 2].abs() > 0.3
+    assert float((u1 - u0).abs()[ok].max()) < 1e-2
+    shifted = [a[1:] for a in args]              # rot6d rows are 24 B, trans rows 12 B: misaligned for 16-byte copies
+    x2, u2 = fk.keypoints(*shifted)
+    assert torch.equal(x2, x1[1:]) and torch.equal(u2, u1[1:])
+
 def test_fk_branching_tree_against_oracle(dev):
     """A URDF whose keypoint paths branch mid-chain (saved frames in shared memory), prismatic + off-axis joints."""
     import ctypes as C

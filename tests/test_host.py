@@ -149,3 +149,11 @@ def test_gather_records_world_size_2_gloo():
     for p in procs:
         p.join(60)
     assert res == [(0, True), (1, True)]
+
+
+def test_generated_fk_chains_are_current():
+    """csrc/fk_programs_gen.h must be exactly what scripts/gen_fk_programs.py emits from the packaged URDFs."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_fk_programs.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
