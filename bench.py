@@ -108,7 +108,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("HRP_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("HRP_PRECISION", "bf16"), choices=["fp32", "tf32", "bf16"],
+                    help="conv/linear contraction arithmetic: bf16 = throughput mode (default), fp32 = parity mode")
     ap.add_argument("--backbone", default="resnet50", choices=["resnet50", "hrnet32"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -36,6 +36,8 @@ struct TensorInfo {
   int H = 0, W = 0, C = 0;
   int last_use = -1, first_def = 1 << 30;
   bool keep = false;
+  int home_lane = 0;     // lane of the defining op: the tensor lives in that lane's arena
+  bool cross = false;    // touched by an op of another lane: never recycled (no cross-stream write-after-read hazards)
   std::string name;
 };
 
@@ -60,7 +62,10 @@ struct OpDesc {
   const float* wptr = nullptr;   // small head weights
   const float* bptr = nullptr;
   double flops = 0.0;    // per frame
+  int lane = 0;          // execution lane (stream of the captured graph); ops of one lane run in list order
 };
+
+constexpr int kMaxLanes = 12;
 
 struct Plan {
   int B = 0;
@@ -103,6 +108,12 @@ struct hrp_handle {
   std::map<int, std::unique_ptr<Plan>> plans;
   std::unordered_map<std::string, int> debug;
   cudaStream_t capture_stream = nullptr;
+  int n_lanes = 1;
+  cudaStream_t lane_stream[hrp::kMaxLanes] = {};   // lanes 1.. of the captured graph (lane 0 is the capture stream)
+  std::vector<cudaEvent_t> events;                 // cross-lane edges, created while capturing
+  std::vector<std::vector<int>> waits;             // per op: producer ops on other lanes it must wait for
+  std::vector<char> signals;                       // per op: some other lane waits for it
+  bool use_lanes = true;
   int64_t last_launches = 0;
   int t_xreg = -1, t_xroot = -1, t_kval = -1, t_kmat = -1, t_field[HRP_NUM_FIELDS];
   int field_width[HRP_NUM_FIELDS];
@@ -235,6 +246,8 @@ struct GraphBuilder {
   int status = HRP_OK;
   int act_esize = 4;
   int prec = HRP_PREC_FP32;
+  int cur_lane = 0;
+  void push(OpDesc op) { op.lane = cur_lane; h->ops.push_back(op); }
   bool tc() const { return prec != HRP_PREC_FP32; }
   bool tf32() const { return prec == HRP_PREC_TF32; }
 
@@ -338,7 +351,7 @@ struct GraphBuilder {
     Tn y = new_tensor(op.Ho, op.Wo, Cout, out_esize > 0 ? out_esize : act_esize, name);
     op.in = x.id; op.out = y.id; op.ld = Cout;
     op.flops = 2.0 * op.Ho * op.Wo * Cout * k * k * x.C;
-    h->ops.push_back(op);
+    push(op);
     return y;
   }
 
@@ -363,7 +376,7 @@ struct GraphBuilder {
     op.kind = OP_STEM; op.cls = CLS_STEM; op.layer = (int)h->layers.size() - 1;
     op.in = x_ext; op.out = y.id; op.Hi = op.Wi = 256; op.Ho = op.Wo = 128; op.KH = op.KW = k; op.pad_h = pad;
     op.flops = 2.0 * 128 * 128 * 64 * k * k * 3;
-    h->ops.push_back(op);
+    push(op);
     return y;
   }
 
@@ -380,12 +393,18 @@ struct GraphBuilder {
     return conv(y, p + ".conv2", p + ".bn2", x.C, 3, 1, 1, 1, x.id);
   }
 
-  std::vector<Tn> hr_module(std::vector<Tn> xs, const std::string& p) {
+  // Branch i of an HRNet (its blocks and the fuse ops that produce output i) runs on lane lane0 + i: the branches of a
+  // module are independent until the fuse layers exchange them (HRnet.py:247-265), and the low-resolution ones are far
+  // too small to fill 148 SMs on their own.
+  std::vector<Tn> hr_module(std::vector<Tn> xs, const std::string& p, int lane0) {
     const int n = (int)xs.size();
-    for (int i = 0; i < n; ++i)
+    for (int i = 0; i < n; ++i) {
+      cur_lane = lane0 + i;
       for (int k = 0; k < 4; ++k) xs[i] = basic(xs[i], S("%s.branches.%d.%d", p.c_str(), i, k));
+    }
     std::vector<Tn> out(n);
     for (int i = 0; i < n; ++i) {
+      cur_lane = lane0 + i;
       Tn acc = xs[i];
       const bool has_low = i < n - 1;
       for (int j = 0; j < i; ++j) {  // strided 3x3 chains from higher resolutions; the last conv adds the running sum
@@ -409,43 +428,49 @@ struct GraphBuilder {
       }
       Tn y = new_tensor(xs[i].H, xs[i].W, xs[i].C, act_esize);
       op.out = y.id; op.Ho = y.H; op.Wo = y.W; op.Cout = y.C; op.relu = 1;
-      h->ops.push_back(op);
+      push(op);
       out[i] = y;
     }
+    cur_lane = lane0;
     return out;
   }
 
   // returns feat tensor id (fp32 [2048]); *hm receives the NCHW heatmap tensor when hm_channels > 0
-  Tn hrnet(int x_ext, const std::string& p, int hm_channels, Tn* hm) {
+  Tn hrnet(int x_ext, const std::string& p, int hm_channels, Tn* hm, int lane0) {
+    cur_lane = lane0;
     Tn x = stem(x_ext, p + "conv1", p + "bn1", 3, 1);
     x = conv(x, p + "conv2", p + "bn2", 64, 3, 2, 1, 1);
     for (int b = 0; b < 4; ++b) x = bottleneck(x, S("%slayer1.%d", p.c_str(), b), 64, 1);
     std::vector<Tn> ys;
     ys.push_back(conv(x, p + "transition1.0.0", p + "transition1.0.1", 32, 3, 1, 1, 1));
+    cur_lane = lane0 + 1;
     ys.push_back(conv(x, p + "transition1.1.0.0", p + "transition1.1.0.1", 64, 3, 2, 1, 1));
-    ys = hr_module(ys, p + "stage2.0");
+    ys = hr_module(ys, p + "stage2.0", lane0);
     for (int st = 1; st < 3; ++st) {
       const int nb = st + 2;
       const std::string t = S("%stransition%d.%d.0", p.c_str(), st + 1, nb - 1);
+      cur_lane = lane0 + nb - 1;
       ys.push_back(conv(ys.back(), t + ".0", t + ".1", kHrChannels[nb - 1], 3, 2, 1, 1));   // reads y_list[-1], HRnet.py:519
-      for (int m = 0; m < kHrModules[st]; ++m) ys = hr_module(ys, S("%sstage%d.%d", p.c_str(), st + 2, m));
+      for (int m = 0; m < kHrModules[st]; ++m) ys = hr_module(ys, S("%sstage%d.%d", p.c_str(), st + 2, m), lane0);
     }
+    cur_lane = lane0;
     if (hm_channels) *hm = conv(ys[0], p + "final_layer", "", hm_channels, 1, 1, 0, 0, -1, 0, 1, 4, "logits");
     Tn y = bottleneck(ys[0], p + "incre_modules.0.0", kHrHead[0], 1);
     for (int i = 0; i < 3; ++i) {
+      cur_lane = lane0 + i + 1;
       Tn a = bottleneck(ys[i + 1], S("%sincre_modules.%d.0", p.c_str(), i + 1), kHrHead[i + 1], 1);
       const std::string d = S("%sdownsamp_modules.%d", p.c_str(), i);
       y = conv(y, d + ".0", d + ".1", kHrHead[i + 1] * 4, 3, 2, 1, 1, a.id, /*res_after_act=*/1);   // incre(x) + relu(bn(conv(y)))
     }
     y = conv(y, p + "final_feat_layer.0", p + "final_feat_layer.1", 2048, 1, 1, 0, 1);
-    return avgpool(y);
+    return avgpool(y);      // stays on lane0 + 3 (the caller continues there)
   }
 
   Tn avgpool(const Tn& y) {
     Tn f = new_tensor(1, 1, y.C, 4);
     OpDesc op{};
     op.kind = OP_AVGPOOL; op.cls = CLS_ELEM; op.in = y.id; op.out = f.id; op.Hi = y.H; op.Wi = y.W; op.Cin = y.C;
-    h->ops.push_back(op);
+    push(op);
     return f;
   }
 
@@ -454,7 +479,7 @@ struct GraphBuilder {
     Tn y = new_tensor(64, 64, 64, act_esize);
     OpDesc op{};
     op.kind = OP_MAXPOOL; op.cls = CLS_ELEM; op.in = x.id; op.out = y.id; op.Hi = x.H; op.Wi = x.W; op.Cin = 64;
-    h->ops.push_back(op);
+    push(op);
     x = y;
     for (int l = 0; l < 4; ++l)
       for (int b = 0; b < kResnetBlocks[l]; ++b)
@@ -491,7 +516,7 @@ struct GraphBuilder {
         op.layer = finish_layer(wp, dbias, Cin, Cout, 2, 2, shape_of(op)); op.out_sy = op.out_sx = 2; op.out_oy = py; op.out_ox = px;
         op.Ho_full = y.H; op.Wo_full = y.W; op.relu = 1; op.ld = Cout;
         op.flops = 2.0 * x.H * x.W * Cout * 4 * Cin;
-        h->ops.push_back(op);
+        push(op);
       }
     return y;
   }
@@ -507,7 +532,7 @@ struct GraphBuilder {
     op.Cin = x.C; op.Cout = Cout; op.ld = Cout;
     Tn y = new_tensor(1, 1, Cout, 4);
     op.in = x.id; op.out = y.id; op.flops = 2.0 * x.C * Cout;
-    h->ops.push_back(op);
+    push(op);
     return y;
   }
 
@@ -565,17 +590,17 @@ struct GraphBuilder {
         r.kind = OP_RANK; r.cls = CLS_HEADS; r.in = xc1.id; r.in2 = state[k]; r.out = h1.id; r.ld = 2 * Hd; r.coff = k * Hd;
         r.state_stride = (it == 0) ? 0 : sd[k]; r.dof = sd[k]; r.N = Hd; r.wptr = dw1b[k];
         r.flops = 2.0 * Hd * sd[k];
-        h->ops.push_back(r);
+        push(r);
         Tn h2 = new_tensor(1, 1, Hd, 4);
         OpDesc c{};
         c.kind = OP_CONV; c.cls = CLS_HEADS; c.layer = l2[k]; c.in = h1.id; c.out = h2.id; c.Cin = Hd; c.Cout = Hd; c.ld = Hd;
         c.flops = 2.0 * Hd * Hd;
-        h->ops.push_back(c);
+        push(c);
         OpDesc d{};
         d.kind = OP_DEC; d.cls = CLS_HEADS; d.in = h2.id; d.in2 = state[k]; d.out = h->t_field[field[k]];
         d.state_stride = r.state_stride; d.dof = sd[k]; d.N = Hd; d.wptr = dw[k]; d.bptr = db[k];
         d.flops = 2.0 * Hd * sd[k];
-        h->ops.push_back(d);
+        push(d);
         state[k] = h->t_field[field[k]];
       }
   }
@@ -592,8 +617,8 @@ struct GraphBuilder {
     h->t_kmat = special(T_KMAT, 9);
     for (int f = 0; f < HRP_NUM_FIELDS; ++f) { h->field_width[f] = fw[f]; h->t_field[f] = special(T_FIELD, fw[f], f); }
 
-    // DepthNet
-    Tn img_feat = hrnet(h->t_xroot, "rootnet_backbone.", 0, nullptr);
+    // DepthNet: lanes 0-3 (one per HRNet branch); its head ends on lane 3
+    Tn img_feat = hrnet(h->t_xroot, "rootnet_backbone.", 0, nullptr, 0);
     h->tensors[img_feat.id].keep = true; h->debug["img_feat"] = img_feat.id;
     {
       const float* w = W("depth_layer.weight"); const float* b = W("depth_layer.bias");
@@ -602,21 +627,29 @@ struct GraphBuilder {
       op.kind = OP_DEPTH; op.cls = CLS_HEADS; op.in = img_feat.id; op.in2 = h->t_kval; op.out = h->t_field[HRP_F_DEPTH];
       op.wptr = upload(std::vector<float>(w, w + 2048)); op.bptr = upload(std::vector<float>(b, b + 1)); op.Cin = 2048;
       op.flops = 2.0 * 2048;
-      h->ops.push_back(op);
+      push(op);
     }
-    // keypoint branch
+    // keypoint branch: lane 4 (ResNet-50 trunk, deconv head, logits, soft-argmax) or lanes 4-7 (HRNet-W32); the
+    // regression heads and FK run on their own lane beside the deconv head
     Tn xf, logits;
+    int kp_lane = 4, head_lane = 5;
     if (h->cfg.backbone == HRP_BACKBONE_RESNET50) {
+      cur_lane = kp_lane;
       Tn x = resnet50(h->t_xreg, "reg_backbone.");
+      cur_lane = head_lane;
       xf = avgpool(x);
+      cur_lane = kp_lane;
       Tn d = deconv(x, 0, 256);
       d = deconv(d, 1, 256);
       d = deconv(d, 2, 256);
       logits = conv(d, "final_layer", "", nk * 64, 1, 1, 0, 0, -1, 0, /*nchw=*/1, 4, "logits");
     } else {
-      xf = hrnet(h->t_xreg, "reg_backbone.", nk * 64, &logits);
+      xf = hrnet(h->t_xreg, "reg_backbone.", nk * 64, &logits, 4);
+      head_lane = 8;                       // xf ends on lane 7, the logits on lane 4
     }
+    h->n_lanes = head_lane + 1;
     if (status != HRP_OK) return status;
+    cur_lane = kp_lane;
     h->tensors[xf.id].keep = true; h->debug["xf"] = xf.id;
     h->tensors[logits.id].keep = true; h->debug["logits"] = logits.id;
     {
@@ -624,25 +657,42 @@ struct GraphBuilder {
       op.kind = OP_SOFTARGMAX; op.cls = CLS_SOFTARGMAX; op.in = logits.id; op.in2 = h->t_kmat; op.in3 = h->t_field[HRP_F_DEPTH];
       op.out = h->t_field[HRP_F_UVD]; op.out2 = h->t_field[HRP_F_XYZ_INT]; op.out3 = h->t_field[HRP_F_ROOT_UV];
       op.out4 = h->t_field[HRP_F_TRANS]; op.out5 = h->t_field[HRP_F_KP2D_INT];
-      h->ops.push_back(op);
+      push(op);
     }
+    cur_lane = head_lane;
     heads(xf);
     if (status != HRP_OK) return status;
     {
       OpDesc op{};
       op.kind = OP_FK; op.cls = CLS_FK; op.in = h->t_field[HRP_F_POSE]; op.in2 = h->t_field[HRP_F_ROT]; op.in3 = h->t_field[HRP_F_TRANS];
       op.in4 = h->t_kmat; op.out = h->t_field[HRP_F_XYZ_FK]; op.out2 = h->t_field[HRP_F_KP2D_FK];
-      h->ops.push_back(op);
+      push(op);
     }
-    // liveness
+    // liveness, lanes and cross-lane dependencies
+    std::vector<int> last_writer(h->tensors.size(), -1);
+    h->waits.assign(h->ops.size(), {});
+    h->signals.assign(h->ops.size(), 0);
     for (size_t i = 0; i < h->ops.size(); ++i) {
       const OpDesc& o = h->ops[i];
-      const int ids[] = {o.in, o.res, o.out, o.in2, o.in3, o.in4, o.out2, o.out3, o.out4, o.out5, o.same[0], o.same[1], o.same[2], o.same[3], o.low[0], o.low[1], o.low[2]};
-      for (int id : ids)
-        if (id >= 0) {
-          h->tensors[id].last_use = std::max(h->tensors[id].last_use, (int)i);
-          h->tensors[id].first_def = std::min(h->tensors[id].first_def, (int)i);
-        }
+      const int reads[] = {o.in, o.res, o.in2, o.in3, o.in4, o.same[0], o.same[1], o.same[2], o.same[3], o.low[0], o.low[1], o.low[2]};
+      const int writes[] = {o.out, o.out2, o.out3, o.out4, o.out5};
+      for (int id : writes)
+        if (id >= 0 && h->tensors[id].first_def > (int)i) { h->tensors[id].first_def = (int)i; h->tensors[id].home_lane = o.lane; }
+      auto touch = [&](int id) {
+        TensorInfo& t = h->tensors[id];
+        t.last_use = std::max(t.last_use, (int)i);
+        t.first_def = std::min(t.first_def, (int)i);
+        if (t.kind == T_WS && t.home_lane != o.lane) t.cross = true;
+      };
+      auto depend = [&](int j) {                 // op i must see op j's effects
+        if (j < 0 || h->ops[j].lane == o.lane) return;
+        auto& w = h->waits[i];
+        if (std::find(w.begin(), w.end(), j) == w.end()) { w.push_back(j); h->signals[j] = 1; }
+      };
+      for (int id : reads)
+        if (id >= 0) { touch(id); depend(last_writer[id]); }
+      for (int id : writes)
+        if (id >= 0) { touch(id); depend(last_writer[id]); last_writer[id] = (int)i; }   // write-after-write keeps list order
     }
     return status;
   }
@@ -716,22 +766,29 @@ int make_plan(hrp_handle* h, int B, Plan** out) {
   p->io_out = fl.alloc(align_up((size_t)record_floats(h, B, nullptr) * 4, A));
   p->sa_ws_bytes = softargmax_workspace(B, h->nkpt, 64, 64, 64);
   p->sa_ws = fl.alloc(align_up(p->sa_ws_bytes, A));
+  // Activations: one arena per lane. Ops of a lane run in list order on one stream, so recycling a tensor for a later
+  // tensor of the same lane is safe; tensors that another lane touches are never recycled.
   std::vector<size_t> sz(h->tensors.size(), 0);
   std::vector<char> live(h->tensors.size(), 0);
+  std::vector<FreeList> arena(h->n_lanes);
   for (size_t i = 0; i < h->ops.size(); ++i) {
     for (size_t t = 0; t < h->tensors.size(); ++t) {
       const TensorInfo& ti = h->tensors[t];
       if (ti.kind == T_WS && ti.first_def == (int)i && !live[t]) {
         sz[t] = align_up((size_t)ti.elems * B * ti.esize, A);
-        p->off[t] = fl.alloc(sz[t]);
+        p->off[t] = arena[ti.home_lane].alloc(sz[t]);
         live[t] = 1;
       }
     }
     for (size_t t = 0; t < h->tensors.size(); ++t) {
       const TensorInfo& ti = h->tensors[t];
-      if (ti.kind == T_WS && live[t] && !ti.keep && ti.last_use == (int)i) { fl.release(p->off[t], sz[t]); live[t] = 2; }
+      if (ti.kind == T_WS && live[t] && !ti.keep && !ti.cross && ti.last_use == (int)i) { arena[ti.home_lane].release(p->off[t], sz[t]); live[t] = 2; }
     }
   }
+  std::vector<size_t> lane_base(h->n_lanes, 0);
+  for (int l = 0; l < h->n_lanes; ++l) { lane_base[l] = fl.top; fl.top += align_up(arena[l].top, A); }
+  for (size_t t = 0; t < h->tensors.size(); ++t)
+    if (h->tensors[t].kind == T_WS) p->off[t] += lane_base[h->tensors[t].home_lane];
   p->ws_bytes = fl.top;
   HRP_CUDA(cudaSetDevice(h->device));
   void* ws = nullptr;
@@ -756,7 +813,10 @@ struct Profile {
   FILE* dump = nullptr;    // HRP_DUMP_OPS=<path>: one CSV line per op (development / profiles/)
 };
 
-int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* prof) {
+// `lanes`: only while capturing the graph. Ops are enqueued on their lane's stream (lane 0 = `st`), cross-lane producers
+// signal through events, and every lane joins `st` at the end, so the instantiated graph carries the true dependency DAG
+// of the network instead of a serial chain. Without it (eager / profiling) everything runs in list order on `st`.
+int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* prof, bool lanes = false) {
   const int B = p->B;
   int64_t offs[HRP_NUM_FIELDS + 1];
   record_floats(h, B, offs);
@@ -776,13 +836,31 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
   };
   int64_t launches = 0;
   const int bf16 = h->cfg.precision == HRP_PREC_BF16 ? 1 : 0, tf32 = h->cfg.precision == HRP_PREC_TF32 ? 1 : 0;
-  for (const OpDesc& o : h->ops) {
+  std::vector<cudaEvent_t> op_event(h->ops.size(), nullptr);
+  auto new_event = [&]() -> cudaEvent_t {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    h->events.push_back(e);
+    return e;
+  };
+  auto stream_of = [&](int lane) { return (lanes && lane > 0) ? h->lane_stream[lane] : st; };
+  if (lanes) {                                   // fork: every lane starts after whatever precedes the graph on `st`
+    cudaEvent_t e = new_event();
+    if (!e) return fail(HRP_ERR_CUDA, "cudaEventCreate failed");
+    HRP_CUDA(cudaEventRecord(e, st));
+    for (int l = 1; l < h->n_lanes; ++l) HRP_CUDA(cudaStreamWaitEvent(h->lane_stream[l], e, 0));
+  }
+  for (size_t oi = 0; oi < h->ops.size(); ++oi) {
+    const OpDesc& o = h->ops[oi];
+    cudaStream_t st_op = stream_of(o.lane);
+    if (lanes)
+      for (int j : h->waits[oi]) HRP_CUDA(cudaStreamWaitEvent(st_op, op_event[j], 0));
     if (prof) HRP_CUDA(cudaEventRecord(prof->e0, st));
     int n_launch = 1;
     switch (o.kind) {
       case OP_STEM: {
         const Layer& L = h->layers[o.layer];
-        HRP_TRY(stem_conv_launch(static_cast<const float*>(ptr(o.in)), L.w, L.bias, ptr(o.out), B, o.Hi, o.Wi, o.Ho, o.Wo, o.KH, o.KW, o.pad_h, bf16 ? 1 : (tf32 ? 2 : 0), st));
+        HRP_TRY(stem_conv_launch(static_cast<const float*>(ptr(o.in)), L.w, L.bias, ptr(o.out), B, o.Hi, o.Wi, o.Ho, o.Wo, o.KH, o.KW, o.pad_h, bf16 ? 1 : (tf32 ? 2 : 0), st_op));
         break;
       }
       case OP_CONV: {
@@ -793,47 +871,52 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         a.KH = o.KH; a.KW = o.KW; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w;
         a.out_sy = o.out_sy; a.out_sx = o.out_sx; a.out_oy = o.out_oy; a.out_ox = o.out_ox; a.Ho_full = o.Ho_full; a.Wo_full = o.Wo_full;
         a.relu = o.relu; a.out_nchw = o.out_nchw; a.ld_out = o.ld; a.out_coff = 0; a.res_after_act = o.res_after_act;
-        if (o.cls == CLS_CONV_TC) HRP_TRY(conv_tc_launch(a, tf32, tf32 && !o.out_nchw, st));
-        else HRP_TRY(conv_f32_launch(a, st));
+        if (o.cls == CLS_CONV_TC) HRP_TRY(conv_tc_launch(a, tf32, tf32 && !o.out_nchw, st_op));
+        else HRP_TRY(conv_f32_launch(a, st_op));
         break;
       }
       case OP_MAXPOOL:
-        HRP_TRY(maxpool3x3s2_launch(ptr(o.in), ptr(o.out), B, o.Hi, o.Wi, o.Cin, bf16, st));
+        HRP_TRY(maxpool3x3s2_launch(ptr(o.in), ptr(o.out), B, o.Hi, o.Wi, o.Cin, bf16, st_op));
         break;
       case OP_FUSE: {
         FuseArgs a{};
         for (int k = 0; k < o.n_same; ++k) a.same[k] = ptr(o.same[k]);
         for (int k = 0; k < o.n_low; ++k) { a.low[k] = ptr(o.low[k]); a.shift[k] = o.shift[k]; }
         a.n_same = o.n_same; a.n_low = o.n_low; a.out = ptr(o.out); a.B = B; a.H = o.Ho; a.W = o.Wo; a.C = o.Cout; a.relu = o.relu; a.round_tf32 = tf32;
-        HRP_TRY(fuse_sum_launch(a, bf16, st));
+        HRP_TRY(fuse_sum_launch(a, bf16, st_op));
         break;
       }
       case OP_AVGPOOL:
-        HRP_TRY(avgpool_launch(ptr(o.in), static_cast<float*>(ptr(o.out)), B, o.Hi * o.Wi, o.Cin, bf16, st));
+        HRP_TRY(avgpool_launch(ptr(o.in), static_cast<float*>(ptr(o.out)), B, o.Hi * o.Wi, o.Cin, bf16, st_op));
         break;
       case OP_DEPTH:
-        HRP_TRY(depth_head_launch(static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, static_cast<const float*>(ptr(o.in2)), static_cast<float*>(ptr(o.out)), B, o.Cin, st));
+        HRP_TRY(depth_head_launch(static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, static_cast<const float*>(ptr(o.in2)), static_cast<float*>(ptr(o.out)), B, o.Cin, st_op));
         break;
       case OP_RANK:
-        HRP_TRY(mlp_rank_launch(static_cast<float*>(ptr(o.out)), static_cast<const float*>(ptr(o.in)) + o.coff, o.ld, static_cast<const float*>(ptr(o.in2)), o.state_stride, o.wptr, B, o.N, o.dof, st));
+        HRP_TRY(mlp_rank_launch(static_cast<float*>(ptr(o.out)), static_cast<const float*>(ptr(o.in)) + o.coff, o.ld, static_cast<const float*>(ptr(o.in2)), o.state_stride, o.wptr, B, o.N, o.dof, st_op));
         break;
       case OP_DEC:
-        HRP_TRY(mlp_dec_launch(static_cast<float*>(ptr(o.out)), static_cast<const float*>(ptr(o.in2)), o.state_stride, static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, B, o.N, o.dof, st));
+        HRP_TRY(mlp_dec_launch(static_cast<float*>(ptr(o.out)), static_cast<const float*>(ptr(o.in2)), o.state_stride, static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, B, o.N, o.dof, st_op));
         break;
       case OP_SOFTARGMAX: {
         int nl = 0;
         HRP_TRY(softargmax_launch(static_cast<const float*>(ptr(o.in)), B, h->nkpt, 64, 64, 64, static_cast<const float*>(ptr(o.in2)), static_cast<const float*>(ptr(o.in3)),
                                   h->cfg.depth_factor, h->cfg.image_size, h->ref_kp, h->cfg.fix_root, static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)),
-                                  p->ws + p->sa_ws, p->sa_ws_bytes, static_cast<float*>(ptr(o.out3)), static_cast<float*>(ptr(o.out4)), static_cast<float*>(ptr(o.out5)), st, &nl));
+                                  p->ws + p->sa_ws, p->sa_ws_bytes, static_cast<float*>(ptr(o.out3)), static_cast<float*>(ptr(o.out4)), static_cast<float*>(ptr(o.out5)), st_op, &nl));
         n_launch = nl;
         break;
       }
       case OP_FK:
         HRP_TRY(fk_launch(h->fk, static_cast<const float*>(ptr(o.in)), static_cast<const float*>(ptr(o.in2)), static_cast<const float*>(ptr(o.in3)), static_cast<const float*>(ptr(o.in4)), B,
-                          static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)), st));
+                          static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)), st_op));
         break;
     }
     launches += n_launch;
+    if (lanes && h->signals[oi]) {
+      op_event[oi] = new_event();
+      if (!op_event[oi]) return fail(HRP_ERR_CUDA, "cudaEventCreate failed");
+      HRP_CUDA(cudaEventRecord(op_event[oi], st_op));
+    }
     if (prof) {
       HRP_CUDA(cudaEventRecord(prof->e1, st));
       HRP_CUDA(cudaEventSynchronize(prof->e1));
@@ -845,6 +928,13 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
                 o.stride, o.res >= 0 ? 1 : 0, o.out_nchw, ms, ms > 0 ? o.flops * B / (ms * 1e-3) / 1e12 : 0.0);
     }
   }
+  if (lanes)                                     // join
+    for (int l = 1; l < h->n_lanes; ++l) {
+      cudaEvent_t e = new_event();
+      if (!e) return fail(HRP_ERR_CUDA, "cudaEventCreate failed");
+      HRP_CUDA(cudaEventRecord(e, h->lane_stream[l]));
+      HRP_CUDA(cudaStreamWaitEvent(st, e, 0));
+    }
   h->last_launches = launches;
   return HRP_OK;
 }
@@ -890,6 +980,8 @@ extern "C" void hrp_destroy(hrp_handle* h) {
   }
   for (void* p : h->dev_allocs) cudaFree(p);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+  for (int l = 1; l < kMaxLanes; ++l) if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
+  for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   hrp_fk_destroy(h->fk);
   delete h;
 }
@@ -939,6 +1031,9 @@ extern "C" int hrp_finalize_weights(hrp_handle* h) {
   HRP_CUDA(cudaDeviceSynchronize());
   h->host.clear();
   HRP_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+  if (h->n_lanes > kMaxLanes) return fail(HRP_ERR_INVALID, "internal: %d lanes", h->n_lanes);
+  for (int l = 1; l < h->n_lanes; ++l) HRP_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
+  if (const char* e = getenv("HRP_NO_LANES")) h->use_lanes = atoi(e) == 0;
   h->finalized = true;
   return HRP_OK;
 }
@@ -959,6 +1054,10 @@ extern "C" size_t hrp_workspace_bytes(hrp_handle* h, int B) {
 extern "C" int hrp_set_option(hrp_handle* h, const char* name, int64_t value) {
   if (!h || !name) return fail(HRP_ERR_INVALID, "hrp_set_option: null argument");
   if (std::strcmp(name, "cuda_graph") == 0) { h->use_graph = value != 0; return HRP_OK; }
+  if (std::strcmp(name, "lanes") == 0) {         // multi-stream graph (default 1); takes effect for graphs not yet captured
+    h->use_lanes = value != 0;
+    return HRP_OK;
+  }
   return fail(HRP_ERR_INVALID, "hrp_set_option: unknown option '%s'", name);
 }
 
@@ -982,7 +1081,7 @@ extern "C" int hrp_forward(hrp_handle* h, const float* x_reg, const float* x_roo
   if (!p->exec[same]) {
     cudaGraph_t g = nullptr;
     HRP_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
-    const int rs = run_ops(h, p, IoPtrs{s_xreg, s_xroot, s_kv, s_K, s_out}, h->capture_stream, nullptr);
+    const int rs = run_ops(h, p, IoPtrs{s_xreg, s_xroot, s_kv, s_K, s_out}, h->capture_stream, nullptr, h->use_lanes && h->n_lanes > 1);
     cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &g);
     if (rs != HRP_OK) { if (g) cudaGraphDestroy(g); return rs; }
     if (ce != cudaSuccess) return fail(HRP_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));

@@ -253,6 +253,23 @@ def test_fullnet_graph_replay_and_eager_agree(dev):
         assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
 
 
+
+@pytest.mark.parametrize("backbone,prec", [("resnet50", "bf16"), ("hrnet32", "bf16"), ("hrnet32", "fp32")])
+def test_fullnet_multi_lane_graph_equals_serial_execution(backbone, prec, dev):
+    """The captured graph runs HRNet branches, the two backbones and the heads on separate streams (lane arenas + event
+    edges); at a batch that really overlaps them it must reproduce the serial single-stream execution bit for bit."""
+    m = gpu_model("panda", backbone, dev, prec)
+    B = 24
+    img, K, kv = helpers.inputs(B, 4141)
+    img, K, kv = img.to(dev), K.to(dev), kv.to(dev)
+    m.set_option("cuda_graph", 0)
+    serial = {k: v.clone() for k, v in m.forward_dict(img, K, kv).items()}
+    m.set_option("cuda_graph", 1)
+    for _ in range(3):
+        out = m.forward_dict(img, K, kv)
+        for k in out:
+            assert torch.equal(out[k], serial[k]), k
+
 def test_fullnet_batch64_frames_are_independent(dev):
     """BASELINE config 2 size (Panda, B=64): every frame of the big batch equals the same frame run alone or in a small
     batch (eval-mode BN, per-frame softmax/FK => no cross-frame coupling), and the oracle agrees on a sample of frames."""
