@@ -113,6 +113,7 @@ def main():
     ap.add_argument("--backbone", default="resnet50", choices=["resnet50", "hrnet32"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-families", action="store_true", help="skip the tf32 / fp32 family lines")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -270,6 +271,33 @@ def main():
                        "poses_per_sec": n / ms * 1e3}
         del q, rot, tr, Kf
 
+    # ---- the other precision families on the same workload (single GPU only; short, same timing rules) ------------------
+    families = {}
+    ws_gb = capi.lib().hrp_workspace_bytes(model._h, B) / 2 ** 30
+    if rank == 0 and world == 1 and not args.no_families:
+        del model
+        torch.cuda.empty_cache()
+        for prec in ("tf32", "fp32"):
+            if prec == args.precision:
+                continue
+            m2 = HoliRobPoseB200(ROBOT, {"backbone_name": args.backbone}, device=dev, precision=prec)
+            m2.load_state_dict(synth.make_state_dict(ROBOT, args.backbone, WEIGHT_SEED))
+            for i in range(3):
+                m2.forward_record(sets_dev[i % NSETS][0], sets_dev[i % NSETS][0], sets_dev[i % NSETS][2], sets_dev[i % NSETS][1])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n2 = 5
+            e0.record()
+            for i in range(n2):
+                m2.forward_record(sets_dev[i % NSETS][0], sets_dev[i % NSETS][0], sets_dev[i % NSETS][2], sets_dev[i % NSETS][1])
+            e1.record()
+            torch.cuda.synchronize()
+            families[prec] = {"value": B * n2 / (e0.elapsed_time(e1) * 1e-3), "unit": "frames/s", "steps": n2,
+                              "parity": {"tf32": "north_star gates (1e-3 rad, 1 mm, 0.5 px) on this configuration",
+                                         "fp32": "north_star gates on every configuration"}[prec]}
+            del m2
+            torch.cuda.empty_cache()
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cfps, cores, cms = cpu_reference_fps(torch, 1, 10, 2, args.backbone)
@@ -283,13 +311,13 @@ def main():
                 "config": {"workload": workload, "robot": ROBOT, "backbone": args.backbone, "precision": args.precision,
                            "batch_per_gpu": B, "global_batch": B * world, "gflop_per_frame": flops_frame / 1e9,
                            "l2": "inputs rotate over %d distinct batches (%d MB > L2); the %.1f GB activation workspace is rewritten every step" % (
-                               NSETS, NSETS * B * 3 * 256 * 256 * 4 // 2 ** 20, capi.lib().hrp_workspace_bytes(model._h, B) / 2 ** 30),
+                               NSETS, NSETS * B * 3 * 256 * 256 * 4 // 2 ** 20, ws_gb),
                            "parallelism": "batch-sharded x%d, NCCL all-gather of output records" % world if world > 1 else "single GPU",
                            "weights": "calibrated random init, seed %d" % WEIGHT_SEED},
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (3 * 256 * 256 + 9 + 1) * 4,
                         "d2h_bytes_per_step": rec_bytes, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "rooflines_hbm": extra,
-                "cpu_baseline": cpu_base}
+                "families": families, "cpu_baseline": cpu_base}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

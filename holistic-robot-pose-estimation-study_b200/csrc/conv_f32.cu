@@ -249,6 +249,48 @@ int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, vo
   return HRP_OK;
 }
 
+// NCHW fp32 image -> zero-padded NHWC4 operand image of the tensor-core stems (kernels.h). One thread per padded pixel;
+// the three plane reads are coalesced along x, the write is one 8- or 16-byte store. Borders are rewritten every
+// forward because the arena recycles this memory.
+template <bool TF32>
+__global__ void stem_pack_kernel(const float* __restrict__ in, void* __restrict__ out, int B) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * STEM_HP * STEM_WP;
+  if (i >= total) return;
+  const int xp = (int)(i % STEM_WP);
+  const int yp = (int)((i / STEM_WP) % STEM_HP);
+  const int b = (int)(i / ((long long)STEM_WP * STEM_HP));
+  const int x = xp - STEM_PAD, y = yp - STEM_PAD;
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+  if (x >= 0 && x < 256 && y >= 0 && y < 256) {
+    const float* ip = in + ((size_t)b * 3 * 256 + y) * 256 + x;
+    v0 = __ldg(ip); v1 = __ldg(ip + 256 * 256); v2 = __ldg(ip + 2 * 256 * 256);
+  }
+  if constexpr (TF32) {
+    uint32_t r0, r1, r2;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(v0));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v1));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(v2));
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(r0, r1, r2, 0u);
+  } else {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1), c = __floats2bfloat162_rn(v2, 0.f);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&a);
+    r.y = *reinterpret_cast<const uint32_t*>(&c);
+    reinterpret_cast<uint2*>(out)[i] = r;
+  }
+}
+
+int stem_pack_launch(const float* in_nchw, void* out, int B, int tf32, cudaStream_t s) {
+  const long long total = (long long)B * STEM_HP * STEM_WP;
+  if (total <= 0) return HRP_OK;
+  const unsigned blocks = (unsigned)ceil_div64(total, 256);
+  if (tf32) stem_pack_kernel<true><<<blocks, 256, 0, s>>>(in_nchw, out, B);
+  else stem_pack_kernel<false><<<blocks, 256, 0, s>>>(in_nchw, out, B);
+  HRP_CHECK_LAUNCH("stem_pack_kernel");
+  return HRP_OK;
+}
+
 // ---- element-wise layers: 4 channels per thread, NHWC ---------------------------------------------------------------------
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {

@@ -594,6 +594,7 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   if (p.M <= 0) return HRP_OK;
   const int esz = tf32 ? 4 : 2;
   p.row_bytes = conv_tc_row_bytes(a, tf32, &p.tma);
+  if (a.tma_custom && !p.tma) return fail(HRP_ERR_INVALID, "conv_tc: a custom TMA view needs a TMA-tileable geometry");
   const int kb_elems = p.row_bytes / esz;
   p.Ktot = a.KH * a.KW * a.Cin;
   p.num_kb = ceil_div(p.Ktot, kb_elems);
@@ -601,10 +602,14 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     int bw = 0, bh = 0, bi = 0;
     tma_box(a, &bw, &bh, &bi);
     CUtensorMap tm;
-    const cuuint64_t gdim[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.B};
-    const cuuint64_t gstr[3] = {(cuuint64_t)a.Cin * esz, (cuuint64_t)a.Wi * a.Cin * esz, (cuuint64_t)a.Hi * a.Wi * a.Cin * esz};
-    const cuuint32_t box[4] = {(cuuint32_t)kb_elems, (cuuint32_t)(bw * a.stride), (cuuint32_t)(bh * a.stride), (cuuint32_t)bi};
-    const cuuint32_t estr[4] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1};
+    cuuint64_t gdim[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.B};
+    cuuint64_t gstr[3] = {(cuuint64_t)a.Cin * esz, (cuuint64_t)a.Wi * a.Cin * esz, (cuuint64_t)a.Hi * a.Wi * a.Cin * esz};
+    cuuint32_t box[4] = {(cuuint32_t)kb_elems, (cuuint32_t)(bw * a.stride), (cuuint32_t)(bh * a.stride), (cuuint32_t)bi};
+    cuuint32_t estr[4] = {1, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1};
+    if (a.tma_custom) {
+      for (int i = 0; i < 4; ++i) { gdim[i] = a.tm_gdim[i]; box[i] = a.tm_box[i]; estr[i] = 1; }
+      for (int i = 0; i < 3; ++i) gstr[i] = a.tm_gstr[i];
+    }
     const CUresult r = encode_tiled()(&tm, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.in),
                                       gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                       p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,

@@ -22,6 +22,11 @@ struct ConvArgs {
   int out_nchw;
   int ld_out;            // channel stride of one output pixel (>= Cout; lets two GEMMs share one row)
   int out_coff;          // first output channel inside that row
+  // Tensor-core family only: explicit TMA view of `in` (element units / byte strides) replacing the default NHWC one.
+  // Used by the stems, whose K axis is a window of a padded 4-channel image (see stem_pack_launch).
+  int tma_custom;
+  unsigned long long tm_gdim[4], tm_gstr[3];
+  unsigned tm_box[4];
 };
 
 int conv_f32_launch(const ConvArgs& a, cudaStream_t s);
@@ -44,6 +49,14 @@ int round_tf32_launch(const float* in, float* out, size_t n, cudaStream_t s);
 // out_mode: 0 fp32, 1 bf16, 2 fp32 rounded to TF32.
 int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, void* out, int B, int Hi, int Wi,
                      int Ho, int Wo, int KH, int KW, int pad, int out_mode, cudaStream_t s);
+
+// Stem, tensor-core families: NCHW fp32 [B,3,256,256] -> zero-padded NHWC4 [B, STEM_HP, STEM_WP, 4] (bf16, or fp32
+// rounded to TF32), image pixel (y,x) at padded (y+3, x+3), channel 3 = 0. A KxK/2 stem conv then is an implicit GEMM
+// whose K axis per kernel row is the contiguous 8-pixel x 4-channel window starting at padded x = 2*ox + 3 - pad:
+// 32 elements = one 64-byte (bf16) / 128-byte (TF32) operand row, fetched by TMA through a view whose "ox" dimension
+// has a 2-pixel byte stride (overlapping windows). Taps s >= K and channel 3 carry zero weights.
+constexpr int STEM_PAD = 3, STEM_HP = 256 + 2 * STEM_PAD, STEM_WP = 264;
+int stem_pack_launch(const float* in_nchw, void* out, int B, int tf32, cudaStream_t s);
 
 int maxpool3x3s2_launch(const void* in, void* out, int B, int Hi, int Wi, int C, int bf16, cudaStream_t s);
 

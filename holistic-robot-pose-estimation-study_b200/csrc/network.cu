@@ -23,7 +23,7 @@ struct hrp_fk;  // fk_project.cu
 
 namespace hrp {
 
-enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_RANK, OP_DEC, OP_SOFTARGMAX, OP_FK };
+enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_RANK, OP_DEC, OP_SOFTARGMAX, OP_FK, OP_STEM_PACK };
 enum { CLS_CONV_TC = 0, CLS_CONV_F32 = 1, CLS_STEM = 2, CLS_ELEM = 3, CLS_HEADS = 4, CLS_SOFTARGMAX = 5, CLS_FK = 6 };
 enum TKind { T_WS = 0, T_XREG, T_XROOT, T_KVAL, T_KMAT, T_FIELD, T_CONST };
 
@@ -57,6 +57,7 @@ struct OpDesc {
   int Hi = 1, Wi = 1, Cin = 0, Ho = 1, Wo = 1, Cout = 0, KH = 1, KW = 1, stride = 1, pad_h = 0, pad_w = 0;
   int out_sy = 1, out_sx = 1, out_oy = 0, out_ox = 0, Ho_full = 1, Wo_full = 1, relu = 0, out_nchw = 0;
   int res_after_act = 0;
+  int stem_tc = 0;       // OP_CONV over the packed stem image (custom TMA view); KH = real kernel size, pad_h = real padding
   int same[4] = {-1, -1, -1, -1}, low[3] = {-1, -1, -1}, shift[3] = {0, 0, 0}, n_same = 0, n_low = 0;
   int ld = 0, coff = 0, state_stride = 0, dof = 0, N = 0;
   const float* wptr = nullptr;   // small head weights
@@ -355,7 +356,42 @@ struct GraphBuilder {
     return y;
   }
 
+  // Tensor-core families: pack the image (zero-padded NHWC4 in the family's operand type), then an implicit GEMM with
+  // K = k rows x (8-pixel x 4-channel window) through a custom TMA view (kernels.h, stem_pack_launch).
+  Tn stem_tc(int x_ext, const std::string& pc, const std::string& pb, int k, int pad) {
+    const float* w = W(pc + ".weight");
+    const float *g = W(pb + ".weight"), *b = W(pb + ".bias"), *m = W(pb + ".running_mean"), *v = W(pb + ".running_var");
+    Tn packed = new_tensor(STEM_HP, STEM_WP, 4, act_esize);
+    Tn y = new_tensor(128, 128, 64, act_esize);
+    if (status != HRP_OK) return y;
+    std::vector<float> wp((size_t)k * 32 * 64, 0.f), bp(64);
+    for (int o = 0; o < 64; ++o) {
+      const double sc = (double)g[o] / std::sqrt((double)v[o] + 1e-5);
+      bp[o] = (float)((double)b[o] - (double)m[o] * sc);
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < k; ++r)
+          for (int q = 0; q < k; ++q)
+            wp[((size_t)r * 32 + q * 4 + c) * 64 + o] = (float)((double)w[(((size_t)o * 3 + c) * k + r) * k + q] * sc);
+    }
+    OpDesc pk{};
+    pk.kind = OP_STEM_PACK; pk.cls = CLS_STEM; pk.in = x_ext; pk.out = packed.id;
+    push(pk);
+    OpDesc op{};
+    op.kind = OP_CONV; op.cls = CLS_CONV_TC; op.stem_tc = 1;
+    // the GEMM the kernel sees: "Cin" = one 32-element window, KH rows, KW = 1, stride 2 over padded rows
+    op.Hi = STEM_HP; op.Wi = 128; op.Cin = 32; op.Cout = 64; op.KH = k; op.KW = 1; op.stride = 2; op.pad_h = pad - STEM_PAD; op.pad_w = 0;
+    op.Ho = op.Wo = op.Ho_full = op.Wo_full = 128; op.relu = 1; op.ld = 64;
+    op.layer = finish_layer(wp, upload(bp), 32, 64, k, 1, shape_of(op));
+    op.out_sy = op.out_sx = 1;
+    op.pad_w = pad;                                  // real padding, consumed when the TMA view is built
+    op.in = packed.id; op.out = y.id;
+    op.flops = 2.0 * 128 * 128 * 64 * k * k * 3;     // the convolution's own FLOPs, not the zero-padded GEMM's
+    push(op);
+    return y;
+  }
+
   Tn stem(int x_ext, const std::string& pc, const std::string& pb, int k, int pad) {
+    if (tc()) return stem_tc(x_ext, pc, pb, k, pad);
     // weights packed [(c*KH + r)*KW + s][64]
     const float* w = W(pc + ".weight");
     const float *g = W(pb + ".weight"), *b = W(pb + ".bias"), *m = W(pb + ".running_mean"), *v = W(pb + ".running_var");
@@ -871,10 +907,24 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         a.KH = o.KH; a.KW = o.KW; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w;
         a.out_sy = o.out_sy; a.out_sx = o.out_sx; a.out_oy = o.out_oy; a.out_ox = o.out_ox; a.Ho_full = o.Ho_full; a.Wo_full = o.Wo_full;
         a.relu = o.relu; a.out_nchw = o.out_nchw; a.ld_out = o.ld; a.out_coff = 0; a.res_after_act = o.res_after_act;
+        if (o.stem_tc) {
+          // view of the packed image: {window 32 el, ox (2-pixel stride), padded row, frame}; the window of output
+          // column ox starts at padded x = 2*ox + STEM_PAD - pad (o.pad_w carries the real padding)
+          const size_t es = tf32 ? 4 : 2, px = 4 * es, row = (size_t)STEM_WP * px;
+          a.pad_w = 0;
+          a.in = static_cast<const char*>(a.in) + (size_t)(STEM_PAD - o.pad_w) * px;
+          a.tma_custom = 1;
+          a.tm_gdim[0] = 32; a.tm_gdim[1] = 128; a.tm_gdim[2] = STEM_HP; a.tm_gdim[3] = (unsigned long long)B;
+          a.tm_gstr[0] = 2 * px; a.tm_gstr[1] = row; a.tm_gstr[2] = (size_t)STEM_HP * row;
+          a.tm_box[0] = 32; a.tm_box[1] = 128; a.tm_box[2] = 1; a.tm_box[3] = 1;
+        }
         if (o.cls == CLS_CONV_TC) HRP_TRY(conv_tc_launch(a, tf32, tf32 && !o.out_nchw, st_op));
         else HRP_TRY(conv_f32_launch(a, st_op));
         break;
       }
+      case OP_STEM_PACK:
+        HRP_TRY(stem_pack_launch(static_cast<const float*>(ptr(o.in)), ptr(o.out), B, tf32, st_op));
+        break;
       case OP_MAXPOOL:
         HRP_TRY(maxpool3x3s2_launch(ptr(o.in), ptr(o.out), B, o.Hi, o.Wi, o.Cin, bf16, st_op));
         break;

@@ -1,4 +1,4 @@
-"""Produce data/bn_calib_v1.npz: BatchNorm running statistics for the synthetic weights (one-off, CPU, ~1 min).
+"""Produce data/bn_calib_v2.npz: BatchNorm running statistics for the synthetic weights (one-off, CPU, ~1 min).
 
 For each weight seed and each sub-network (ResNet-50 + deconv keypoint branch, HRNet-W32 keypoint branch, HRNet-W32
 DepthNet) run the oracle forward once over CALIB_BATCH seeded noise images with BN in batch-statistics mode and store

@@ -290,13 +290,17 @@ def test_fullnet_batch64_frames_are_independent(dev):
     check_gates(auto, ref2)
 
 
-# Tensor-core families: separately stated tolerances (north_star). The synthetic weights are deliberately harsh (an
-# untrained network amplifies the per-layer operand rounding 2^-11 / 2^-9 by ~30x over ~55 sequential layers; DESIGN.md
-# "Precision families"), so these bounds are about this weight set: worst case measured on B200 x ~2.
+# Tensor-core families against the reference's fp32 forward (goldens). TF32 (operands rounded to nearest, fp32
+# accumulation in TMEM) is held to the north_star parity gates themselves -- 1e-3 rad, 1 mm, 0.5 px -- on the shipped
+# configuration (ResNet-50 keypoint backbone; measured worst case 5.4e-4 rad / 0.2 mm / 0.15 px); with the HRNet-W32
+# keypoint backbone (twice as many sequential roundings before the heads) its joint angles reach 1.8e-3 rad, stated as
+# 3e-3. bf16 carries the separately stated tolerance 2e-2 rad / 5 mm / 3 px (measured worst case 1.4e-2 rad, 0.9 mm,
+# 2.1 px). The fp32 family meets the gates everywhere (test_fullnet_against_reference_golden). DESIGN.md section 2.
 FAMILY_TOL = {
-    "tf32": dict(joint_angles=6e-2, root_depth=3e-3, px=8.0, rot6d=8e-2, uvd=3e-2, m3d=4e-2),
-    "bf16": dict(joint_angles=3e-1, root_depth=2e-2, px=40.0, rot6d=4e-1, uvd=1.5e-1, m3d=2e-1),
+    "tf32": dict(joint_angles=helpers.TOL_RAD, root_depth=helpers.TOL_DEPTH_M, px=helpers.TOL_PX, rot6d=2e-3, uvd=1e-3, m3d=2e-3, rel=0.01),
+    "bf16": dict(joint_angles=2e-2, root_depth=5e-3, px=3.0, rot6d=2e-2, uvd=5e-3, m3d=1.5e-2, rel=0.05),
 }
+FAMILY_TOL_HRNET_KP = {"tf32": dict(joint_angles=3e-3, rot6d=3e-3)}
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
@@ -310,13 +314,13 @@ def test_fullnet_tensor_core_families_against_reference_golden(prec, robot, back
     names = ["joint_angles", "rot6d", "trans", "root_uv", "root_depth", "uvd", "kp3d_int", "kp3d_fk", "kp2d_int", "kp2d_fk"]
     d = {k: helpers.maxdiff(out[k], g[k]) for k in names}
     print(prec, robot, backbone, {k: "%.2e" % v for k, v in d.items()})
-    t = FAMILY_TOL[prec]
+    t = dict(FAMILY_TOL[prec], **(FAMILY_TOL_HRNET_KP.get(prec, {}) if backbone == "hrnet32" else {}))
     assert d["joint_angles"] < t["joint_angles"] and d["root_depth"] < t["root_depth"] and d["rot6d"] < t["rot6d"], d
     assert max(d["kp2d_int"], d["kp2d_fk"], d["root_uv"]) < t["px"] and d["uvd"] < t["uvd"], d
     assert max(d["kp3d_int"], d["kp3d_fk"], d["trans"]) < t["m3d"], d
-    # the features feeding the heads stay close in the relative-RMS sense (the honest measure for a chaotic random net)
+    # the 2048-d features feeding the heads, relative RMS
     for name, key in (("xf", "probe_xf"), ("img_feat", "probe_img_feat")):
         a = m.debug_tensor(name, B).view(B, -1).cpu().double().numpy()
         rel = float(np.linalg.norm(a - g[key]) / np.linalg.norm(g[key]))
-        assert rel < (0.05 if prec == "tf32" else 0.25), (name, rel)
+        assert rel < t["rel"], (name, rel)
     assert m.launch_count() > 300
