@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "tc_ptx.h"
 
 namespace hrp {
 namespace {
@@ -57,109 +58,7 @@ struct TcParams {
   int round_tf32;    // round fp32 NHWC outputs to TF32 (nearest, ties away) so the next MMA sees exact operands
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-// for waiters off the critical path: back off between polls so the spinning warp leaves issue slots to the producers
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(20);
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-template <bool TF32>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (TF32) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(ignored)=1 | SBO = 1024 B
-// (one 8-row group) | version 1 | layout 2. Stepping K inside the 128-byte row adds bytes>>4 to the start field.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int row_bytes) {
-  const uint64_t sbo = (uint64_t)(8 * row_bytes) >> 4;       // one 8-row group
-  const uint64_t layout = row_bytes == 128 ? 2ull : 4ull;    // SWIZZLE_128B : SWIZZLE_64B
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-      ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-      : "memory");
-}
-
-__device__ __forceinline__ float round_tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+using namespace tc;
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------
 template <int EPI>
@@ -291,9 +190,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     for (int k = max(it - lag, 0); k < it; ++k) { mbar_arrive(bar_full + 8u * as); if (++as == S) as = 0; }
     }
   } else if (warp == 4) {
-    // ===== MMA issuer ===================================================================================================
+    // ===== MMA issuer: all lanes walk the loops (uniform operands), one elected lane issues (tc_ptx.h: elect_one) ========
+    const bool leader = elect_one();
     const uint32_t idesc = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                            ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    const uint32_t dhi = umma_desc_hi(p.row_bytes);
+    const int kbe = p.row_bytes / ESZ;                          // K elements per k-block
     int li = 0, s = 0;
     uint32_t ph = 0;
     const int num_kb = p.num_kb;
@@ -305,13 +207,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(bar_full + 8u * s, ph);
         tc_fence_after();
-        if (lane == 0) {
-          const int kbe = p.row_bytes / ESZ;                  // K elements per k-block
-          const int kleft = p.Ktot - kb * kbe;
-          const int nk = (kleft >= kbe ? kbe : kleft) / UK;
-          const uint64_t da = umma_desc(sA + (uint32_t)(s * a_stage), p.row_bytes), db = umma_desc(sB + (uint32_t)(s * b_stage), p.row_bytes);
-          for (int kk = 0; kk < nk; ++kk) umma<TF32>(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0);
-          umma_commit(bar_empty + 8u * s);                     // frees the stage once these MMAs have read it
+        const int kleft = p.Ktot - kb * kbe;
+        const int nk = (kleft >= kbe ? kbe : kleft) / UK;
+        const uint32_t aa = sA + (uint32_t)(s * a_stage), bb = sB + (uint32_t)(s * b_stage);
+        for (int kk = 0; kk < nk; ++kk)
+          if (leader) umma<TF32>(tmem_d, umma_desc_at(aa + 32u * kk, dhi), umma_desc_at(bb + 32u * kk, dhi), idesc, (kb | kk) != 0);
+        if (leader) {
+          umma_commit(bar_empty + 8u * s);                       // frees the stage once these MMAs have read it
           if (kb == num_kb - 1) umma_commit(bar_accf + 8u * buf);   // accumulator complete
         }
         __syncwarp();
@@ -320,8 +222,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     }
   } else if (warp == 5) {
     // ===== loader: weights [kb][Cout][row_bytes] pre-swizzled, one bulk copy per k-block; in TMA mode also the
-    // activation tile: one 4-D tensor copy {channels, Wo-run, rows, images} per k-block, zero-filled outside the image ====
-    if (lane == 0) {
+    // activation tile: one 4-D tensor copy {channels, Wo-run, rows, images} per k-block, zero-filled outside the image.
+    // All lanes walk the loops, one elected lane issues (uniform operands; tc_ptx.h: elect_one) ============================
+    {
+      const bool leader = elect_one();
       const size_t kb_stride = (size_t)a.Cout * p.row_bytes;
       const int kbe = p.row_bytes / ESZ;
       const uint32_t tx = (uint32_t)b_stage + (p.tma ? (uint32_t)a_stage : 0u);
@@ -335,13 +239,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         int c = 0, fr = 0, fs = 0;
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           if (it >= S) mbar_wait(bar_empty + 8u * s, ph);
-          mbar_arrive_expect_tx(bar_full + 8u * s, tx);
+          const uint32_t bar = bar_full + 8u * s;
+          if (leader) {
+            mbar_arrive_expect_tx(bar, tx);
+            if (p.tma) tma_load_4d(sA + (uint32_t)(s * a_stage), p.tmap, c, x0 + fs, y0 + fr, b0, bar);
+            bulk_g2s(sB + (uint32_t)(s * b_stage), wsrc + kb * kb_stride, (uint32_t)b_stage, bar);
+          }
           if (p.tma) {
-            tma_load_4d(sA + (uint32_t)(s * a_stage), p.tmap, c, x0 + fs, y0 + fr, b0, bar_full + 8u * s);
             c += kbe;
             if (c >= a.Cin) { c = 0; if (++fs == a.KW) { fs = 0; ++fr; } }
           }
-          bulk_g2s(sB + (uint32_t)(s * b_stage), wsrc + kb * kb_stride, (uint32_t)b_stage, bar_full + 8u * s);
           if (++s == S) { s = 0; ph ^= 1u; }
         }
       }
@@ -588,6 +495,7 @@ int conv_tc_row_bytes(const ConvArgs& a, int tf32, int* use_tma) {
 int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st) {
   if (!conv_tc_supported(a, tf32))
     return fail(HRP_ERR_INVALID, "conv_tc: unsupported shape Cin=%d Cout=%d ld=%d coff=%d", a.Cin, a.Cout, a.ld_out, a.out_coff);
+  if (!a.tma_custom && conv_slab_supported(a, tf32)) return conv_slab_launch(a, tf32, round_tf32, st);
   TcParams p{};
   p.a = a;
   p.M = a.B * a.Ho * a.Wo;

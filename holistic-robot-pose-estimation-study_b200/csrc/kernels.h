@@ -36,6 +36,10 @@ int conv_f32_launch(const ConvArgs& a, cudaStream_t s);
 // TF32 (nearest) for the next layer's operands.
 bool conv_tc_supported(const ConvArgs& a, int tf32);
 int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s);
+// Shifted-GEMM kernel for 3x3 / stride 1 / pad 1 convs with Cin == Cout (conv_slab.cu); same operands and weight image
+// as conv_tc. conv_tc_launch dispatches to it when it applies.
+bool conv_slab_supported(const ConvArgs& a, int tf32);
+int conv_slab_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s);
 // Operand-row width (64 / 128 bytes) the layer described by `a` (shape fields only) must be packed for; *use_tma tells
 // whether its activations will arrive by TMA tensor copies or by the cp.async gather.
 int conv_tc_row_bytes(const ConvArgs& a, int tf32, int* use_tma);

@@ -974,8 +974,8 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
       HRP_CUDA(cudaEventElapsedTime(&ms, prof->e0, prof->e1));
       prof->ms[o.cls] += ms; prof->launches[o.cls] += n_launch; prof->flops[o.cls] += o.flops * B;
       if (prof->dump)
-        fprintf(prof->dump, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.3f\n", (int)o.kind, o.cls, B, o.Hi, o.Wi, o.Cin, o.Ho, o.Wo, o.Cout, o.KH,
-                o.stride, o.res >= 0 ? 1 : 0, o.out_nchw, ms, ms > 0 ? o.flops * B / (ms * 1e-3) / 1e12 : 0.0);
+        fprintf(prof->dump, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.3f,%d\n", (int)o.kind, o.cls, B, o.Hi, o.Wi, o.Cin, o.Ho, o.Wo, o.Cout, o.KH,
+                o.stride, o.res >= 0 ? 1 : 0, o.out_nchw, ms, ms > 0 ? o.flops * B / (ms * 1e-3) / 1e12 : 0.0, o.lane);
     }
   }
   if (lanes)                                     // join
@@ -1163,7 +1163,7 @@ extern "C" int hrp_forward_profile(hrp_handle* h, const float* x_reg, const floa
   HRP_CUDA(cudaEventCreate(&prof.e1));
   if (const char* path = getenv("HRP_DUMP_OPS")) {
     prof.dump = fopen(path, "w");
-    if (prof.dump) fprintf(prof.dump, "kind,cls,B,Hi,Wi,Cin,Ho,Wo,Cout,k,stride,res,nchw,ms,tflops\n");
+    if (prof.dump) fprintf(prof.dump, "kind,cls,B,Hi,Wi,Cin,Ho,Wo,Cout,k,stride,res,nchw,ms,tflops,lane\n");
   }
   const int rs = run_ops(h, p, IoPtrs{x_reg, x_root, k_value, Kmat, out}, (cudaStream_t)stream, &prof);
   if (prof.dump) fclose(prof.dump);
@@ -1243,5 +1243,75 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
   }
   if (cudaStreamSynchronize(st) != cudaSuccess && rs == HRP_OK) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: %s", cudaGetErrorString(cudaGetLastError()));
   for (void* d : tmp) cudaFree(d);
+  return rs;
+}
+
+// Micro-benchmark of one tensor-core conv layer in isolation (random operands already in the family's type; the weight
+// image is packed once; `iters` back-to-back launches timed with CUDA events on `stream`). Tuning aid for the kernels.
+extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int Cout, int k, int stride, int with_residual,
+                              int iters, float* ms_per_launch, void* stream) {
+  if (precision != HRP_PREC_TF32 && precision != HRP_PREC_BF16) return fail(HRP_ERR_INVALID, "hrp_conv_bench: tensor-core families only");
+  if (!ms_per_launch || iters <= 0) return fail(HRP_ERR_INVALID, "hrp_conv_bench: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tf32 = precision == HRP_PREC_TF32;
+  const size_t es = tf32 ? 4 : 2;
+  ConvArgs a{};
+  a.B = B; a.Hi = H; a.Wi = W; a.Cin = Cin; a.Cout = Cout; a.KH = a.KW = k; a.stride = stride; a.pad_h = a.pad_w = k / 2;
+  a.Ho = (H + 2 * a.pad_h - k) / stride + 1; a.Wo = (W + 2 * a.pad_w - k) / stride + 1;
+  a.out_sy = a.out_sx = 1; a.Ho_full = a.Ho; a.Wo_full = a.Wo; a.relu = 1; a.ld_out = Cout;
+  if (!conv_tc_supported(a, tf32)) return fail(HRP_ERR_INVALID, "hrp_conv_bench: shape not supported");
+  const size_t n_in = (size_t)B * H * W * Cin, n_out = (size_t)B * a.Ho * a.Wo * Cout, K = (size_t)k * k * Cin;
+  std::vector<float> wp(K * Cout), bp(Cout, 0.1f);
+  uint32_t lcg = 12345u;
+  for (auto& v : wp) { lcg = lcg * 1664525u + 1013904223u; v = ((lcg >> 8) * (1.0f / 16777216.0f) - 0.5f) / std::sqrt((float)K); }
+  const int rb = conv_tc_row_bytes(a, tf32, nullptr);
+  std::vector<uint8_t> img(pack_conv_tc_bytes((int)K, Cout, tf32, rb));
+  pack_conv_tc(wp.data(), (int)K, Cout, tf32, rb, img.data());
+  void *dw = nullptr, *din = nullptr, *dout = nullptr, *dres = nullptr, *db = nullptr;
+  float* tmp = nullptr;
+  int rs = HRP_OK;
+  auto A = [&](void** ptr, size_t bytes) { if (rs == HRP_OK && cudaMalloc(ptr, std::max<size_t>(bytes, 16)) != cudaSuccess) { cudaGetLastError(); rs = fail(HRP_ERR_NOMEM, "hrp_conv_bench: out of device memory"); } };
+  A(&dw, img.size()); A(&din, n_in * es); A(&dout, n_out * es); A(&db, (size_t)Cout * 4); A((void**)&tmp, std::max(n_in, n_out) * 4);
+  if (with_residual) A(&dres, n_out * es);
+  if (rs == HRP_OK) {
+    std::vector<float> host(std::max(n_in, n_out));
+    for (auto& v : host) { lcg = lcg * 1664525u + 1013904223u; v = (lcg >> 8) * (1.0f / 16777216.0f) - 0.5f; }
+    cudaMemcpyAsync(dw, img.data(), img.size(), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(db, bp.data(), (size_t)Cout * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(tmp, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st);
+    rs = tf32 ? round_tf32_launch(tmp, static_cast<float*>(din), n_in, st) : cast_f32_to_bf16_launch(tmp, din, n_in, st);
+    if (rs == HRP_OK && with_residual) rs = tf32 ? round_tf32_launch(tmp, static_cast<float*>(dres), n_out, st) : cast_f32_to_bf16_launch(tmp, dres, n_out, st);
+    cudaStreamSynchronize(st);
+  }
+  a.in = din; a.w = dw; a.bias = static_cast<const float*>(db); a.res = dres; a.out = dout;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (rs == HRP_OK) {
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3 && rs == HRP_OK; ++i) rs = conv_tc_launch(a, tf32, tf32, st);
+    // the timed launches replay from a CUDA graph so that host-side launch cost (tensor-map encoding, ~15 us) is not what
+    // gets measured for kernels shorter than that
+    cudaStream_t cs = nullptr;
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    cudaStreamSynchronize(st);
+    if (rs == HRP_OK && cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      for (int i = 0; i < iters && rs == HRP_OK; ++i) rs = conv_tc_launch(a, tf32, tf32, cs);
+      if (cudaStreamEndCapture(cs, &g) != cudaSuccess || cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv_bench: graph capture failed");
+    }
+    if (rs == HRP_OK) cudaGraphLaunch(ge, st);      // warm replay
+    cudaEventRecord(e0, st);
+    if (rs == HRP_OK) cudaGraphLaunch(ge, st);
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess && rs == HRP_OK) rs = fail(HRP_ERR_CUDA, "hrp_conv_bench: %s", cudaGetErrorString(cudaGetLastError()));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_per_launch = ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ge) cudaGraphExecDestroy(ge);
+    if (g) cudaGraphDestroy(g);
+    if (cs) cudaStreamDestroy(cs);
+  }
+  for (void* d : {dw, din, dout, dres, db, (void*)tmp}) if (d) cudaFree(d);
   return rs;
 }

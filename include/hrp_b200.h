@@ -167,6 +167,11 @@ int hrp_forward_profile(hrp_handle* h, const float* x_reg, const float* x_root, 
                         const float* Kmat, int B, float* out, float* ms_by_class, int64_t* launches_by_class,
                         double* flops_by_class, void* stream);
 
+/* Micro-benchmark of one tensor-core conv layer (tf32 / bf16 families) on random operands: average device time of
+ * `iters` back-to-back launches. Tuning aid (scripts/conv_bench.py); not used on the forward path. */
+int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int Cout, int k, int stride, int with_residual,
+                   int iters, float* ms_per_launch, void* stream);
+
 const char* hrp_last_error(void);
 const char* hrp_version(void);
 

@@ -6,7 +6,7 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 tot = sum(float(r['ms']) for r in rows)
 print("total ms %.3f over %d ops" % (tot, len(rows)))
 agg = collections.OrderedDict()
-KIND = {0: "stem", 1: "conv", 2: "maxpool", 3: "fuse", 4: "avgpool", 5: "depth", 6: "rank", 7: "dec", 8: "softargmax", 9: "fk"}
+KIND = {0: "stem", 1: "conv", 2: "maxpool", 3: "fuse", 4: "avgpool", 5: "depth", 6: "rank", 7: "dec", 8: "softargmax", 9: "fk", 10: "stem_pack"}
 for r in rows:
     if r['kind'] != '1':
         key = (KIND[int(r['kind'])],)
@@ -16,3 +16,8 @@ for r in rows:
     a[0] += 1; a[1] += float(r['ms']); a[2] = float(r['tflops'])
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print("%-70s n=%3d total %7.3f ms  avg %7.4f ms  %6.1f TF/s" % (" ".join(k), v[0], v[1], v[1] / v[0], v[2]))
+if rows and "lane" in rows[0]:
+    lanes = collections.OrderedDict()
+    for r in rows:
+        lanes[r["lane"]] = lanes.get(r["lane"], 0.0) + float(r["ms"])
+    print("serial ms per lane:", {k: round(v, 3) for k, v in sorted(lanes.items(), key=lambda kv: int(kv[0]))})

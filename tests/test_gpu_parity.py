@@ -196,6 +196,29 @@ def test_conv_layer_tensor_core_families(prec, B, H, Cin, Cout, k, stride, dev):
     assert bool(((out.cpu().double() - ref).abs() <= tol).all())
 
 
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+@pytest.mark.parametrize("B,H,C,res,relu", [(37, 64, 32, True, True), (9, 32, 64, False, True), (3, 24, 32, True, False),
+                                             (5, 40, 64, False, False), (1, 8, 32, True, True), (130, 16, 32, False, True)])
+def test_conv3x3_shifted_gemm_kernel(prec, B, H, C, res, relu, dev):
+    """conv_slab.cu (3x3/s1/p1, Cin == Cout): units that straddle frames, several units per persistent CTA, map widths
+    that are not a multiple of 8 positions, with and without residual / ReLU. Same exactness bound as above."""
+    from hrp_b200.model import conv2d_nhwc
+    g = torch.Generator().manual_seed(B * 100 + H + C)
+    x = _round_like(torch.randn(B, H, H, C, generator=g), prec)
+    w = _round_like(torch.randn(C, C, 3, 3, generator=g) / (9 * C) ** 0.5, prec)
+    b = torch.randn(C, generator=g)
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), 1, 1)
+    r = _round_like(torch.randn(ref.shape, generator=g), prec) if res else None
+    if res:
+        ref = ref + r.double()
+    if relu:
+        ref = torch.relu(ref)
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    out = conv2d_nhwc(x.to(dev), w.to(dev), b.to(dev), r.permute(0, 2, 3, 1).contiguous().to(dev) if res else None, 1, 1, relu, prec)
+    tol = (2.0 ** -8 if prec == "bf16" else 2.0 ** -11) * (1.0 + ref.abs()) * 1.01 + 2e-5
+    assert bool(((out.cpu().double() - ref).abs() <= tol).all())
+
 # ---------------------------------------------------------------------------------------------------- full network
 _models = {}
 
