@@ -76,6 +76,7 @@ conv_slab_kernel(const __grid_constant__ SlabParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_trigger();
 
   const int unit_pos = 128 * p.nblk;
   if (warp == 0) {
@@ -83,8 +84,9 @@ conv_slab_kernel(const __grid_constant__ SlabParams p) {
     const bool leader = elect_one();
     if (leader) mbar_arrive_expect_tx(bar_w, (uint32_t)p.w_bytes);
     const int tap_bytes = p.w_bytes / 9;
-    for (int t = 0; t < 9; ++t)
+    for (int t = 0; t < 9; ++t)          // weights are constants: staged before the previous layer has finished
       if (leader) bulk_g2s(sW + (uint32_t)(t * tap_bytes), static_cast<const uint8_t*>(a.w) + (size_t)t * tap_bytes, (uint32_t)tap_bytes, bar_w);
+    pdl_wait();
     const int total_rows = a.B * p.Hp;
     const uint32_t row_tx = (uint32_t)(Wp * p.row_bytes);
     int li = 0;
@@ -163,6 +165,7 @@ conv_slab_kernel(const __grid_constant__ SlabParams p) {
     // ===== epilogue: every warp is its own pipeline over the 32 tile rows of its TMEM lane quarter =========================
     // group g takes blocks gb % G == g; no barrier wider than a warp: residual rows arrive by cp.async into the warp's
     // staging tile, are combined in place with the accumulator, and leave as 16-byte chunks, 512 contiguous bytes per request
+    pdl_wait();
     const int e = warp - 2, g = e >> 2, quarter = warp & 3;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t pitch = (uint32_t)C * ESZ + 16u;
@@ -414,13 +417,15 @@ int conv_slab_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s
     HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
     attr_done = true;
   }
-  const int grid = std::min(p.units, sm_count());
+  const int grid = std::min(p.units, std::max(1, sm_count() * (a.grid_pct > 0 ? a.grid_pct : 100) / 100));
   const int threads = 64 + 128 * p.groups;
-  if (tf32 && p.planes == 1) conv_slab_kernel<true, 128, 1><<<grid, threads, smem, st>>>(p);
-  else if (tf32) conv_slab_kernel<true, 128, 2><<<grid, threads, smem, st>>>(p);
-  else if (p.row_bytes == 64) conv_slab_kernel<false, 64, 1><<<grid, threads, smem, st>>>(p);
-  else if (p.planes == 1) conv_slab_kernel<false, 128, 1><<<grid, threads, smem, st>>>(p);
-  else conv_slab_kernel<false, 128, 2><<<grid, threads, smem, st>>>(p);
+  cudaError_t le;
+  if (tf32 && p.planes == 1) le = launch_pdl(conv_slab_kernel<true, 128, 1>, grid, threads, smem, st, p);
+  else if (tf32) le = launch_pdl(conv_slab_kernel<true, 128, 2>, grid, threads, smem, st, p);
+  else if (p.row_bytes == 64) le = launch_pdl(conv_slab_kernel<false, 64, 1>, grid, threads, smem, st, p);
+  else if (p.planes == 1) le = launch_pdl(conv_slab_kernel<false, 128, 1>, grid, threads, smem, st, p);
+  else le = launch_pdl(conv_slab_kernel<false, 128, 2>, grid, threads, smem, st, p);
+  if (le != cudaSuccess) return fail(HRP_ERR_CUDA, "conv_slab_kernel launch: %s", cudaGetErrorString(le));
   HRP_CHECK_LAUNCH("conv_slab_kernel");
   return HRP_OK;
 }

@@ -114,6 +114,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_trigger();
+  if (warp != 4) pdl_wait();      // every warp that touches global memory (the MMA warp only reads shared memory / TMEM)
 
   if (warp < 4) {
     if (!p.tma) {
@@ -577,14 +579,11 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr_done = true;
   }
-  const int grid = std::min(p.total_tiles, sms * ctas);
-  if (tf32) {
-    if (epi == 8) conv_tc_kernel<true, 8><<<grid, tc_threads(8), smem, st>>>(p);
-    else conv_tc_kernel<true, 4><<<grid, tc_threads(4), smem, st>>>(p);
-  } else {
-    if (epi == 8) conv_tc_kernel<false, 8><<<grid, tc_threads(8), smem, st>>>(p);
-    else conv_tc_kernel<false, 4><<<grid, tc_threads(4), smem, st>>>(p);
-  }
+  const int grid = std::min(p.total_tiles, std::max(1, sms * ctas * (a.grid_pct > 0 ? a.grid_pct : 100) / 100));
+  cudaError_t le;
+  if (tf32) le = epi == 8 ? launch_pdl(conv_tc_kernel<true, 8>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<true, 4>, grid, tc_threads(4), smem, st, p);
+  else le = epi == 8 ? launch_pdl(conv_tc_kernel<false, 8>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<false, 4>, grid, tc_threads(4), smem, st, p);
+  if (le != cudaSuccess) return fail(HRP_ERR_CUDA, "conv_tc_kernel launch: %s", cudaGetErrorString(le));
   HRP_CHECK_LAUNCH("conv_tc_kernel");
   return HRP_OK;
 }

@@ -27,6 +27,9 @@ struct ConvArgs {
   int tma_custom;
   unsigned long long tm_gdim[4], tm_gstr[3];
   unsigned tm_box[4];
+  // Tensor-core family only: percentage of the GPU's CTA slots this launch's persistent grid may take (0 = all). The
+  // multi-lane graph runs several convs at once; most are latency-bound, so sharing the SMs beats time-slicing them.
+  int grid_pct;
 };
 
 int conv_f32_launch(const ConvArgs& a, cudaStream_t s);

@@ -115,6 +115,7 @@ struct hrp_handle {
   std::vector<std::vector<int>> waits;             // per op: producer ops on other lanes it must wait for
   std::vector<char> signals;                       // per op: some other lane waits for it
   bool use_lanes = true;
+  int lane_pct[hrp::kMaxLanes] = {};               // share of the CTA slots a conv of this lane may occupy (graph mode)
   int64_t last_launches = 0;
   int t_xreg = -1, t_xroot = -1, t_kval = -1, t_kmat = -1, t_field[HRP_NUM_FIELDS];
   int field_width[HRP_NUM_FIELDS];
@@ -918,6 +919,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
           a.tm_gstr[0] = 2 * px; a.tm_gstr[1] = row; a.tm_gstr[2] = (size_t)STEM_HP * row;
           a.tm_box[0] = 32; a.tm_box[1] = 128; a.tm_box[2] = 1; a.tm_box[3] = 1;
         }
+        if (lanes) a.grid_pct = h->lane_pct[o.lane];
         if (o.cls == CLS_CONV_TC) HRP_TRY(conv_tc_launch(a, tf32, tf32 && !o.out_nchw, st_op));
         else HRP_TRY(conv_f32_launch(a, st_op));
         break;
@@ -1084,6 +1086,13 @@ extern "C" int hrp_finalize_weights(hrp_handle* h) {
   if (h->n_lanes > kMaxLanes) return fail(HRP_ERR_INVALID, "internal: %d lanes", h->n_lanes);
   for (int l = 1; l < h->n_lanes; ++l) HRP_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
   if (const char* e = getenv("HRP_NO_LANES")) h->use_lanes = atoi(e) == 0;
+  {
+    // lanes 0-3 / 4-7: HRNet branches (full resolution first); lane 4 with the ResNet-50 keypoint backbone: its trunk
+    const bool two_hrnets = h->cfg.backbone == HRP_BACKBONE_HRNET32;
+    const char* e0 = getenv("HRP_PCT_HI");  const int hi = e0 ? atoi(e0) : 50;     // full-resolution branch, ResNet trunk
+    const char* e1 = getenv("HRP_PCT_LO");  const int lo = e1 ? atoi(e1) : 50;     // lower-resolution branches
+    for (int l = 0; l < kMaxLanes; ++l) h->lane_pct[l] = ((l & 3) == 0 || (!two_hrnets && l == 4)) ? hi : lo;
+  }
   h->finalized = true;
   return HRP_OK;
 }
