@@ -227,14 +227,27 @@ def main():
     conv = prof["conv_tensor"] if prof["conv_tensor"]["launches"] else prof["conv_fp32"]
     conv_name = "conv_tensor" if prof["conv_tensor"]["launches"] else "conv_fp32"
     total_ms = sum(v["ms"] for v in prof.values())
-    conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+    serial_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
     tensor_peak = peaks["bf16_sustained"] * (0.5 if args.precision == "tf32" else 1.0)
-    roofline = {"bound": "tensor", "kernel": conv_name, "achieved": conv_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": conv_tflops / tensor_peak, "traffic": None,
+    # The conv family is ~98 % of the step's FLOPs and its launches overlap across the graph's lanes, so per-launch
+    # durations are not additive: achieved = the family's algorithmic FLOPs of one step / the measured step time (CUDA
+    # events around the timed graph replays). `serial_launch_tflops` is the same FLOPs / the SUM of per-launch durations of
+    # one un-graphed, single-stream forward (CUDA events around every launch).
+    step_s = ms_total / args.steps * 1e-3
+    conv_tflops = conv["flops"] / step_s / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic_per_step.json")
+    if os.path.exists(tpath) and args.precision == "bf16" and B == BATCH_PER_GPU:
+        traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+    roofline = {"bound": "tensor", "kernel": "%s (conv_tc_kernel + conv_slab_kernel, %d launches per step)" % (conv_name, conv["launches"]),
+                "achieved": conv_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": conv_tflops / tensor_peak, "traffic": traffic,
+                "traffic_note": "DRAM bytes of ALL kernels of one step (ncu dram__bytes_read+write, profiles/r01_launches_bf16_b64.csv); null when not profiled for this config",
                 "peak_source": "%s bf16 sustained%s" % (peaks["source"], " / 2 (tf32)" if args.precision == "tf32" else ""),
-                "launches_per_step": conv["launches"], "share_of_step": conv["ms"] / total_ms if total_ms else None,
-                "whole_step_frac": fps / world * flops_frame / 1e12 / tensor_peak,
-                "by_class_ms": {k: round(v["ms"], 4) for k, v in prof.items()}}
+                "flops_per_launch_avg": conv["flops"] / max(conv["launches"], 1),
+                "launches_per_step": conv["launches"], "serial_launch_tflops": serial_tflops,
+                "share_of_serial_step": conv["ms"] / total_ms if total_ms else None,
+                "by_class_serial_ms": {k: round(v["ms"], 4) for k, v in prof.items()}}
 
     # ---- the two HBM-bound kernels in isolation, on inputs larger than L2 ------------------------------------------------
     extra = {}

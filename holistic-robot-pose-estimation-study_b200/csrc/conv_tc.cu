@@ -41,6 +41,12 @@ constexpr int TC_SMEM_LIMIT = 227 * 1024;
 
 struct TcParams {
   alignas(64) unsigned char tmap[128];   // CUtensorMap of the NHWC input (TMA mode)
+  alignas(64) unsigned char tmap_out[128];   // epi_tma: output as [M][ld_out], box {chunk columns, 128 rows}
+  alignas(64) unsigned char tmap_res[128];   // epi_tma: residual, same geometry
+  int epi_tma;       // 1: the epilogue stages the tile in swizzled shared memory and moves it with TMA (residual in, result out)
+  int chunk_bytes;   // epi_tma: bytes of one staged row chunk (128, or 64 when block_n*elem == 64)
+  int n_chunks;      // epi_tma: block_n*elem / chunk_bytes
+  int n_stg;         // epi_tma: staging buffers (2 when shared memory allows: the store of tile i overlaps tile i+1)
   ConvArgs a;
   int tma;           // 1: activations arrive by cp.async.bulk.tensor (one thread), 0: cp.async gather (four warps)
   int row_bytes;     // bytes of K per operand row: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B, Cin*elem == 64 in TMA mode)
@@ -105,6 +111,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       mbar_init(bar_empty + 8u * s, 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8u * i, 1); mbar_init(bar_acce + 8u * i, 1); }
+    for (int i = 0; i < 2; ++i) mbar_init(sBar + 16u * TC_MAX_STAGES + 48u + 16u * TC_BLOCK_M + 8u * i, 1);   // residual boxes landed (epi_tma)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5 && lane == 0 && p.tma) asm volatile("prefetch.tensormap [%0];" ::"l"(p.tmap) : "memory");
@@ -305,6 +312,100 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         if (eid == 0) mbar_arrive(bar_acce + 8u * buf);
         continue;
       }
+      if (p.epi_tma) {
+        // NHWC, dense output: the tile lives in shared memory as n_chunks boxes of [128 rows][chunk_bytes], 16-byte units
+        // XOR-swizzled exactly as the TMA unit expects (SWIZZLE_128B / 64B), so threads that each own one tile ROW write
+        // without bank conflicts. One thread pulls the residual boxes in (as soon as the previous store has finished
+        // reading this buffer) and pushes the finished boxes out; rows beyond M are clipped by the TMA unit.
+        const int sb = p.n_stg == 2 ? (li & 1) : 0;
+        const uint32_t tile_stg = stg + (uint32_t)sb * (uint32_t)(p.n_chunks * TC_BLOCK_M * p.chunk_bytes);
+        const uint32_t bar_res = sBar + 16u * TC_MAX_STAGES + 48u + 16u * TC_BLOCK_M + 8u * (uint32_t)sb;
+        const uint32_t cbytes = (uint32_t)p.chunk_bytes, chunk_sz = (uint32_t)TC_BLOCK_M * cbytes;
+        const uint32_t swz = cbytes == 128 ? ((uint32_t)et & 7u) : (((uint32_t)et >> 1) & 3u);
+        if (eid == 0) {                                        // the store that last read this buffer has finished reading
+          if (p.n_stg == 2) bulk_wait_read1(); else bulk_wait_read0();
+        }
+        epi_barrier<EPI>();
+        if (has_res && eid == 0) {
+          mbar_arrive_expect_tx(bar_res, (uint32_t)p.n_chunks * chunk_sz);
+          for (int k = 0; k < p.n_chunks; ++k)
+            tma_load_2d(tile_stg + (uint32_t)k * chunk_sz, p.tmap_res, a.out_coff + n0 + k * (int)(cbytes / ESZ), m0, bar_res);
+        }
+        mbar_wait(bar_accf + 8u * buf, (li >> 1) & 1);
+        tc_fence_after();
+        if (has_res) mbar_wait(bar_res, p.n_stg == 2 ? ((li >> 1) & 1) : (li & 1));
+        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
+            f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + bq.x;
+            f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + bq.y;
+            f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + bq.z;
+            f[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + bq.w;
+          }
+          // 16 columns = (16*ESZ)/16 sixteen-byte units starting at unit u0 of chunk ck
+          const uint32_t byte0 = (uint32_t)c0 * ESZ, ck = byte0 / cbytes, u0 = (byte0 - ck * cbytes) >> 4;
+          const uint32_t rowp = tile_stg + ck * chunk_sz + (uint32_t)et * cbytes;
+          constexpr int UNITS = 16 * ESZ / 16;
+#pragma unroll
+          for (int uu = 0; uu < UNITS; ++uu) {
+            const uint32_t addr = rowp + (((u0 + (uint32_t)uu) ^ swz) << 4);
+            float* ff = f + uu * (16 / ESZ);
+            if (has_res) {
+              uint32_t w[4];
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+              float r[16 / ESZ];
+              if constexpr (TF32) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) r[e] = __uint_as_float(w[e]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                  r[2 * e] = t2.x; r[2 * e + 1] = t2.y;
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 16 / ESZ; ++e) {
+                float t = ff[e];
+                if (!a.res_after_act) t += r[e];
+                if (a.relu) t = fmaxf(t, 0.f);
+                if (a.res_after_act) t += r[e];
+                ff[e] = t;
+              }
+            } else if (a.relu) {
+#pragma unroll
+              for (int e = 0; e < 16 / ESZ; ++e) ff[e] = fmaxf(ff[e], 0.f);
+            }
+            uint32_t o[4];
+            if constexpr (TF32) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = __float_as_uint(p.round_tf32 ? round_tf32_rna(ff[e]) : ff[e]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(ff[2 * e], ff[2 * e + 1]);
+                o[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+          }
+        }
+        fence_proxy_async();                                   // generic-proxy writes -> visible to the TMA store
+        tc_fence_before();
+        epi_barrier<EPI>();
+        if (eid == 0) {
+          mbar_arrive(bar_acce + 8u * buf);                    // accumulator buffer may be overwritten by tile li+2
+          for (int k = 0; k < p.n_chunks; ++k)
+            tma_store_2d(p.tmap_out, a.out_coff + n0 + k * (int)(cbytes / ESZ), m0, tile_stg + (uint32_t)k * chunk_sz);
+          bulk_commit();
+        }
+        continue;
+      }
       // NHWC: the 128 x BLOCK_N tile passes through a shared-memory staging tile so that residual loads and output
       // stores run as 16-byte chunks along the channel axis; the residual is fetched while the MMAs are still running.
       if (eh == 0) {
@@ -403,6 +504,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       }
       epi_barrier<EPI>();                                           // staging tile and row offsets are reused by the next tile
     }
+    if (p.epi_tma && eid == 0) bulk_wait_all();                     // the storing thread: its TMA stores have completed
   }
   tc_fence_before();
   __syncthreads();
@@ -541,6 +643,11 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     if ((long long)mtiles * (a.Cout / cand[i]) >= (sms * 4) / 5) break;
   }
   if (bn == 0) return fail(HRP_ERR_INVALID, "conv_tc: Cout=%d must be a multiple of 32", a.Cout);
+  // very short K (1x1 expansions out of 64 / 128 channels): the tile is all epilogue and the layer is bound by the bytes it
+  // writes, so two co-resident CTAs with 128-wide tiles keep more stores in flight than one CTA with a 256-wide tile
+  // (measured: 64->256 @64x64 with residual 81 -> 75 us, without 60 -> 47 us)
+  const bool short_k = p.Ktot <= 128 && bn > 128 && a.Cout % 128 == 0;
+  if (short_k) bn = 128;
   if (force_bn && a.Cout % force_bn == 0 && (!tf32 || force_bn <= 128)) bn = force_bn;
   p.block_n = bn;
   p.tiles_n = a.Cout / bn;
@@ -550,12 +657,25 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   p.tmem_cols = tm;
   // epilogue-heavy tiles (wide N, short K) get eight epilogue warps and the SM to themselves
   static const int force_epi = env_int("HRP_TC_EPI", 0);
-  int epi = (bn >= 128 && p.Ktot <= 256) ? 8 : 4;
+  int epi = (bn >= 128 && p.Ktot <= 256 && !short_k) ? 8 : 4;
   if (force_epi == 4 || force_epi == 8) epi = force_epi;
   int ctas = (epi == 4 && p.total_tiles >= 2 * sms && tm <= 256) ? 2 : 1;
   if (force_ctas) ctas = (epi == 4 && force_ctas == 2 && tm <= 256) ? 2 : 1;
   const size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 1024 : 0);
-  const size_t fixed = 2048 + tc_staging_bytes(bn, esz) + tc_tail_bytes();
+  // TMA epilogue: dense NHWC output whose tile rows are consecutive rows of the [M][Cout] matrix
+  static const int no_epi_tma = env_int("HRP_TC_NO_EPI_TMA", 0);
+  p.epi_tma = !no_epi_tma && !a.out_nchw && a.out_sy == 1 && a.out_sx == 1 && a.out_oy == 0 && a.out_ox == 0 && a.Ho_full == a.Ho &&
+              a.Wo_full == a.Wo && a.ld_out == a.Cout && a.out_coff == 0 && (bn * esz) % 64 == 0 && encode_tiled() != nullptr;
+  size_t staging = tc_staging_bytes(bn, esz);
+  if (p.epi_tma) {
+    p.chunk_bytes = (bn * esz) % 128 == 0 ? 128 : 64;
+    p.n_chunks = bn * esz / p.chunk_bytes;
+    const size_t one = (size_t)TC_BLOCK_M * bn * esz;
+    // two staging buffers when at least three operand stages still fit beside them
+    p.n_stg = (2048 + 2 * one + tc_tail_bytes() + 3 * tc_stage_bytes(bn, p.row_bytes) <= budget) ? 2 : 1;
+    staging = (p.n_stg * one + 1023) / 1024 * 1024;
+  }
+  const size_t fixed = 2048 + staging + tc_tail_bytes();
   int smax = (int)((budget - fixed) / tc_stage_bytes(bn, p.row_bytes));
   smax = std::max(1, std::min(smax, TC_MAX_STAGES));
   if (force_stages) smax = std::max(1, std::min(force_stages, smax));
@@ -565,11 +685,28 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   p.lag = std::min(TC_MAX_LAG, p.stages - 1);
   p.round_tf32 = round_tf32;
   p.stg_off = (int)((p.stages * tc_stage_bytes(bn, p.row_bytes) + 1023) / 1024 * 1024);
-  p.bar_off = p.stg_off + (int)tc_staging_bytes(bn, esz);
+  p.bar_off = p.stg_off + (int)staging;
   int cl = 0;
   while ((16 << cl) < bn * esz) ++cl;
   p.cpr_log = cl;
-  const size_t smem = tc_smem_bytes(p.stages, bn, esz, p.row_bytes);
+  const size_t smem = 1024 + (size_t)p.bar_off + tc_tail_bytes();
+  if (p.epi_tma) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)a.ld_out, (cuuint64_t)p.M};
+    const cuuint64_t gstr[1] = {(cuuint64_t)a.ld_out * esz};
+    const cuuint32_t box[2] = {(cuuint32_t)(p.chunk_bytes / esz), (cuuint32_t)TC_BLOCK_M};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle sw = p.chunk_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUtensorMap tmo, tmr;
+    CUresult r = encode_tiled()(&tmo, dt, 2, a.out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && a.res)
+      r = encode_tiled()(&tmr, dt, 2, const_cast<void*>(a.res), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HRP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for output [%d,%d]", (int)r, p.M, a.ld_out);
+    std::memcpy(p.tmap_out, &tmo, 128);
+    if (a.res) std::memcpy(p.tmap_res, &tmr, 128);
+  }
   if (smem > (size_t)TC_SMEM_LIMIT) return fail(HRP_ERR_INVALID, "conv_tc: %zu bytes of shared memory needed (block_n %d)", smem, bn);
   static bool attr_done = false;
   if (!attr_done) {
