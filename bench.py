@@ -123,6 +123,17 @@ def main():
     workload = "Panda full network (%s keypoint backbone + HRNet-W32 DepthNet + heatmap soft-argmax + heads + FK/projection), batch %d per GPU, 256x256 synthetic RGB" % (
         "ResNet-50+deconv" if args.backbone == "resnet50" else "HRNet-W32", args.batch)
 
+    # the contract is ONE JSON line on stdout: anything a library prints while we set up (NCCL's version banner goes to
+    # stdout) is sent to stderr instead, and the real stdout comes back just before the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     import torch
 
     if args.impl == "reference":
@@ -137,7 +148,7 @@ def main():
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": "%d frames per step of the batch-%d workload, oracle port of the reference (torch %s CPU fp32)" % (sample, args.batch, torch.__version__)},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch.distributed as dist
@@ -331,7 +342,7 @@ def main():
                         "d2h_bytes_per_step": rec_bytes, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "rooflines_hbm": extra,
                 "families": families, "cpu_baseline": cpu_base}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -36,8 +36,9 @@ typedef enum { HRP_F32 = 0, HRP_I64 = 1 } hrp_dtype;
 
 /* Arithmetic of the conv / linear contractions. Everything else (softmax, kinematics, heads' epilogues) is fp32. */
 typedef enum {
-  HRP_PREC_FP32 = 0,        /* fp32 FFMA implicit GEMM: bit-faithful parity mode */
-  HRP_PREC_TF32 = 1,        /* tcgen05 kind::tf32, operands rounded to nearest TF32, fp32 accumulate in TMEM */
+  HRP_PREC_FP32 = 0,        /* fp32 FFMA implicit GEMM: parity mode for every configuration */
+  HRP_PREC_TF32 = 1,        /* tcgen05 kind::tf32, operands rounded to nearest TF32, fp32 accumulate in TMEM: parity
+                               mode on the shipped configuration */
   HRP_PREC_BF16 = 2         /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
 } hrp_precision;
 
@@ -154,7 +155,9 @@ size_t hrp_workspace_bytes(hrp_handle* h, int B);
 int hrp_forward(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
                 int B, float* out, void* stream);
 
-/* Options: "cuda_graph" (0/1, default 1). Unknown option -> HRP_ERR_INVALID. */
+/* Options: "cuda_graph" (0/1, default 1: replay one graph per batch size), "lanes" (0/1, default 1: capture the graph
+ * over several streams so independent sub-networks overlap; takes effect for graphs not yet captured).
+ * Unknown option -> HRP_ERR_INVALID. */
 int hrp_set_option(hrp_handle* h, const char* name, int64_t value);
 
 /* Introspection for the bench / tests. */
