@@ -48,6 +48,19 @@ int conv_slab_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s
 int conv_tc_row_bytes(const ConvArgs& a, int tf32, int* use_tma);
 size_t pack_conv_tc_bytes(int K, int Cout, int tf32, int row_bytes);
 void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, void* out);   // from pack_conv_f32's [K][Cout]
+// One whole BasicBlock (two 3x3/s1/p1 convs, Cin == Cout == C, BN folded, ReLU, identity residual) in one launch
+// (conv_block.cu): bf16 NHWC in/out, w1/w2 = pack_conv_tc images (64-byte operand rows), b1/b2 folded biases.
+struct BlockArgs {
+  const void* x;
+  const void *w1, *w2;
+  const float *b1, *b2;
+  void* out;
+  int B, H, W, C;
+  int grid_pct;          // as ConvArgs::grid_pct
+};
+bool conv_block_supported(const BlockArgs& a);
+int conv_block_launch(const BlockArgs& a, cudaStream_t s);
+
 int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t s);
 int cast_bf16_to_f32_launch(const void* in, float* out, size_t n, cudaStream_t s);
 int round_tf32_launch(const float* in, float* out, size_t n, cudaStream_t s);

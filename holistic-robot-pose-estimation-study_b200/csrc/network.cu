@@ -23,7 +23,7 @@ struct hrp_fk;  // fk_project.cu
 
 namespace hrp {
 
-enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_RANK, OP_DEC, OP_SOFTARGMAX, OP_FK, OP_STEM_PACK };
+enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_RANK, OP_DEC, OP_SOFTARGMAX, OP_FK, OP_STEM_PACK, OP_BLOCK };
 enum { CLS_CONV_TC = 0, CLS_CONV_F32 = 1, CLS_STEM = 2, CLS_ELEM = 3, CLS_HEADS = 4, CLS_SOFTARGMAX = 5, CLS_FK = 6 };
 enum TKind { T_WS = 0, T_XREG, T_XROOT, T_KVAL, T_KMAT, T_FIELD, T_CONST };
 
@@ -53,7 +53,7 @@ struct OpDesc {
   int cls;
   int in = -1, res = -1, out = -1, in2 = -1, in3 = -1, in4 = -1;
   int out2 = -1, out3 = -1, out4 = -1, out5 = -1;
-  int layer = -1;
+  int layer = -1, layer2 = -1;   // layer2: second conv of a fused BasicBlock (OP_BLOCK)
   int Hi = 1, Wi = 1, Cin = 0, Ho = 1, Wo = 1, Cout = 0, KH = 1, KW = 1, stride = 1, pad_h = 0, pad_w = 0;
   int out_sy = 1, out_sx = 1, out_oy = 0, out_ox = 0, Ho_full = 1, Wo_full = 1, relu = 0, out_nchw = 0;
   int res_after_act = 0;
@@ -115,6 +115,7 @@ struct hrp_handle {
   std::vector<std::vector<int>> waits;             // per op: producer ops on other lanes it must wait for
   std::vector<char> signals;                       // per op: some other lane waits for it
   bool use_lanes = true;
+  unsigned long long* timeline = nullptr;           // HRP_TIMELINE: 2 stamps per op (device)
   int lane_pct[hrp::kMaxLanes] = {};               // share of the CTA slots a conv of this lane may occupy (graph mode)
   int64_t last_launches = 0;
   int t_xreg = -1, t_xroot = -1, t_kval = -1, t_kmat = -1, t_field[HRP_NUM_FIELDS];
@@ -122,6 +123,13 @@ struct hrp_handle {
 };
 
 namespace {
+
+// development aid (HRP_TIMELINE=<csv path>): %globaltimer stamps around every op of the captured graph
+__global__ void stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // expected tensors, in the reference's naming (mirrors holistic-robot-pose-estimation-study_b200/arch.py)
@@ -249,6 +257,7 @@ struct GraphBuilder {
   int act_esize = 4;
   int prec = HRP_PREC_FP32;
   int cur_lane = 0;
+  int phase_lane0 = 0;   // first of three extra lanes for the deconv phases (0: keep them on the caller's lane)
   void push(OpDesc op) { op.lane = cur_lane; h->ops.push_back(op); }
   bool tc() const { return prec != HRP_PREC_FP32; }
   bool tf32() const { return prec == HRP_PREC_TF32; }
@@ -426,6 +435,22 @@ struct GraphBuilder {
   }
 
   Tn basic(const Tn& x, const std::string& p) {
+    BlockArgs probe{};
+    probe.B = 1; probe.H = x.H; probe.W = x.W; probe.C = x.C;
+    if (prec == HRP_PREC_BF16 && conv_block_supported(probe)) {
+      // both convs in one launch, the intermediate stays in shared memory (conv_block.cu)
+      OpDesc op{};
+      op.kind = OP_BLOCK; op.cls = CLS_CONV_TC;
+      op.Hi = op.Ho = op.Ho_full = x.H; op.Wi = op.Wo = op.Wo_full = x.W; op.Cin = op.Cout = x.C; op.KH = op.KW = 3; op.stride = 1; op.pad_h = op.pad_w = 1;
+      op.relu = 1; op.ld = x.C;
+      op.layer = make_layer(p + ".conv1", p + ".bn1", x.C, x.C, 3, 3, shape_of(op));
+      op.layer2 = make_layer(p + ".conv2", p + ".bn2", x.C, x.C, 3, 3, shape_of(op));
+      Tn y = new_tensor(x.H, x.W, x.C, act_esize);
+      op.in = x.id; op.out = y.id;
+      op.flops = 2.0 * 2.0 * x.H * x.W * x.C * 9 * x.C;
+      push(op);
+      return y;
+    }
     Tn y = conv(x, p + ".conv1", p + ".bn1", x.C, 3, 1, 1, 1);
     return conv(y, p + ".conv2", p + ".bn2", x.C, 3, 1, 1, 1, x.id);
   }
@@ -536,8 +561,12 @@ struct GraphBuilder {
     std::vector<float> bp(Cout);
     for (int o = 0; o < Cout; ++o) { sc[o] = (double)g[o] / std::sqrt((double)v[o] + 1e-5); bp[o] = (float)((double)b[o] - (double)m[o] * sc[o]); }
     float* dbias = upload(bp);
+    const int lane0 = cur_lane;
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
+        // the four sub-pixel phases are independent GEMMs over the same input: one lane each (phase 0 stays on the
+        // caller's lane), joined again by whatever reads y
+        if (phase_lane0 > 0 && (py | px)) cur_lane = phase_lane0 + py * 2 + px - 1;
         std::vector<float> wp((size_t)4 * Cin * Cout);
         for (int ty = 0; ty < 2; ++ty)
           for (int tx = 0; tx < 2; ++tx) {
@@ -555,6 +584,7 @@ struct GraphBuilder {
         op.flops = 2.0 * x.H * x.W * Cout * 4 * Cin;
         push(op);
       }
+    cur_lane = lane0;
     return y;
   }
 
@@ -676,6 +706,7 @@ struct GraphBuilder {
       cur_lane = head_lane;
       xf = avgpool(x);
       cur_lane = kp_lane;
+      phase_lane0 = head_lane + 1;           // lanes 6, 7, 8
       Tn d = deconv(x, 0, 256);
       d = deconv(d, 1, 256);
       d = deconv(d, 2, 256);
@@ -684,7 +715,7 @@ struct GraphBuilder {
       xf = hrnet(h->t_xreg, "reg_backbone.", nk * 64, &logits, 4);
       head_lane = 8;                       // xf ends on lane 7, the logits on lane 4
     }
-    h->n_lanes = head_lane + 1;
+    h->n_lanes = head_lane + 1 + (phase_lane0 > 0 ? 3 : 0);
     if (status != HRP_OK) return status;
     cur_lane = kp_lane;
     h->tensors[xf.id].keep = true; h->debug["xf"] = xf.id;
@@ -706,7 +737,9 @@ struct GraphBuilder {
       push(op);
     }
     // liveness, lanes and cross-lane dependencies
-    std::vector<int> last_writer(h->tensors.size(), -1);
+    // writers of each tensor whose effects a later reader must see: normally the last one; the sub-pixel phases of a
+    // transposed conv write disjoint pixels of one tensor, so they do not order among themselves and a reader waits for all
+    std::vector<std::vector<int>> last_writers(h->tensors.size());
     h->waits.assign(h->ops.size(), {});
     h->signals.assign(h->ops.size(), 0);
     for (size_t i = 0; i < h->ops.size(); ++i) {
@@ -727,9 +760,17 @@ struct GraphBuilder {
         if (std::find(w.begin(), w.end(), j) == w.end()) { w.push_back(j); h->signals[j] = 1; }
       };
       for (int id : reads)
-        if (id >= 0) { touch(id); depend(last_writer[id]); }
+        if (id >= 0) { touch(id); for (int j : last_writers[id]) depend(j); }
       for (int id : writes)
-        if (id >= 0) { touch(id); depend(last_writer[id]); last_writer[id] = (int)i; }   // write-after-write keeps list order
+        if (id >= 0) {
+          touch(id);
+          auto& lw = last_writers[id];
+          const bool phase = o.kind == OP_CONV && o.out_sy == 2;
+          const bool joins = phase && !lw.empty() && h->ops[lw[0]].kind == OP_CONV && h->ops[lw[0]].out_sy == 2 && h->ops[lw[0]].in == o.in;
+          if (joins) { lw.push_back((int)i); continue; }
+          for (int j : lw) depend(j);                      // write-after-write keeps list order
+          lw.assign(1, (int)i);
+        }
     }
     return status;
   }
@@ -893,6 +934,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
     if (lanes)
       for (int j : h->waits[oi]) HRP_CUDA(cudaStreamWaitEvent(st_op, op_event[j], 0));
     if (prof) HRP_CUDA(cudaEventRecord(prof->e0, st));
+    if (lanes && h->timeline) stamp_kernel<<<1, 1, 0, st_op>>>(h->timeline + 2 * oi);
     int n_launch = 1;
     switch (o.kind) {
       case OP_STEM: {
@@ -922,6 +964,15 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         if (lanes) a.grid_pct = h->lane_pct[o.lane];
         if (o.cls == CLS_CONV_TC) HRP_TRY(conv_tc_launch(a, tf32, tf32 && !o.out_nchw, st_op));
         else HRP_TRY(conv_f32_launch(a, st_op));
+        break;
+      }
+      case OP_BLOCK: {
+        const Layer &L1 = h->layers[o.layer], &L2 = h->layers[o.layer2];
+        BlockArgs a{};
+        a.x = ptr(o.in); a.w1 = L1.w_tc; a.w2 = L2.w_tc; a.b1 = L1.bias; a.b2 = L2.bias; a.out = ptr(o.out);
+        a.B = B; a.H = o.Hi; a.W = o.Wi; a.C = o.Cin;
+        if (lanes) a.grid_pct = h->lane_pct[o.lane];
+        HRP_TRY(conv_block_launch(a, st_op));
         break;
       }
       case OP_STEM_PACK:
@@ -964,6 +1015,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         break;
     }
     launches += n_launch;
+    if (lanes && h->timeline) stamp_kernel<<<1, 1, 0, st_op>>>(h->timeline + 2 * oi + 1);
     if (lanes && h->signals[oi]) {
       op_event[oi] = new_event();
       if (!op_event[oi]) return fail(HRP_ERR_CUDA, "cudaEventCreate failed");
@@ -1026,6 +1078,22 @@ extern "C" int hrp_create(const hrp_config* cfg, const hrp_fk_program* robot, in
 
 extern "C" void hrp_destroy(hrp_handle* h) {
   if (!h) return;
+  if (h->timeline) {                                 // stamps of the most recent graph replay
+    cudaDeviceSynchronize();
+    std::vector<unsigned long long> t(h->ops.size() * 2);
+    cudaMemcpy(t.data(), h->timeline, t.size() * 8, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(getenv("HRP_TIMELINE"), "w")) {
+      fprintf(f, "op,kind,lane,Hi,Cin,Cout,k,stride,start_ns,end_ns\n");
+      unsigned long long t0 = ~0ull;
+      for (auto v : t) if (v && v < t0) t0 = v;
+      for (size_t i = 0; i < h->ops.size(); ++i) {
+        const OpDesc& o = h->ops[i];
+        fprintf(f, "%zu,%d,%d,%d,%d,%d,%d,%d,%llu,%llu\n", i, (int)o.kind, o.lane, o.Hi, o.Cin, o.Cout, o.KH, o.stride, t[2 * i] - t0, t[2 * i + 1] - t0);
+      }
+      fclose(f);
+    }
+    cudaFree(h->timeline);
+  }
   for (auto& kv : h->plans) {
     for (int i = 0; i < 2; ++i) if (kv.second->exec[i]) cudaGraphExecDestroy(kv.second->exec[i]);
     if (kv.second->ws) cudaFree(kv.second->ws);
@@ -1086,6 +1154,10 @@ extern "C" int hrp_finalize_weights(hrp_handle* h) {
   if (h->n_lanes > kMaxLanes) return fail(HRP_ERR_INVALID, "internal: %d lanes", h->n_lanes);
   for (int l = 1; l < h->n_lanes; ++l) HRP_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
   if (const char* e = getenv("HRP_NO_LANES")) h->use_lanes = atoi(e) == 0;
+  if (getenv("HRP_TIMELINE")) {
+    HRP_CUDA(cudaMalloc(&h->timeline, h->ops.size() * 16));
+    HRP_CUDA(cudaMemset(h->timeline, 0, h->ops.size() * 16));
+  }
   {
     // lanes 0-3 / 4-7: HRNet branches (full resolution first); lane 4 with the ResNet-50 keypoint backbone: its trunk
     const bool two_hrnets = h->cfg.backbone == HRP_BACKBONE_HRNET32;
@@ -1322,5 +1394,51 @@ extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int C
     if (cs) cudaStreamDestroy(cs);
   }
   for (void* d : {dw, din, dout, dres, db, (void*)tmp}) if (d) cudaFree(d);
+  return rs;
+}
+
+// One BasicBlock through the fused kernel (layer-level parity test): x NHWC [B,H,W,C] fp32 (rounded to bf16 here), OIHW
+// fp32 weights and biases of the two convs; out fp32. Synchronises; not a timed path.
+extern "C" int hrp_basic_block_nhwc(const float* x, const float* w1_oihw, const float* b1, const float* w2_oihw, const float* b2,
+                                    float* out, int B, int H, int W, int C, void* stream) {
+  if (!x || !w1_oihw || !w2_oihw || !out) return fail(HRP_ERR_INVALID, "hrp_basic_block_nhwc: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  BlockArgs a{};
+  a.B = B; a.H = H; a.W = W; a.C = C;
+  if (!conv_block_supported(a)) return fail(HRP_ERR_INVALID, "hrp_basic_block_nhwc: block not supported by the fused kernel (C=%d, %dx%d)", C, H, W);
+  const size_t nw = (size_t)C * C * 9, n = (size_t)B * H * W * C;
+  std::vector<float> w(nw), b(C), wp(nw), bp(C);
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) -> void* { void* d = nullptr; if (cudaMalloc(&d, std::max<size_t>(bytes, 16)) != cudaSuccess) { cudaGetLastError(); return nullptr; } tmp.push_back(d); return d; };
+  ConvArgs g{};
+  g.B = 1; g.Hi = g.Ho = H; g.Wi = g.Wo = W; g.Cin = g.Cout = C; g.KH = g.KW = 3; g.stride = 1; g.pad_h = g.pad_w = 1; g.ld_out = C;
+  const int rb = conv_tc_row_bytes(g, 0, nullptr);
+  int rs = rb == 64 ? HRP_OK : fail(HRP_ERR_INVALID, "hrp_basic_block_nhwc: unexpected operand row width %d", rb);
+  void* dw[2] = {nullptr, nullptr};
+  float* db[2] = {nullptr, nullptr};
+  const float* wsrc[2] = {w1_oihw, w2_oihw};
+  const float* bsrc[2] = {b1, b2};
+  for (int k = 0; k < 2 && rs == HRP_OK; ++k) {
+    cudaMemcpyAsync(w.data(), wsrc[k], nw * 4, cudaMemcpyDeviceToHost, st);
+    if (bsrc[k]) cudaMemcpyAsync(b.data(), bsrc[k], (size_t)C * 4, cudaMemcpyDeviceToHost, st); else std::fill(b.begin(), b.end(), 0.f);
+    cudaStreamSynchronize(st);
+    pack_conv_f32(w.data(), b.data(), nullptr, nullptr, nullptr, nullptr, C, C, 3, 3, wp.data(), bp.data());
+    std::vector<uint8_t> img(pack_conv_tc_bytes(9 * C, C, 0, rb));
+    pack_conv_tc(wp.data(), 9 * C, C, 0, rb, img.data());
+    dw[k] = dalloc(img.size());
+    db[k] = static_cast<float*>(dalloc((size_t)C * 4));
+    if (!dw[k] || !db[k]) { rs = fail(HRP_ERR_NOMEM, "hrp_basic_block_nhwc: out of device memory"); break; }
+    cudaMemcpy(dw[k], img.data(), img.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(db[k], bp.data(), (size_t)C * 4, cudaMemcpyHostToDevice);
+  }
+  void* dx = dalloc(n * 2);
+  void* dout = dalloc(n * 2);
+  if (rs == HRP_OK && (!dx || !dout)) rs = fail(HRP_ERR_NOMEM, "hrp_basic_block_nhwc: out of device memory");
+  if (rs == HRP_OK) rs = cast_f32_to_bf16_launch(x, dx, n, st);
+  a.x = dx; a.w1 = dw[0]; a.w2 = dw[1]; a.b1 = db[0]; a.b2 = db[1]; a.out = dout;
+  if (rs == HRP_OK) rs = conv_block_launch(a, st);
+  if (rs == HRP_OK) rs = cast_bf16_to_f32_launch(dout, out, n, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess && rs == HRP_OK) rs = fail(HRP_ERR_CUDA, "hrp_basic_block_nhwc: %s", cudaGetErrorString(cudaGetLastError()));
+  for (void* d : tmp) cudaFree(d);
   return rs;
 }

@@ -105,6 +105,18 @@ def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, relu=False
     return out
 
 
+def basic_block_nhwc(x, w1, b1, w2, b2):
+    """One HRNet BasicBlock through the fused bf16 kernel (layer-level parity tests). x NHWC, weights OIHW, CUDA fp32."""
+    nb, hh, ww, ch = x.shape
+    out = torch.empty_like(x)
+    st = torch.cuda.current_stream(x.device).cuda_stream
+    z = C.c_void_p(0)
+    capi.check(capi.lib().hrp_basic_block_nhwc(_ptr(x.contiguous()), _ptr(w1.contiguous()), _ptr(b1.contiguous()) if b1 is not None else z,
+                                               _ptr(w2.contiguous()), _ptr(b2.contiguous()) if b2 is not None else z, _ptr(out),
+                                               nb, hh, ww, ch, C.c_void_p(st)))
+    return out
+
+
 class HoliRobPoseB200(torch.nn.Module):
     """CUDA drop-in for RootNetwithRegInt (inference forward only)."""
 

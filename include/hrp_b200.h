@@ -104,6 +104,13 @@ int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias
                     int B, int Hi, int Wi, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu,
                     int precision, void* stream);
 
+/* One HRNet BasicBlock -- relu(conv2(relu(conv1(x) + b1)) + b2 + x), both convs 3x3/s1/p1, C -> C (HRnet.py:28-57, BN
+ * already folded by the caller) -- through the fused two-GEMM kernel of the bf16 family. x, out NHWC [B,H,W,C] fp32
+ * (operands are rounded to bf16 inside), weights OIHW fp32, biases [C] or NULL. HRP_ERR_INVALID when the block shape is
+ * not one the fused kernel takes (it never falls back silently). Layer-level parity tests. */
+int hrp_basic_block_nhwc(const float* x, const float* w1_oihw, const float* b1, const float* w2_oihw, const float* b2,
+                         float* out, int B, int H, int W, int C, void* stream);
+
 /* ---- full network ------------------------------------------------------------------------------------------------------ */
 typedef struct {
   int32_t backbone;          /* hrp_backbone: keypoint-branch backbone; the DepthNet backbone is always HRNet-W32 */

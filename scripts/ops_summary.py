@@ -6,7 +6,7 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 tot = sum(float(r['ms']) for r in rows)
 print("total ms %.3f over %d ops" % (tot, len(rows)))
 agg = collections.OrderedDict()
-KIND = {0: "stem", 1: "conv", 2: "maxpool", 3: "fuse", 4: "avgpool", 5: "depth", 6: "rank", 7: "dec", 8: "softargmax", 9: "fk", 10: "stem_pack"}
+KIND = {0: "stem", 1: "conv", 2: "maxpool", 3: "fuse", 4: "avgpool", 5: "depth", 6: "rank", 7: "dec", 8: "softargmax", 9: "fk", 10: "stem_pack", 11: "block"}
 for r in rows:
     if r['kind'] != '1':
         key = (KIND[int(r['kind'])],)

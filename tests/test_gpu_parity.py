@@ -219,6 +219,24 @@ def test_conv3x3_shifted_gemm_kernel(prec, B, H, C, res, relu, dev):
     tol = (2.0 ** -8 if prec == "bf16" else 2.0 ** -11) * (1.0 + ref.abs()) * 1.01 + 2e-5
     assert bool(((out.cpu().double() - ref).abs() <= tol).all())
 
+
+@pytest.mark.parametrize("B,H", [(37, 64), (3, 64), (64, 64), (1, 64), (9, 32), (130, 16)])
+def test_fused_basic_block_equals_two_convs(B, H, dev):
+    """conv_block.cu (a whole HRNet BasicBlock in one launch, intermediate in shared memory) against the same block run
+    as two tensor-core convs: same operands, same K order, same bf16 rounding of the intermediate => bit-identical."""
+    from hrp_b200.model import basic_block_nhwc, conv2d_nhwc
+    C = 32
+    g = torch.Generator().manual_seed(B * 7 + H)
+    x = torch.randn(B, H, H, C, generator=g).bfloat16().float().to(dev)
+    w1 = (torch.randn(C, C, 3, 3, generator=g) / (9 * C) ** 0.5).to(dev)
+    w2 = (torch.randn(C, C, 3, 3, generator=g) / (9 * C) ** 0.5).to(dev)
+    b1, b2 = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+    y = conv2d_nhwc(x, w1, b1, None, 1, 1, True, "bf16")
+    ref = conv2d_nhwc(y, w2, b2, x, 1, 1, True, "bf16")
+    out = basic_block_nhwc(x, w1, b1, w2, b2)
+    assert torch.equal(out, ref), float((out - ref).abs().max())
+
+
 # ---------------------------------------------------------------------------------------------------- full network
 _models = {}
 
