@@ -103,6 +103,7 @@ def cpu_reference_fps(torch, frames_per_step, steps, warmup, backbone):
 
 
 def main():
+    global ROBOT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -112,15 +113,18 @@ def main():
                     help="conv/linear contraction arithmetic: bf16 = throughput mode (default), fp32 = parity mode")
     ap.add_argument("--backbone", default="resnet50", choices=["resnet50", "hrnet32"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="frames per GPU per step")
+    ap.add_argument("--robot", default=ROBOT, choices=["panda", "kuka", "baxter"],
+                    help="panda = the headline workload (BASELINE configs[1]); kuka / baxter with --batch 256 / 128 are configs[2] / [3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-families", action="store_true", help="skip the tf32 / fp32 family lines")
     args = ap.parse_args()
+    ROBOT = args.robot
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    workload = "Panda full network (%s keypoint backbone + HRNet-W32 DepthNet + heatmap soft-argmax + heads + FK/projection), batch %d per GPU, 256x256 synthetic RGB" % (
+    workload = ROBOT.capitalize() + " full network (%s keypoint backbone + HRNet-W32 DepthNet + heatmap soft-argmax + heads + FK/projection), batch %d per GPU, 256x256 synthetic RGB" % (
         "ResNet-50+deconv" if args.backbone == "resnet50" else "HRNet-W32", args.batch)
 
     # the contract is ONE JSON line on stdout: anything a library prints while we set up (NCCL's version banner goes to
@@ -141,7 +145,7 @@ def main():
             return 0
         sample = 4
         fps, cores, ms = cpu_reference_fps(torch, sample, args.steps, args.warmup, args.backbone)
-        line = {"impl": "reference", "metric": "panda_fullnet_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        line = {"impl": "reference", "metric": "%s_fullnet_frames_per_sec" % ROBOT, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "l2": "n/a (CPU)"},
@@ -154,7 +158,7 @@ def main():
     import torch.distributed as dist
     import hrp_b200  # noqa: F401
     from hrp_b200 import arch, capi, consts, synth, dist as hdist
-    from hrp_b200.model import HoliRobPoseB200, FkRobot, soft_argmax
+    from hrp_b200.model import HoliRobPoseB200, FkRobot, HostPipeline, soft_argmax
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
@@ -187,16 +191,24 @@ def main():
             hdist.gather_records(rec, B, spec["dof"], spec["nkpt"])
         return rec
 
-    host_out = torch.empty(offs[-1], dtype=torch.float32).pin_memory()
+    # e2e: the public streaming API (HostPipeline): every step uploads its own batch from pinned host memory and reads its
+    # own result record back; with two slots the upload of step i+1 overlaps the forward of step i
+    def gathered(rec):
+        if world > 1:
+            hdist.gather_records(rec, B, spec["dof"], spec["nkpt"])
+        return rec
+    pipe = HostPipeline(model, B, depth=2, post=gathered)
+    pending = []
 
     def step_e2e(i):
         img, K, kv = sets_host[i % NSETS]
-        out = model.forward_dict(img.to(dev, non_blocking=True), K.to(dev, non_blocking=True), kv.to(dev, non_blocking=True))
-        rec = torch.cat([out[k].reshape(-1) for k in capi.FIELD_NAMES])
-        if world > 1:
-            hdist.gather_records(rec, B, spec["dof"], spec["nkpt"])
-        host_out[:rec.numel()].copy_(rec, non_blocking=True)
-        torch.cuda.current_stream().synchronize()        # the caller reads the result every step
+        pending.append(pipe.submit(img, K, kv))
+        if len(pending) > 1:
+            pipe.result(pending.pop(0))                  # the caller consumes every step's record
+
+    def drain_e2e():
+        while pending:
+            pipe.result(pending.pop(0))
 
     def timed(fn, steps):
         torch.cuda.synchronize()
@@ -207,6 +219,8 @@ def main():
         e0.record()
         for i in range(steps):
             fn(i)
+        if fn is step_e2e:
+            drain_e2e()
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -219,6 +233,7 @@ def main():
         step_resident(i)
     for i in range(3):
         step_e2e(i)
+    drain_e2e()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_total = timed(step_resident, args.steps)
@@ -329,7 +344,7 @@ def main():
                     "sample": "batch 1 x 10 forwards (+2 warm-up) of the oracle port of the reference, torch %s CPU fp32, %.0f ms/frame" % (torch.__version__, cms)}
 
     if rank == 0:
-        line = {"metric": "panda_fullnet_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": "%s_fullnet_frames_per_sec" % ROBOT, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
                 "config": {"workload": workload, "robot": ROBOT, "backbone": args.backbone, "precision": args.precision,

@@ -331,6 +331,26 @@ def test_fullnet_batch64_frames_are_independent(dev):
     check_gates(auto, ref2)
 
 
+
+def test_host_pipeline_matches_forward_dict(dev):
+    """HostPipeline (double-buffered host->device upload overlapping the forward) returns, batch after batch, exactly what
+    forward_dict returns for the same inputs."""
+    from hrp_b200.model import HostPipeline
+    m = gpu_model("panda", "resnet50", dev, "bf16")
+    B = 5
+    pipe = HostPipeline(m, B)
+    batches = [tuple(t.pin_memory() for t in helpers.inputs(B, 300 + i)) for i in range(5)]
+    tickets, got = [], []
+    for img, K, kv in batches:
+        tickets.append(pipe.submit(img, K, kv))
+        if len(tickets) > 1:
+            got.append({k: v.clone() for k, v in pipe.result(tickets.pop(0)).items()})
+    got.append({k: v.clone() for k, v in pipe.result(tickets.pop(0)).items()})
+    for (img, K, kv), g in zip(batches, got):
+        ref = m.forward_dict(img.to(dev), K.to(dev), kv.to(dev))
+        for k in ref:
+            assert torch.equal(ref[k].cpu(), g[k]), k
+
 # Tensor-core families against the reference's fp32 forward (goldens). TF32 (operands rounded to nearest, fp32
 # accumulation in TMEM) is held to the north_star parity gates themselves -- 1e-3 rad, 1 mm, 0.5 px -- on the shipped
 # configuration (ResNet-50 keypoint backbone; measured worst case 5.4e-4 rad / 0.2 mm / 0.15 px); with the HRNet-W32
