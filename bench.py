@@ -73,7 +73,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def summary(self):
         s = sorted(self.samples)

@@ -46,6 +46,7 @@ struct SlabParams {
   int w_bytes, w_off, stg_off, bar_off;
   int groups;             // epilogue groups of four warps; blocks go round-robin over groups
   int nacc;               // TMEM accumulator buffers (2 per group)
+  int pdl_early;     // HRP_PDL_EARLY: let the next kernel start launching right after this one's prologue
   int tmem_cols, cpr_log, round_tf32;
 };
 
@@ -76,7 +77,7 @@ conv_slab_kernel(const __grid_constant__ SlabParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_trigger();
+  if (p.pdl_early) pdl_trigger();
 
   const int unit_pos = 128 * p.nblk;
   if (warp == 0) {
@@ -419,6 +420,8 @@ int conv_slab_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s
   }
   const int grid = std::min(p.units, std::max(1, sm_count() * (a.grid_pct > 0 ? a.grid_pct : 100) / 100));
   const int threads = 64 + 128 * p.groups;
+  static const int pdl_early = slab_env("HRP_PDL_EARLY", 0);
+  p.pdl_early = pdl_early;
   cudaError_t le;
   if (tf32 && p.planes == 1) le = launch_pdl(conv_slab_kernel<true, 128, 1>, grid, threads, smem, st, p);
   else if (tf32) le = launch_pdl(conv_slab_kernel<true, 128, 2>, grid, threads, smem, st, p);

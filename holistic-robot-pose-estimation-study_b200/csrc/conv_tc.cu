@@ -43,6 +43,7 @@ struct TcParams {
   alignas(64) unsigned char tmap[128];   // CUtensorMap of the NHWC input (TMA mode)
   alignas(64) unsigned char tmap_out[128];   // epi_tma: output as [M][ld_out], box {chunk columns, 128 rows}
   alignas(64) unsigned char tmap_res[128];   // epi_tma: residual, same geometry
+  int pdl_early;     // HRP_PDL_EARLY: let the next kernel start launching right after this one's prologue
   int epi_tma;       // 1: the epilogue stages the tile in swizzled shared memory and moves it with TMA (residual in, result out)
   int chunk_bytes;   // epi_tma: bytes of one staged row chunk (128, or 64 when block_n*elem == 64)
   int n_chunks;      // epi_tma: block_n*elem / chunk_bytes
@@ -121,7 +122,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_trigger();
+  if (p.pdl_early) pdl_trigger();
   if (warp != 4) pdl_wait();      // every warp that touches global memory (the MMA warp only reads shared memory / TMEM)
 
   if (warp < 4) {
@@ -717,6 +718,8 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     attr_done = true;
   }
   const int grid = std::min(p.total_tiles, std::max(1, sms * ctas * (a.grid_pct > 0 ? a.grid_pct : 100) / 100));
+  static const int pdl_early = env_int("HRP_PDL_EARLY", 0);
+  p.pdl_early = pdl_early;
   cudaError_t le;
   if (tf32) le = epi == 8 ? launch_pdl(conv_tc_kernel<true, 8>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<true, 4>, grid, tc_threads(4), smem, st, p);
   else le = epi == 8 ? launch_pdl(conv_tc_kernel<false, 8>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<false, 4>, grid, tc_threads(4), smem, st, p);
