@@ -505,7 +505,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       }
       epi_barrier<EPI>();                                           // staging tile and row offsets are reused by the next tile
     }
-    if (p.epi_tma && eid == 0) bulk_wait_all();                     // the storing thread: its TMA stores have completed
+    // the storing thread: its TMA stores have finished READING shared memory (the writes themselves are ordered before
+    // the end of the grid like any other store; waiting for their completion here would only lengthen every CTA's tail)
+    if (p.epi_tma && eid == 0) bulk_wait_read0();
   }
   tc_fence_before();
   __syncthreads();
