@@ -75,6 +75,8 @@ struct Plan {
   std::vector<size_t> off;
   size_t io_xreg = 0, io_xroot = 0, io_kv = 0, io_K = 0, io_out = 0, sa_ws = 0, sa_ws_bytes = 0;
   cudaGraphExec_t exec[2] = {nullptr, nullptr};
+  cudaEvent_t done = nullptr;      // recorded after the last forward that used this plan (graph path)
+  bool used = false;
 };
 
 }  // namespace hrp
@@ -106,7 +108,10 @@ struct hrp_handle {
   std::vector<Layer> layers;
   std::vector<TensorInfo> tensors;
   std::vector<OpDesc> ops;
-  std::map<int, std::unique_ptr<Plan>> plans;
+  std::map<int, std::unique_ptr<Plan>> plans;      // key = batch * 8 + slot
+  int slots = 3;                   // graph path: plans (workspace + graph) per batch size, used round-robin so that
+  int next_slot = 0;               //   consecutive forwards enqueued on DIFFERENT streams can overlap
+  std::map<int, int> last_slot;    // batch -> slot of the most recent forward (hrp_debug_tensor)
   std::unordered_map<std::string, int> debug;
   cudaStream_t capture_stream = nullptr;
   int n_lanes = 1;
@@ -828,8 +833,8 @@ int64_t record_floats(const hrp_handle* h, int B, int64_t* offs) {
   return o;
 }
 
-int make_plan(hrp_handle* h, int B, Plan** out) {
-  auto it = h->plans.find(B);
+int make_plan(hrp_handle* h, int B, Plan** out, int slot = 0) {
+  auto it = h->plans.find(B * 8 + slot);
   if (it != h->plans.end()) { *out = it->second.get(); return HRP_OK; }
   std::unique_ptr<Plan> p(new Plan());
   p->B = B;
@@ -875,8 +880,9 @@ int make_plan(hrp_handle* h, int B, Plan** out) {
     return fail(HRP_ERR_NOMEM, "cudaMalloc of %zu workspace bytes for batch %d failed", p->ws_bytes, B);
   }
   p->ws = static_cast<char*>(ws);
+  HRP_CUDA(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
   *out = p.get();
-  h->plans[B] = std::move(p);
+  h->plans[B * 8 + slot] = std::move(p);
   return HRP_OK;
 }
 
@@ -1096,6 +1102,7 @@ extern "C" void hrp_destroy(hrp_handle* h) {
   }
   for (auto& kv : h->plans) {
     for (int i = 0; i < 2; ++i) if (kv.second->exec[i]) cudaGraphExecDestroy(kv.second->exec[i]);
+    if (kv.second->done) cudaEventDestroy(kv.second->done);
     if (kv.second->ws) cudaFree(kv.second->ws);
   }
   for (void* p : h->dev_allocs) cudaFree(p);
@@ -1154,6 +1161,7 @@ extern "C" int hrp_finalize_weights(hrp_handle* h) {
   if (h->n_lanes > kMaxLanes) return fail(HRP_ERR_INVALID, "internal: %d lanes", h->n_lanes);
   for (int l = 1; l < h->n_lanes; ++l) HRP_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
   if (const char* e = getenv("HRP_NO_LANES")) h->use_lanes = atoi(e) == 0;
+  if (const char* e = getenv("HRP_SLOTS")) h->slots = std::max(1, std::min(4, atoi(e)));
   if (getenv("HRP_TIMELINE")) {
     HRP_CUDA(cudaMalloc(&h->timeline, h->ops.size() * 16));
     HRP_CUDA(cudaMemset(h->timeline, 0, h->ops.size() * 16));
@@ -1161,8 +1169,8 @@ extern "C" int hrp_finalize_weights(hrp_handle* h) {
   {
     // lanes 0-3 / 4-7: HRNet branches (full resolution first); lane 4 with the ResNet-50 keypoint backbone: its trunk
     const bool two_hrnets = h->cfg.backbone == HRP_BACKBONE_HRNET32;
-    const char* e0 = getenv("HRP_PCT_HI");  const int hi = e0 ? atoi(e0) : 50;     // full-resolution branch, ResNet trunk
-    const char* e1 = getenv("HRP_PCT_LO");  const int lo = e1 ? atoi(e1) : 50;     // lower-resolution branches
+    const char* e0 = getenv("HRP_PCT_HI");  const int hi = e0 ? atoi(e0) : 25;     // full-resolution branch, ResNet trunk
+    const char* e1 = getenv("HRP_PCT_LO");  const int lo = e1 ? atoi(e1) : 25;     // lower-resolution branches
     for (int l = 0; l < kMaxLanes; ++l) h->lane_pct[l] = ((l & 3) == 0 || (!two_hrnets && l == 4)) ? hi : lo;
   }
   h->finalized = true;
@@ -1185,6 +1193,16 @@ extern "C" size_t hrp_workspace_bytes(hrp_handle* h, int B) {
 extern "C" int hrp_set_option(hrp_handle* h, const char* name, int64_t value) {
   if (!h || !name) return fail(HRP_ERR_INVALID, "hrp_set_option: null argument");
   if (std::strcmp(name, "cuda_graph") == 0) { h->use_graph = value != 0; return HRP_OK; }
+  if (std::strcmp(name, "slots") == 0) {         // plans per batch size, 1..4 (default 3)
+    if (value < 1 || value > 4) return fail(HRP_ERR_INVALID, "hrp_set_option: slots must be 1..4");
+    h->slots = (int)value; h->next_slot = 0;
+    return HRP_OK;
+  }
+  if (std::strcmp(name, "lane_share_pct") == 0) { // share of the CTA slots one conv launch may take (default 25: tuned for a
+    if (value < 5 || value > 100) return fail(HRP_ERR_INVALID, "hrp_set_option: lane_share_pct must be 5..100");   // stream of overlapping
+    for (int l = 0; l < kMaxLanes; ++l) h->lane_pct[l] = (int)value;                                               // forwards; 50 gives the
+    return HRP_OK;                                                                                                 // lowest single-call latency)
+  }
   if (std::strcmp(name, "lanes") == 0) {         // multi-stream graph (default 1); takes effect for graphs not yet captured
     h->use_lanes = value != 0;
     return HRP_OK;
@@ -1200,8 +1218,19 @@ extern "C" int hrp_forward(hrp_handle* h, const float* x_reg, const float* x_roo
   HRP_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   Plan* p = nullptr;
-  HRP_TRY(make_plan(h, B, &p));
-  if (!h->use_graph) return run_ops(h, p, IoPtrs{x_reg, x_root, k_value, Kmat, out}, st, nullptr);
+  const int slot = h->use_graph ? h->next_slot : 0;
+  if (h->use_graph) h->next_slot = (h->next_slot + 1) % h->slots;
+  HRP_TRY(make_plan(h, B, &p, slot));
+  h->last_slot[B] = slot;
+  if (!h->use_graph) {
+    if (p->used) HRP_CUDA(cudaStreamWaitEvent(st, p->done, 0));
+    const int rs = run_ops(h, p, IoPtrs{x_reg, x_root, k_value, Kmat, out}, st, nullptr);
+    HRP_CUDA(cudaEventRecord(p->done, st));
+    p->used = true;
+    return rs;
+  }
+  // whatever stream used this plan last must be done with its workspace before this forward touches it
+  if (p->used) HRP_CUDA(cudaStreamWaitEvent(st, p->done, 0));
   // graph path: the graph reads/writes the plan's static staging buffers, so one instantiation serves every call
   const int same = (x_reg == x_root) ? 1 : 0;
   float* s_xreg = reinterpret_cast<float*>(p->ws + p->io_xreg);
@@ -1227,6 +1256,8 @@ extern "C" int hrp_forward(hrp_handle* h, const float* x_reg, const float* x_roo
   HRP_CUDA(cudaMemcpyAsync(s_K, Kmat, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   HRP_CUDA(cudaGraphLaunch(p->exec[same], st));
   HRP_CUDA(cudaMemcpyAsync(out, s_out, (size_t)record_floats(h, B, nullptr) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  HRP_CUDA(cudaEventRecord(p->done, st));
+  p->used = true;
   return HRP_OK;
 }
 
@@ -1257,7 +1288,8 @@ extern "C" int hrp_debug_tensor(hrp_handle* h, const char* name, int B, float* d
   if (!h || !name || !numel) return fail(HRP_ERR_INVALID, "hrp_debug_tensor: null argument");
   auto it = h->debug.find(name);
   if (it == h->debug.end()) return fail(HRP_ERR_INVALID, "hrp_debug_tensor: unknown tensor '%s' (xf, img_feat, logits)", name);
-  auto pit = h->plans.find(B);
+  auto ls = h->last_slot.find(B);
+  auto pit = ls == h->last_slot.end() ? h->plans.end() : h->plans.find(B * 8 + ls->second);
   if (pit == h->plans.end()) return fail(HRP_ERR_STATE, "hrp_debug_tensor: no forward has run for batch %d", B);
   const TensorInfo& t = h->tensors[it->second];
   *numel = t.elems * B;

@@ -308,8 +308,9 @@ class HoliRobPoseB200(torch.nn.Module):
 class HostPipeline:
     """Streaming inference from HOST batches: `submit()` enqueues the host->device copy of one batch on a copy stream
     (double-buffered device staging), the forward on the compute stream behind it and the device->host copy of the packed
-    output record; `result()` blocks on that batch only. With two slots the upload of batch i+1 overlaps the forward of
-    batch i (50 MB of fp32 images per 64 frames is ~0.9 ms over PCIe 5, 15 % of the forward at batch 64). Inputs should be
+    output record; `result()` blocks on that batch only. With `depth` slots (default 3, the library's number of plans
+    per batch size) uploads overlap forwards and the low-parallelism tail of batch i overlaps the head of batch i+1
+    (50 MB of fp32 images per 64 frames is ~0.9 ms over PCIe 5, 15 % of the forward at batch 64). Inputs should be
     pinned (`torch.Tensor.pin_memory()`), otherwise the copies serialise with the host.
 
         pipe = HostPipeline(model, batch=64)
@@ -317,10 +318,13 @@ class HostPipeline:
         out = pipe.result(t)                         # dict of pinned-host views, valid until the slot is reused
     """
 
-    def __init__(self, model, batch, depth=2, post=None):
+    def __init__(self, model, batch, depth=3, post=None):
         self.model, self.B, self.depth, self.post = model, int(batch), int(depth), post
         dev = model.device
         self.copy_stream = torch.cuda.Stream(dev)
+        # one compute stream per slot: the library keeps two plans (workspace + graph) per batch size and uses them
+        # round-robin, so forwards enqueued on different streams overlap (the tail of batch i with the head of batch i+1)
+        self.compute = [torch.cuda.Stream(dev) for _ in range(depth)]
         self.img = [torch.empty(self.B, 3, 256, 256, device=dev) for _ in range(depth)]
         self.K = [torch.empty(self.B, 3, 3, device=dev) for _ in range(depth)]
         self.kv = [torch.empty(self.B, device=dev) for _ in range(depth)]
@@ -336,7 +340,8 @@ class HostPipeline:
         self.n += 1
         if k_value is None:
             k_value = torch.sqrt(K[:, 0, 0] * K[:, 1, 1] * 1000.0 * 1000.0 / (self.model.image_size * self.model.image_size))
-        compute = torch.cuda.current_stream(self.model.device)
+        compute = self.compute[s]
+        compute.wait_stream(torch.cuda.current_stream(self.model.device))
         with torch.cuda.stream(self.copy_stream):
             if self.ev_free[s] is not None:
                 self.copy_stream.wait_event(self.ev_free[s])
@@ -345,16 +350,17 @@ class HostPipeline:
             self.kv[s].copy_(k_value, non_blocking=True)
             self.ev_in[s].record(self.copy_stream)
         compute.wait_event(self.ev_in[s])
-        rec, _ = self.model.forward_record(self.img[s], self.img[s], self.kv[s], self.K[s])
-        self.ev_free[s] = torch.cuda.Event()
-        self.ev_free[s].record(compute)
-        if self.post is not None:
-            rec = self.post(rec)                 # e.g. the multi-GPU gather of the packed records
-        if self.host[s] is None or self.host[s].numel() != rec.numel():
-            self.host[s] = torch.empty(rec.numel(), dtype=torch.float32).pin_memory()
-        self.host[s].copy_(rec.reshape(-1), non_blocking=True)
-        self.ev_done[s] = torch.cuda.Event()
-        self.ev_done[s].record(compute)
+        with torch.cuda.stream(compute):
+            rec, _ = self.model.forward_record(self.img[s], self.img[s], self.kv[s], self.K[s])
+            self.ev_free[s] = torch.cuda.Event()
+            self.ev_free[s].record(compute)
+            if self.post is not None:
+                rec = self.post(rec)             # e.g. the multi-GPU gather of the packed records
+            if self.host[s] is None or self.host[s].numel() != rec.numel():
+                self.host[s] = torch.empty(rec.numel(), dtype=torch.float32).pin_memory()
+            self.host[s].copy_(rec.reshape(-1), non_blocking=True)
+            self.ev_done[s] = torch.cuda.Event()
+            self.ev_done[s].record(compute)
         return s
 
     def result(self, ticket):
