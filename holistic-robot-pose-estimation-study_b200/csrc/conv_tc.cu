@@ -1,19 +1,27 @@
 // Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (kind::f16 with bf16 operands, or kind::tf32) with the
-// accumulator in TMEM, weights streamed by the TMA bulk-copy engine, activations gathered (im2col on the fly) with
-// cp.async straight into the 128-byte-swizzled K-major operand layout the MMA reads.
+// accumulator in TMEM, weights streamed by the TMA bulk-copy engine, activations fetched by TMA tensor copies (im2col
+// on the fly: one {channels, W-run, rows, images} box per kernel tap, zero-filled outside the image) into the
+// 128-/64-byte-swizzled K-major operand layout the MMA reads, results returned by TMA tensor stores.
 //
 // Replaces every nn.Conv2d / nn.ConvTranspose2d (+ folded BatchNorm2d, + residual add, + ReLU) the reference runs in
 // the two backbones and the deconv head (lib/models/backbones/HRnet.py:28-98,247-265,499-570; Resnet.py:57-139;
-// lib/models/full_net.py:214-238,353-355) in the HRP_PREC_BF16 / HRP_PREC_TF32 families.
+// lib/models/full_net.py:214-238,353-355) in the HRP_PREC_BF16 / HRP_PREC_TF32 families, except the 3x3/s1 Cin==Cout
+// layers that conv_slab.cu / conv_block.cu take.
 //
 // GEMM view (same ConvArgs descriptor as the fp32 family): M = B*Ho*Wo output pixels, N = Cout, K = KH*KW*Cin with
-// k = (r*KW + s)*Cin + c. One CTA computes a 128 x BLOCK_N tile:
-//   warps 0-3  producers: thread t owns tile row t (one output pixel); per k-block it issues eight 16-byte cp.async
-//              (zero-filled outside the image) into row t of the A stage, XOR-swizzled; then they become the epilogue
-//              warps (warp w reads TMEM lanes 32w..32w+31): + bias, + residual, ReLU, convert, store.
-//   warp 4     allocates TMEM, then one elected lane issues the tcgen05.mma stream and commits stages back.
-//   warp 5     one lane streams pre-swizzled weight tiles with cp.async.bulk (mbarrier complete_tx).
-// Stages hand over through mbarriers: full[s] (128 producer arrivals + 1 expect_tx arrival), empty[s] (tcgen05.commit).
+// k = (r*KW + s)*Cin + c. Persistent CTAs (one or two per SM) walk 128 x BLOCK_N tiles:
+//   warps 0-3  only for shapes whose tile is not a box of the input: cp.async im2col gather (thread t serves chunk j of
+//              eight rows of its warp's 32; zero-filled outside the image), XOR-swizzled by hand
+//   warp 4     allocates TMEM; issues the tcgen05.mma stream into one of two accumulator buffers and commits ring
+//              slots back (all lanes walk the loop, one elected lane issues: tc_ptx.h, elect_one)
+//   warp 5     loader: pre-swizzled weight tiles with cp.async.bulk and the activation boxes with
+//              cp.async.bulk.tensor.4d, both on the stage's mbarrier (complete_tx)
+//   warps 6..  4 or 8 epilogue warps drain the other accumulator buffer: + bias, + residual, ReLU, convert. Dense NHWC
+//              outputs go through a shared-memory tile already in the TMA swizzle and leave (and the residual arrives)
+//              as tensor copies; strided outputs (transposed-conv phases) and the NCHW fp32 heatmap logits keep a
+//              register / cp.async path.
+// Stages hand over through mbarriers: full[s] (expect_tx, + 128 producer arrivals in gather mode), empty[s]
+// (tcgen05.commit), acc_full / acc_empty per accumulator buffer.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -533,9 +541,6 @@ __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restric
 size_t tc_stage_bytes(int block_n, int row_bytes) { return (size_t)(TC_BLOCK_M + block_n) * row_bytes; }
 size_t tc_staging_bytes(int block_n, int esz) { return ((size_t)TC_BLOCK_M * (block_n * esz + 16) + 127) / 128 * 128; }
 size_t tc_tail_bytes() { return 16 * TC_MAX_STAGES + 16 + 16 + 16 + 8 * TC_BLOCK_M + 8 * TC_BLOCK_M + 64; }
-size_t tc_smem_bytes(int stages, int block_n, int esz, int row_bytes) {
-  return 1024 + (stages * tc_stage_bytes(block_n, row_bytes) + 1023) / 1024 * 1024 + tc_staging_bytes(block_n, esz) + tc_tail_bytes();
-}
 
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
