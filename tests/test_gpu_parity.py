@@ -199,10 +199,13 @@ def test_conv_layer_tensor_core_families(prec, B, H, Cin, Cout, k, stride, dev):
 
 @pytest.mark.parametrize("prec", ["bf16", "tf32"])
 @pytest.mark.parametrize("B,H,C,res,relu", [(37, 64, 32, True, True), (9, 32, 64, False, True), (3, 24, 32, True, False),
-                                             (5, 40, 64, False, False), (1, 8, 32, True, True), (130, 16, 32, False, True)])
+                                             (5, 40, 64, False, False), (1, 8, 32, True, True), (130, 16, 32, False, True),
+                                             (20, 16, 128, True, True), (64, 8, 256, True, True), (3, 32, 128, False, True),
+                                             (5, 16, 256, False, False), (1, 8, 128, True, False), (70, 16, 128, False, True)])
 def test_conv3x3_shifted_gemm_kernel(prec, B, H, C, res, relu, dev):
-    """conv_slab.cu (3x3/s1/p1, Cin == Cout): units that straddle frames, several units per persistent CTA, map widths
-    that are not a multiple of 8 positions, with and without residual / ReLU. Same exactness bound as above."""
+    """3x3/s1/p1 convs with Cin == Cout: conv_slab.cu for 32 / 64 channels (units that straddle frames, several units per
+    persistent CTA, map widths that are not a multiple of 8 positions), conv_tc.cu for the wider ones; with and without
+    residual / ReLU. Same exactness bound as above."""
     from hrp_b200.model import conv2d_nhwc
     g = torch.Generator().manual_seed(B * 100 + H + C)
     x = _round_like(torch.randn(B, H, H, C, generator=g), prec)
