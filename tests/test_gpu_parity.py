@@ -335,6 +335,29 @@ def test_fullnet_batch64_frames_are_independent(dev):
 
 
 
+
+def test_fullnet_distinct_reg_and_root_images(dev):
+    """The reference call takes two crops, x_reg (keypoint branch) and x_root (DepthNet), full_net.py:262-266; the callers
+    usually pass the same tensor, which the graph path special-cases. Distinct tensors take the other graph and must
+    match the oracle too -- and the 8-tuple interface returns the same values as the dict interface."""
+    m = gpu_model("panda", "resnet50", dev)
+    om, _ = helpers.oracle_for("panda", "resnet50")
+    img, K, kv = helpers.inputs(2, 777)
+    img2, _, _ = helpers.inputs(2, 778)
+    tup = m(img.to(dev), img2.to(dev), kv.to(dev), K=K.to(dev))
+    assert len(tup) == 8
+    ref = om.forward_dict(img, img2, kv, K)
+    names = ["joint_angles", "rot6d", "trans", "root_uv", "root_depth", "uvd", "kp3d_int", "kp3d_fk"]
+    got = dict(zip(names, tup))
+    assert helpers.maxdiff(got["joint_angles"], ref["joint_angles"]) < helpers.TOL_RAD
+    assert helpers.maxdiff(got["root_depth"], ref["root_depth"]) < helpers.TOL_DEPTH_M
+    assert helpers.maxdiff(got["root_uv"], ref["root_uv"]) < helpers.TOL_PX
+    for k in ("trans", "kp3d_int", "kp3d_fk", "uvd", "rot6d"):
+        assert helpers.maxdiff(got[k], ref[k]) < 1e-3, k
+    # swapping the two crops changes the result (the two graphs really read different buffers)
+    swapped = dict(zip(names, m(img2.to(dev), img.to(dev), kv.to(dev), K=K.to(dev))))
+    assert helpers.maxdiff(swapped["root_depth"], got["root_depth"]) > 1e-4
+
 def test_host_pipeline_matches_forward_dict(dev):
     """HostPipeline (double-buffered host->device upload overlapping the forward) returns, batch after batch, exactly what
     forward_dict returns for the same inputs."""
