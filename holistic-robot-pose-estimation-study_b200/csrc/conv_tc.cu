@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "sa_state.h"
 #include "tc_ptx.h"
 
 namespace hrp {
@@ -294,6 +295,62 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const int y = oy * a.out_sy + a.out_oy, x = ox * a.out_sx + a.out_ox;
       const size_t pix = ((size_t)b * a.Ho_full + y) * a.Wo_full + x;
       const uint32_t t_row = t_lane + (uint32_t)(buf * p.block_n);
+      if (a.sa_partial != nullptr) {
+        // The heatmap head without the heatmap: this tile is 128 pixels x the 64 depth bins of ONE keypoint. Every thread
+        // owns a pixel, reduces its 64 logits to an online-softmax state (max, sum of exponentials, first moments in
+        // x, y and depth), the tile's 128 states merge by shuffles and one shared-memory hop, and five floats leave
+        // the SM instead of 32 KB of logits (integral.py:102-208; softargmax.cu finishes from the partials).
+        mbar_wait(bar_accf + 8u * buf, (li >> 1) & 1);
+        tc_fence_after();
+        SaState st{-INFINITY, 0.f, 0.f, 0.f, 0.f};
+        float vals[64];
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
+            vals[c0 + q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + bq.x; vals[c0 + q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + bq.y;
+            vals[c0 + q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + bq.z; vals[c0 + q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + bq.w;
+          }
+        }
+        tc_fence_before();
+        if (row_ok) {
+          float mx = vals[0];
+#pragma unroll
+          for (int d = 1; d < 64; ++d) mx = fmaxf(mx, vals[d]);
+          float l = 0.f, sz = 0.f;
+#pragma unroll
+          for (int d = 0; d < 64; ++d) { const float e = __expf(vals[d] - mx); l += e; sz += (float)d * e; }
+          st.m = mx; st.l = l; st.sz = sz; st.sx = (float)ox * l; st.sy = (float)oy * l;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { SaState o = sa_shfl_xor(st, off); sa_merge(st, o); }
+        const uint32_t sa_smem = s_rowoff;                         // 4 warps x 5 floats (the row-offset table is idle in this mode)
+        if (lane == 0) {
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sa_smem + 32u * (uint32_t)(warp & 3)), "f"(st.m), "f"(st.l), "f"(st.sx), "f"(st.sy) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa_smem + 32u * (uint32_t)(warp & 3) + 16u), "f"(st.sz) : "memory");
+        }
+        epi_barrier<EPI>();
+        if (eid == 0) {
+          mbar_arrive(bar_acce + 8u * buf);
+          SaState t{-INFINITY, 0.f, 0.f, 0.f, 0.f};
+          for (int w = 0; w < 4; ++w) {
+            SaState o;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.m), "=f"(o.l), "=f"(o.sx), "=f"(o.sy) : "r"(sa_smem + 32u * (uint32_t)w));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o.sz) : "r"(sa_smem + 32u * (uint32_t)w + 16u));
+            sa_merge(t, o);
+          }
+          const int hw = a.Ho * a.Wo, chunks = hw / TC_BLOCK_M;
+          const int bb = m0 / hw, tile_in_img = (m0 - bb * hw) / TC_BLOCK_M, kp = n0 >> 6;
+          float* dst = a.sa_partial + ((size_t)(bb * (a.Cout >> 6) + kp) * chunks + tile_in_img) * 5;
+          dst[0] = t.m; dst[1] = t.l; dst[2] = t.sx; dst[3] = t.sy; dst[4] = t.sz;
+        }
+        epi_barrier<EPI>();                                        // the shared-memory hop is reused by the next tile
+        continue;
+      }
       if (a.out_nchw) {
         // fp32 [B,Cout,Ho,Wo] (heatmap logits for the integral layer): lanes hold adjacent pixels, stores are coalesced
         mbar_wait(bar_accf + 8u * buf, (li >> 1) & 1);
@@ -654,9 +711,14 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   // very short K (1x1 expansions out of 64 / 128 channels): the tile is all epilogue and the layer is bound by the bytes it
   // writes, so two co-resident CTAs with 128-wide tiles keep more stores in flight than one CTA with a 256-wide tile
   // (measured: 64->256 @64x64 with residual 81 -> 75 us, without 60 -> 47 us)
-  const bool short_k = p.Ktot <= 128 && bn > 128 && a.Cout % 128 == 0;
+  const bool short_k = p.Ktot <= 128 && bn > 128 && a.Cout % 128 == 0 && a.sa_partial == nullptr;
   if (short_k) bn = 128;
-  if (force_bn && a.Cout % force_bn == 0 && (!tf32 || force_bn <= 128)) bn = force_bn;
+  if (a.sa_partial != nullptr) {
+    if (a.Cout % 64 || (a.Ho * a.Wo) % TC_BLOCK_M || a.out_sy != 1 || a.out_sx != 1 || a.Ho_full != a.Ho || a.Wo_full != a.Wo || a.res != nullptr)
+      return fail(HRP_ERR_INVALID, "conv_tc: fused soft-argmax needs Cout %% 64 == 0 and whole 128-pixel tiles per frame (Cout=%d, %dx%d)", a.Cout, a.Ho, a.Wo);
+    bn = 64;                                                // one N tile = the 64 depth bins of one keypoint
+  }
+  if (force_bn && a.Cout % force_bn == 0 && (!tf32 || force_bn <= 128) && a.sa_partial == nullptr) bn = force_bn;
   p.block_n = bn;
   p.tiles_n = a.Cout / bn;
   p.total_tiles = mtiles * p.tiles_n;
@@ -667,6 +729,7 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   static const int force_epi = env_int("HRP_TC_EPI", 0);
   int epi = (bn >= 128 && p.Ktot <= 256 && !short_k) ? 8 : 4;
   if (force_epi == 4 || force_epi == 8) epi = force_epi;
+  if (a.sa_partial != nullptr) epi = 4;
   int ctas = (epi == 4 && p.total_tiles >= 2 * sms && tm <= 256) ? 2 : 1;
   if (force_ctas) ctas = (epi == 4 && force_ctas == 2 && tm <= 256) ? 2 : 1;
   const size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 1024 : 0);

@@ -30,6 +30,10 @@ struct ConvArgs {
   // Tensor-core family only: percentage of the GPU's CTA slots this launch's persistent grid may take (0 = all). The
   // multi-lane graph runs several convs at once; most are latency-bound, so sharing the SMs beats time-slicing them.
   int grid_pct;
+  // Tensor-core family only: the conv IS the heatmap head (Cout = keypoints x 64 depth bins over a 64x64 map). Instead of
+  // storing logits, each 128-pixel x 64-bin tile reduces its own online-softmax state and writes one 5-float partial to
+  // sa_partial[(frame*keypoints + keypoint) * (Ho*Wo/128) + tile] for softargmax_finalize_launch. `out` is not written.
+  float* sa_partial;
 };
 
 int conv_f32_launch(const ConvArgs& a, cudaStream_t s);
@@ -112,6 +116,9 @@ size_t softargmax_workspace(int B, int K, int D, int H, int W);
 int softargmax_launch(const float* hm, int B, int K, int D, int H, int W, const float* Kmat, const float* root_z,
                       float depth_factor, float image_size, int rootid, int fixroot, float* uvd, float* xyz, void* ws,
                       size_t ws_bytes, float* root_uv, float* trans, float* kp2d, cudaStream_t stream, int* launches);
+int softargmax_finalize_launch(const float* partial, int B, int K, int chunks, int D, int H, int W, const float* Kmat,
+                               const float* root_z, float depth_factor, float image_size, int rootid, int fixroot,
+                               float* uvd, float* xyz, float* root_uv, float* trans, float* kp2d, cudaStream_t stream);
 int fk_launch(const hrp_fk* fk, const float* q, const float* rot6d, const float* trans, const float* Kmat, int64_t N,
               float* xyz, float* uv, cudaStream_t stream);
 

@@ -120,6 +120,7 @@ struct hrp_handle {
   std::vector<std::vector<int>> waits;             // per op: producer ops on other lanes it must wait for
   std::vector<char> signals;                       // per op: some other lane waits for it
   bool use_lanes = true;
+  bool sa_fused = false;       // tensor-core families: the heatmap conv reduces its own logits (conv_tc.cu), no logits tensor
   unsigned long long* timeline = nullptr;           // HRP_TIMELINE: 2 stamps per op (device)
   int lane_pct[hrp::kMaxLanes] = {};               // share of the CTA slots a conv of this lane may occupy (graph mode)
   int64_t last_launches = 0;
@@ -681,6 +682,10 @@ struct GraphBuilder {
     h->tensors.clear(); h->ops.clear();
     prec = h->cfg.precision;
     act_esize = prec == HRP_PREC_BF16 ? 2 : 4;
+    {
+      const char* e = getenv("HRP_NO_SA_FUSION");
+      h->sa_fused = prec != HRP_PREC_FP32 && !(e && atoi(e) != 0);
+    }
     const int nk = h->nkpt, dof = h->dof;
     const int fw[HRP_NUM_FIELDS] = {dof, 6, 3, 2, 1, nk * 3, nk * 3, nk * 3, nk * 2, nk * 2};
     h->t_xreg = special(T_XREG, 3LL * 256 * 256);
@@ -724,7 +729,8 @@ struct GraphBuilder {
     if (status != HRP_OK) return status;
     cur_lane = kp_lane;
     h->tensors[xf.id].keep = true; h->debug["xf"] = xf.id;
-    h->tensors[logits.id].keep = true; h->debug["logits"] = logits.id;
+    h->tensors[logits.id].keep = true;
+    if (!h->sa_fused) h->debug["logits"] = logits.id;      // fused: the logits never exist outside the conv's accumulators
     {
       OpDesc op{};
       op.kind = OP_SOFTARGMAX; op.cls = CLS_SOFTARGMAX; op.in = logits.id; op.in2 = h->t_kmat; op.in3 = h->t_field[HRP_F_DEPTH];
@@ -847,7 +853,7 @@ int make_plan(hrp_handle* h, int B, Plan** out, int slot = 0) {
   p->io_kv = fl.alloc(align_up((size_t)B * 4, A));
   p->io_K = fl.alloc(align_up((size_t)B * 9 * 4, A));
   p->io_out = fl.alloc(align_up((size_t)record_floats(h, B, nullptr) * 4, A));
-  p->sa_ws_bytes = softargmax_workspace(B, h->nkpt, 64, 64, 64);
+  p->sa_ws_bytes = std::max(softargmax_workspace(B, h->nkpt, 64, 64, 64), (size_t)B * h->nkpt * (64 * 64 / 128) * 5 * sizeof(float));
   p->sa_ws = fl.alloc(align_up(p->sa_ws_bytes, A));
   // Activations: one arena per lane. Ops of a lane run in list order on one stream, so recycling a tensor for a later
   // tensor of the same lane is safe; tensors that another lane touches are never recycled.
@@ -968,6 +974,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
           a.tm_box[0] = 32; a.tm_box[1] = 128; a.tm_box[2] = 1; a.tm_box[3] = 1;
         }
         if (lanes) a.grid_pct = h->lane_pct[o.lane];
+        if (o.out_nchw && h->sa_fused) a.sa_partial = reinterpret_cast<float*>(p->ws + p->sa_ws);
         if (o.cls == CLS_CONV_TC) HRP_TRY(conv_tc_launch(a, tf32, tf32 && !o.out_nchw, st_op));
         else HRP_TRY(conv_f32_launch(a, st_op));
         break;
@@ -1008,6 +1015,13 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         HRP_TRY(mlp_dec_launch(static_cast<float*>(ptr(o.out)), static_cast<const float*>(ptr(o.in2)), o.state_stride, static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, B, o.N, o.dof, st_op));
         break;
       case OP_SOFTARGMAX: {
+        if (h->sa_fused) {       // the heatmap conv already wrote 32 partial states per (frame, keypoint)
+          HRP_TRY(softargmax_finalize_launch(reinterpret_cast<const float*>(p->ws + p->sa_ws), B, h->nkpt, 64 * 64 / 128, 64, 64, 64,
+                                             static_cast<const float*>(ptr(o.in2)), static_cast<const float*>(ptr(o.in3)), h->cfg.depth_factor,
+                                             h->cfg.image_size, h->ref_kp, h->cfg.fix_root, static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)),
+                                             static_cast<float*>(ptr(o.out3)), static_cast<float*>(ptr(o.out4)), static_cast<float*>(ptr(o.out5)), st_op));
+          break;
+        }
         int nl = 0;
         HRP_TRY(softargmax_launch(static_cast<const float*>(ptr(o.in)), B, h->nkpt, 64, 64, 64, static_cast<const float*>(ptr(o.in2)), static_cast<const float*>(ptr(o.in3)),
                                   h->cfg.depth_factor, h->cfg.image_size, h->ref_kp, h->cfg.fix_root, static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)),

@@ -11,37 +11,13 @@
 //             the camera back-projection.
 // The expectation sum_i i*p_i over a marginal equals sum over all bins of coord*p, so no marginal is materialised.
 #include "common.h"
+#include "sa_state.h"
 
 namespace hrp {
 
 constexpr int SA_THREADS = 256;
 constexpr int SA_CHUNK = 16384;       // floats per CTA (64 KB)
 constexpr int SA_UNROLL = 4;          // float4 loads in flight per thread
-
-struct SaState {
-  float m, l, sx, sy, sz;
-};
-
-__device__ __forceinline__ void sa_merge(SaState& a, const SaState& b) {
-  const float M = fmaxf(a.m, b.m);
-  if (M == -INFINITY) return;  // both empty
-  const float fa = __expf(a.m - M), fb = __expf(b.m - M);
-  a.l = a.l * fa + b.l * fb;
-  a.sx = a.sx * fa + b.sx * fb;
-  a.sy = a.sy * fa + b.sy * fb;
-  a.sz = a.sz * fa + b.sz * fb;
-  a.m = M;
-}
-
-__device__ __forceinline__ SaState sa_shfl_xor(const SaState& s, int off) {
-  SaState o;
-  o.m = __shfl_xor_sync(0xffffffffu, s.m, off);
-  o.l = __shfl_xor_sync(0xffffffffu, s.l, off);
-  o.sx = __shfl_xor_sync(0xffffffffu, s.sx, off);
-  o.sy = __shfl_xor_sync(0xffffffffu, s.sy, off);
-  o.sz = __shfl_xor_sync(0xffffffffu, s.sz, off);
-  return o;
-}
 
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
   float4 v;
@@ -219,6 +195,20 @@ int softargmax_launch(const float* hm, int B, int K, int D, int H, int W, const 
                                                                     depth_factor, image_size, rootid, fixroot, uvd, xyz, tail);
   HRP_CHECK_LAUNCH("softargmax_finalize_kernel");
   if (launches) *launches += 2;
+  return HRP_OK;
+}
+
+// Second half only: merge `chunks` partial states per (frame, keypoint) that something else produced (the final conv's
+// epilogue, conv_tc.cu) and finish exactly as the stand-alone op does.
+int softargmax_finalize_launch(const float* partial, int B, int K, int chunks, int D, int H, int W, const float* Kmat,
+                               const float* root_z, float depth_factor, float image_size, int rootid, int fixroot,
+                               float* uvd, float* xyz, float* root_uv, float* trans, float* kp2d, cudaStream_t stream) {
+  if (B <= 0) return HRP_OK;
+  const int rows = B * K;
+  SaTail tail{root_uv, trans, kp2d};
+  softargmax_finalize_kernel<<<ceil_div(rows, 4), 128, 0, stream>>>(partial, rows, K, chunks, W, H, D, Kmat, root_z,
+                                                                    depth_factor, image_size, rootid, fixroot, uvd, xyz, tail);
+  HRP_CHECK_LAUNCH("softargmax_finalize_kernel");
   return HRP_OK;
 }
 

@@ -358,6 +358,32 @@ def test_fullnet_distinct_reg_and_root_images(dev):
     swapped = dict(zip(names, m(img2.to(dev), img.to(dev), kv.to(dev), K=K.to(dev))))
     assert helpers.maxdiff(swapped["root_depth"], got["root_depth"]) > 1e-4
 
+
+@pytest.mark.parametrize("robot,backbone", [("panda", "resnet50"), ("baxter", "hrnet32")])
+def test_fused_heatmap_head_matches_logits_plus_softargmax(robot, backbone, dev, monkeypatch):
+    """Tensor-core families never store the heatmap: the final 1x1 conv's epilogue reduces each 128-pixel x 64-bin tile to
+    an online-softmax partial (conv_tc.cu) and only the merge kernel runs afterwards. Against the same network with
+    that fusion switched off (logits written as fp32 NCHW, then the single-pass soft-argmax kernel) the integral
+    keypoints agree to summation order."""
+    from hrp_b200.model import HoliRobPoseB200
+    _, sd = helpers.oracle_for(robot, backbone)
+    img, K, kv = helpers.inputs(3, 515)
+    outs = []
+    for off in ("0", "1"):
+        monkeypatch.setenv("HRP_NO_SA_FUSION", off)
+        m = HoliRobPoseB200(robot, {"backbone_name": backbone}, device=dev, precision="bf16")
+        m.load_state_dict(sd)
+        outs.append({k: v.clone() for k, v in m.forward_dict(img.to(dev), K.to(dev), kv.to(dev)).items()})
+        n_launch = m.launch_count()
+        del m
+    assert n_launch > 0
+    fused, plain = outs
+    assert helpers.maxdiff(fused["uvd"], plain["uvd"]) < 2e-6
+    assert helpers.maxdiff(fused["kp2d_int"], plain["kp2d_int"]) < 2e-3
+    assert helpers.maxdiff(fused["kp3d_int"], plain["kp3d_int"]) < 1e-5
+    for k in ("joint_angles", "rot6d", "root_depth"):          # untouched by the fusion
+        assert torch.equal(fused[k], plain[k]), k
+
 def test_host_pipeline_matches_forward_dict(dev):
     """HostPipeline (double-buffered host->device upload overlapping the forward) returns, batch after batch, exactly what
     forward_dict returns for the same inputs."""
