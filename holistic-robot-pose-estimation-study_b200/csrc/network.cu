@@ -123,6 +123,7 @@ struct hrp_handle {
   bool sa_fused = false;       // tensor-core families: the heatmap conv reduces its own logits (conv_tc.cu), no logits tensor
   unsigned long long* timeline = nullptr;           // HRP_TIMELINE: 2 stamps per op (device)
   int lane_pct[hrp::kMaxLanes] = {};               // share of the CTA slots a conv of this lane may occupy (graph mode)
+  bool lane_pct_auto = true;                       // no explicit setting: small batches (latency-bound use) get twice the share
   int64_t last_launches = 0;
   int t_xreg = -1, t_xroot = -1, t_kval = -1, t_kmat = -1, t_field[HRP_NUM_FIELDS];
   int field_width[HRP_NUM_FIELDS];
@@ -973,7 +974,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
           a.tm_gstr[0] = 2 * px; a.tm_gstr[1] = row; a.tm_gstr[2] = (size_t)STEM_HP * row;
           a.tm_box[0] = 32; a.tm_box[1] = 128; a.tm_box[2] = 1; a.tm_box[3] = 1;
         }
-        if (lanes) a.grid_pct = h->lane_pct[o.lane];
+        if (lanes) a.grid_pct = (h->lane_pct_auto && B < 32) ? 2 * h->lane_pct[o.lane] : h->lane_pct[o.lane];
         if (o.out_nchw && h->sa_fused) a.sa_partial = reinterpret_cast<float*>(p->ws + p->sa_ws);
         if (o.cls == CLS_CONV_TC) HRP_TRY(conv_tc_launch(a, tf32, tf32 && !o.out_nchw, st_op));
         else HRP_TRY(conv_f32_launch(a, st_op));
@@ -984,7 +985,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         BlockArgs a{};
         a.x = ptr(o.in); a.w1 = L1.w_tc; a.w2 = L2.w_tc; a.b1 = L1.bias; a.b2 = L2.bias; a.out = ptr(o.out);
         a.B = B; a.H = o.Hi; a.W = o.Wi; a.C = o.Cin;
-        if (lanes) a.grid_pct = h->lane_pct[o.lane];
+        if (lanes) a.grid_pct = (h->lane_pct_auto && B < 32) ? 2 * h->lane_pct[o.lane] : h->lane_pct[o.lane];
         HRP_TRY(conv_block_launch(a, st_op));
         break;
       }
@@ -1185,6 +1186,7 @@ extern "C" int hrp_finalize_weights(hrp_handle* h) {
     const bool two_hrnets = h->cfg.backbone == HRP_BACKBONE_HRNET32;
     const char* e0 = getenv("HRP_PCT_HI");  const int hi = e0 ? atoi(e0) : 25;     // full-resolution branch, ResNet trunk
     const char* e1 = getenv("HRP_PCT_LO");  const int lo = e1 ? atoi(e1) : 25;     // lower-resolution branches
+    if (e0 || e1) h->lane_pct_auto = false;
     for (int l = 0; l < kMaxLanes; ++l) h->lane_pct[l] = ((l & 3) == 0 || (!two_hrnets && l == 4)) ? hi : lo;
   }
   h->finalized = true;
@@ -1214,6 +1216,7 @@ extern "C" int hrp_set_option(hrp_handle* h, const char* name, int64_t value) {
   }
   if (std::strcmp(name, "lane_share_pct") == 0) { // share of the CTA slots one conv launch may take (default 25: tuned for a
     if (value < 5 || value > 100) return fail(HRP_ERR_INVALID, "hrp_set_option: lane_share_pct must be 5..100");   // stream of overlapping
+    h->lane_pct_auto = false;
     for (int l = 0; l < kMaxLanes; ++l) h->lane_pct[l] = (int)value;                                               // forwards; 50 gives the
     return HRP_OK;                                                                                                 // lowest single-call latency)
   }

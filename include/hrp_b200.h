@@ -165,8 +165,8 @@ int hrp_forward(hrp_handle* h, const float* x_reg, const float* x_root, const fl
 /* Options: "cuda_graph" (0/1, default 1: replay one graph per batch size), "lanes" (0/1, default 1: capture the graph
  * over several streams so independent sub-networks overlap), "slots" (1..4, default 3: plans = workspace + graph kept per
  * batch size and used round-robin, so consecutive forwards enqueued on different streams overlap), "lane_share_pct"
- * (5..100, default 25: share of the CTA slots one conv launch may take; 25 maximises the throughput of overlapping
- * forwards, 50 minimises the latency of a single one). Graph-shaping options take effect for graphs not yet captured.
+ * (5..100: share of the CTA slots one conv launch may take; default 25 for batches of 32 frames and more -- it maximises
+ * the throughput of overlapping forwards -- and 50 below, where the latency of a single forward matters). Graph-shaping options take effect for graphs not yet captured.
  * Unknown option -> HRP_ERR_INVALID. */
 int hrp_set_option(hrp_handle* h, const char* name, int64_t value);
 
