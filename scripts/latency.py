@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Single-call latency of the forward (BASELINE configs[0] is batch 1): latency.py [precision] [lane_share_pct]"""
+"""Single-call latency of the forward (BASELINE configs[0] is batch 1): latency.py [precision] [lane_share_pct, 0 = library default]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,7 +11,8 @@ share = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 dev = torch.device("cuda", 0)
 m = HoliRobPoseB200("panda", {"backbone_name": "resnet50"}, device=dev, precision=prec)
 m.load_state_dict(synth.make_state_dict("panda", "resnet50"))
-m.set_option("lane_share_pct", share)
+if share > 0:
+    m.set_option("lane_share_pct", share)
 for B in (1, 4, 16, 64):
     img, K, kv = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(B, 1))
     for _ in range(5):
