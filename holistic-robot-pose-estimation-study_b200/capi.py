@@ -16,7 +16,7 @@ BACKBONE = {"resnet": 0, "resnet50": 0, "hrnet": 1, "hrnet32": 1}
 
 EXPORTS = (
     "hrp_fk_create", "hrp_fk_destroy", "hrp_fk_project", "hrp_softargmax3d_workspace", "hrp_softargmax3d",
-    "hrp_conv2d_nhwc", "hrp_basic_block_nhwc", "hrp_create", "hrp_destroy", "hrp_num_weights", "hrp_weight_name", "hrp_weight_shape",
+    "hrp_conv2d_nhwc", "hrp_basic_block_nhwc", "hrp_basic_chain_nhwc", "hrp_create", "hrp_destroy", "hrp_num_weights", "hrp_weight_name", "hrp_weight_shape",
     "hrp_set_weight", "hrp_finalize_weights", "hrp_output_offsets", "hrp_workspace_bytes", "hrp_forward",
     "hrp_set_option", "hrp_launch_count", "hrp_debug_tensor", "hrp_forward_profile", "hrp_conv_bench", "hrp_last_error",
     "hrp_version",
@@ -81,6 +81,7 @@ def lib():
         L.hrp_forward_profile.argtypes = [vp, f32p, f32p, f32p, f32p, i32, f32p, C.POINTER(C.c_float), C.POINTER(i64),
                                           C.POINTER(C.c_double), vp]
         L.hrp_basic_block_nhwc.argtypes = [f32p] * 6 + [i32] * 4 + [vp]
+        L.hrp_basic_chain_nhwc.argtypes = [f32p] * 3 + [i32, f32p] + [i32] * 4 + [vp]
         L.hrp_conv_bench.argtypes = [i32] * 10 + [C.POINTER(C.c_float), vp]
         _lib = L
     return _lib

@@ -64,6 +64,19 @@ struct BlockArgs {
 };
 bool conv_block_supported(const BlockArgs& a);
 int conv_block_launch(const BlockArgs& a, cudaStream_t s);
+// A chain of BasicBlocks (nconv = 2 x blocks <= 8 convs) on one low-resolution branch in one launch, one image per CTA,
+// activations resident in shared memory, weights streamed (conv_chain.cu): bf16 NHWC in/out, C = 128 or 256,
+// w[j] = pack_conv_tc images (128-byte operand rows), b[j] folded biases; conv 2k, 2k+1 form block k.
+struct ChainArgs {
+  const void* x;
+  void* out;
+  const void* w[8];
+  const float* b[8];
+  int nconv;
+  int B, H, W, C;
+};
+bool conv_chain_supported(const ChainArgs& a);
+int conv_chain_launch(const ChainArgs& a, cudaStream_t s);
 
 int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t s);
 int cast_bf16_to_f32_launch(const void* in, float* out, size_t n, cudaStream_t s);

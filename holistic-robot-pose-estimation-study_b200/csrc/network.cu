@@ -23,7 +23,7 @@ struct hrp_fk;  // fk_project.cu
 
 namespace hrp {
 
-enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_RANK, OP_DEC, OP_SOFTARGMAX, OP_FK, OP_STEM_PACK, OP_BLOCK };
+enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_RANK, OP_DEC, OP_SOFTARGMAX, OP_FK, OP_STEM_PACK, OP_BLOCK, OP_CHAIN };
 enum { CLS_CONV_TC = 0, CLS_CONV_F32 = 1, CLS_STEM = 2, CLS_ELEM = 3, CLS_HEADS = 4, CLS_SOFTARGMAX = 5, CLS_FK = 6 };
 enum TKind { T_WS = 0, T_XREG, T_XROOT, T_KVAL, T_KMAT, T_FIELD, T_CONST };
 
@@ -54,6 +54,7 @@ struct OpDesc {
   int in = -1, res = -1, out = -1, in2 = -1, in3 = -1, in4 = -1;
   int out2 = -1, out3 = -1, out4 = -1, out5 = -1;
   int layer = -1, layer2 = -1;   // layer2: second conv of a fused BasicBlock (OP_BLOCK)
+  int chain[8] = {-1, -1, -1, -1, -1, -1, -1, -1}, n_chain = 0;   // OP_CHAIN: the convs of a fused branch (conv_chain.cu)
   int Hi = 1, Wi = 1, Cin = 0, Ho = 1, Wo = 1, Cout = 0, KH = 1, KW = 1, stride = 1, pad_h = 0, pad_w = 0;
   int out_sy = 1, out_sx = 1, out_oy = 0, out_ox = 0, Ho_full = 1, Wo_full = 1, relu = 0, out_nchw = 0;
   int res_after_act = 0;
@@ -465,10 +466,39 @@ struct GraphBuilder {
   // Branch i of an HRNet (its blocks and the fuse ops that produce output i) runs on lane lane0 + i: the branches of a
   // module are independent until the fuse layers exchange them (HRnet.py:247-265), and the low-resolution ones are far
   // too small to fill 148 SMs on their own.
+  // The four BasicBlocks of a low-resolution branch as one launch (conv_chain.cu), when the kernel takes the shape.
+  bool branch_chain(Tn* x, const std::string& p) {
+    ChainArgs probe{};
+    probe.B = 1; probe.H = x->H; probe.W = x->W; probe.C = x->C; probe.nconv = 8;
+    if (prec != HRP_PREC_BF16 || !conv_chain_supported(probe)) return false;
+    OpDesc op{};
+    op.kind = OP_CHAIN; op.cls = CLS_CONV_TC;
+    op.Hi = op.Ho = op.Ho_full = x->H; op.Wi = op.Wo = op.Wo_full = x->W; op.Cin = op.Cout = x->C; op.KH = op.KW = 3; op.stride = 1; op.pad_h = op.pad_w = 1;
+    op.relu = 1; op.ld = x->C;
+    for (int k = 0; k < 4; ++k) {
+      const std::string b = S("%s.%d", p.c_str(), k);
+      op.chain[op.n_chain++] = make_layer(b + ".conv1", b + ".bn1", x->C, x->C, 3, 3, shape_of(op));
+      op.chain[op.n_chain++] = make_layer(b + ".conv2", b + ".bn2", x->C, x->C, 3, 3, shape_of(op));
+    }
+    op.layer = op.chain[0];
+    Tn y = new_tensor(x->H, x->W, x->C, act_esize);
+    op.in = x->id; op.out = y.id;
+    // scratch for the layer-by-layer form the executor uses for small batches (one CTA per image: a handful of images
+    // is a handful of SMs walking the eight convs serially, slower than eight wide launches)
+    op.out2 = new_tensor(x->H, x->W, x->C, act_esize).id;
+    op.out3 = new_tensor(x->H, x->W, x->C, act_esize).id;
+    op.out4 = new_tensor(x->H, x->W, x->C, act_esize).id;
+    op.flops = 8.0 * 2.0 * x->H * x->W * x->C * 9 * x->C;
+    push(op);
+    *x = y;
+    return true;
+  }
+
   std::vector<Tn> hr_module(std::vector<Tn> xs, const std::string& p, int lane0) {
     const int n = (int)xs.size();
     for (int i = 0; i < n; ++i) {
       cur_lane = lane0 + i;
+      if (branch_chain(&xs[i], S("%s.branches.%d", p.c_str(), i))) continue;
       for (int k = 0; k < 4; ++k) xs[i] = basic(xs[i], S("%s.branches.%d.%d", p.c_str(), i, k));
     }
     std::vector<Tn> out(n);
@@ -989,6 +1019,28 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         HRP_TRY(conv_block_launch(a, st_op));
         break;
       }
+      case OP_CHAIN: {
+        ChainArgs a{};
+        a.x = ptr(o.in); a.out = ptr(o.out); a.nconv = o.n_chain;
+        for (int k = 0; k < o.n_chain; ++k) { a.w[k] = h->layers[o.chain[k]].w_tc; a.b[k] = h->layers[o.chain[k]].bias; }
+        a.B = B; a.H = o.Hi; a.W = o.Wi; a.C = o.Cin;
+        static const int min_b = [] { const char* v = getenv("HRP_CHAIN_MIN_B"); return v ? atoi(v) : 8; }();
+        if (B >= min_b) { HRP_TRY(conv_chain_launch(a, st_op)); break; }
+        // small batch: the same eight convs as separate launches, x -> T -> U -> T -> V -> T -> U -> T -> out
+        void* T = ptr(o.out2);
+        void* blk[5] = {ptr(o.in), ptr(o.out3), ptr(o.out4), ptr(o.out3), ptr(o.out)};
+        for (int k = 0; k < o.n_chain; ++k) {
+          ConvArgs c{};
+          const bool second = (k & 1) != 0;
+          c.in = second ? T : blk[k / 2]; c.w = a.w[k]; c.bias = a.b[k]; c.res = second ? blk[k / 2] : nullptr; c.out = second ? blk[k / 2 + 1] : T;
+          c.B = B; c.Hi = c.Ho = c.Ho_full = o.Hi; c.Wi = c.Wo = c.Wo_full = o.Wi; c.Cin = c.Cout = c.ld_out = o.Cin;
+          c.KH = c.KW = 3; c.stride = 1; c.pad_h = c.pad_w = 1; c.out_sy = c.out_sx = 1; c.relu = 1;
+          if (lanes) c.grid_pct = (h->lane_pct_auto && B < 32) ? 2 * h->lane_pct[o.lane] : h->lane_pct[o.lane];
+          HRP_TRY(conv_tc_launch(c, 0, 0, st_op));
+        }
+        n_launch = o.n_chain;
+        break;
+      }
       case OP_STEM_PACK:
         HRP_TRY(stem_pack_launch(static_cast<const float*>(ptr(o.in)), ptr(o.out), B, tf32, st_op));
         break;
@@ -1417,7 +1469,16 @@ extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int C
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (rs == HRP_OK) {
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3 && rs == HRP_OK; ++i) rs = conv_tc_launch(a, tf32, tf32, st);
+    // with_residual == 8: time the 8-conv branch chain (conv_chain.cu) on this shape instead, the same weights for every conv
+    ChainArgs ch{};
+    const bool chain = with_residual == 8;
+    if (chain) {
+      ch.x = din; ch.out = dout; ch.nconv = 8; ch.B = B; ch.H = H; ch.W = W; ch.C = Cin;
+      for (int j = 0; j < 8; ++j) { ch.w[j] = dw; ch.b[j] = static_cast<const float*>(db); }
+      if (k != 3 || stride != 1 || Cin != Cout || tf32 || !conv_chain_supported(ch)) rs = fail(HRP_ERR_INVALID, "hrp_conv_bench: shape not taken by the chain kernel");
+    }
+    auto launch = [&](cudaStream_t s_) { return chain ? conv_chain_launch(ch, s_) : conv_tc_launch(a, tf32, tf32, s_); };
+    for (int i = 0; i < 3 && rs == HRP_OK; ++i) rs = launch(st);
     // the timed launches replay from a CUDA graph so that host-side launch cost (tensor-map encoding, ~15 us) is not what
     // gets measured for kernels shorter than that
     cudaStream_t cs = nullptr;
@@ -1426,7 +1487,7 @@ extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int C
     cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
     cudaStreamSynchronize(st);
     if (rs == HRP_OK && cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      for (int i = 0; i < iters && rs == HRP_OK; ++i) rs = conv_tc_launch(a, tf32, tf32, cs);
+      for (int i = 0; i < iters && rs == HRP_OK; ++i) rs = launch(cs);
       if (cudaStreamEndCapture(cs, &g) != cudaSuccess || cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv_bench: graph capture failed");
     }
     if (rs == HRP_OK) cudaGraphLaunch(ge, st);      // warm replay
@@ -1488,6 +1549,47 @@ extern "C" int hrp_basic_block_nhwc(const float* x, const float* w1_oihw, const 
   if (rs == HRP_OK) rs = conv_block_launch(a, st);
   if (rs == HRP_OK) rs = cast_bf16_to_f32_launch(dout, out, n, st);
   if (cudaStreamSynchronize(st) != cudaSuccess && rs == HRP_OK) rs = fail(HRP_ERR_CUDA, "hrp_basic_block_nhwc: %s", cudaGetErrorString(cudaGetLastError()));
+  for (void* d : tmp) cudaFree(d);
+  return rs;
+}
+
+// A chain of `nblocks` BasicBlocks through the one-launch branch kernel (conv_chain.cu); layer-level parity tests.
+// w_oihw: [2*nblocks][C][C][3][3], b: [2*nblocks][C] (may be null), device fp32; x / out NHWC fp32 (cast to / from bf16 here).
+extern "C" int hrp_basic_chain_nhwc(const float* x, const float* w_oihw, const float* b, int nblocks, float* out, int B, int H, int W, int C,
+                                    void* stream) {
+  if (!x || !w_oihw || !out) return fail(HRP_ERR_INVALID, "hrp_basic_chain_nhwc: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  ChainArgs a{};
+  a.B = B; a.H = H; a.W = W; a.C = C; a.nconv = 2 * nblocks;
+  if (nblocks < 1 || nblocks > 4 || !conv_chain_supported(a))
+    return fail(HRP_ERR_INVALID, "hrp_basic_chain_nhwc: chain not supported by the fused kernel (C=%d, %dx%d, %d blocks)", C, H, W, nblocks);
+  const size_t nw = (size_t)C * C * 9, n = (size_t)B * H * W * C;
+  std::vector<float> w(nw), bb(C), wp(nw), bp(C);
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) -> void* { void* d = nullptr; if (cudaMalloc(&d, std::max<size_t>(bytes, 16)) != cudaSuccess) { cudaGetLastError(); return nullptr; } tmp.push_back(d); return d; };
+  int rs = HRP_OK;
+  for (int k = 0; k < a.nconv && rs == HRP_OK; ++k) {
+    cudaMemcpyAsync(w.data(), w_oihw + (size_t)k * nw, nw * 4, cudaMemcpyDeviceToHost, st);
+    if (b) cudaMemcpyAsync(bb.data(), b + (size_t)k * C, (size_t)C * 4, cudaMemcpyDeviceToHost, st); else std::fill(bb.begin(), bb.end(), 0.f);
+    cudaStreamSynchronize(st);
+    pack_conv_f32(w.data(), bb.data(), nullptr, nullptr, nullptr, nullptr, C, C, 3, 3, wp.data(), bp.data());
+    std::vector<uint8_t> img(pack_conv_tc_bytes(9 * C, C, 0, 128));
+    pack_conv_tc(wp.data(), 9 * C, C, 0, 128, img.data());
+    void* dw = dalloc(img.size());
+    float* db = static_cast<float*>(dalloc((size_t)C * 4));
+    if (!dw || !db) { rs = fail(HRP_ERR_NOMEM, "hrp_basic_chain_nhwc: out of device memory"); break; }
+    cudaMemcpy(dw, img.data(), img.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(db, bp.data(), (size_t)C * 4, cudaMemcpyHostToDevice);
+    a.w[k] = dw; a.b[k] = db;
+  }
+  void* dx = dalloc(n * 2);
+  void* dout = dalloc(n * 2);
+  if (rs == HRP_OK && (!dx || !dout)) rs = fail(HRP_ERR_NOMEM, "hrp_basic_chain_nhwc: out of device memory");
+  if (rs == HRP_OK) rs = cast_f32_to_bf16_launch(x, dx, n, st);
+  a.x = dx; a.out = dout;
+  if (rs == HRP_OK) rs = conv_chain_launch(a, st);
+  if (rs == HRP_OK) rs = cast_bf16_to_f32_launch(dout, out, n, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess && rs == HRP_OK) rs = fail(HRP_ERR_CUDA, "hrp_basic_chain_nhwc: %s", cudaGetErrorString(cudaGetLastError()));
   for (void* d : tmp) cudaFree(d);
   return rs;
 }

@@ -117,6 +117,19 @@ def basic_block_nhwc(x, w1, b1, w2, b2):
     return out
 
 
+def basic_chain_nhwc(x, weights, biases):
+    """A chain of HRNet BasicBlocks through the one-launch branch kernel (layer-level parity tests). x NHWC fp32;
+    weights [2*nblocks, C, C, 3, 3], biases [2*nblocks, C] or None, CUDA fp32."""
+    nb, hh, ww, ch = x.shape
+    out = torch.empty_like(x)
+    st = torch.cuda.current_stream(x.device).cuda_stream
+    z = C.c_void_p(0)
+    capi.check(capi.lib().hrp_basic_chain_nhwc(_ptr(x.contiguous()), _ptr(weights.contiguous()),
+                                               _ptr(biases.contiguous()) if biases is not None else z, weights.shape[0] // 2,
+                                               _ptr(out), nb, hh, ww, ch, C.c_void_p(st)))
+    return out
+
+
 class HoliRobPoseB200(torch.nn.Module):
     """CUDA drop-in for RootNetwithRegInt (inference forward only)."""
 

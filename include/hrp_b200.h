@@ -111,6 +111,13 @@ int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias
 int hrp_basic_block_nhwc(const float* x, const float* w1_oihw, const float* b1, const float* w2_oihw, const float* b2,
                          float* out, int B, int H, int W, int C, void* stream);
 
+/* A chain of `nblocks` (1..4) such BasicBlocks -- one branch of an HRNet module (HRnet.py:137-149) -- through the one-launch
+ * branch kernel of the bf16 family (one image per CTA, activations resident in shared memory, weights streamed). w_oihw:
+ * [2*nblocks][C][C][3][3] (conv1, conv2 of block 0, conv1 of block 1, ...), b: [2*nblocks][C] or NULL; x, out NHWC fp32.
+ * HRP_ERR_INVALID when the shape is not one the kernel takes (C = 128 / 256 at the low HRNet resolutions). Parity tests. */
+int hrp_basic_chain_nhwc(const float* x, const float* w_oihw, const float* b, int nblocks, float* out, int B, int H, int W, int C,
+                         void* stream);
+
 /* ---- full network ------------------------------------------------------------------------------------------------------ */
 typedef struct {
   int32_t backbone;          /* hrp_backbone: keypoint-branch backbone; the DepthNet backbone is always HRNet-W32 */
@@ -181,7 +188,8 @@ int hrp_forward_profile(hrp_handle* h, const float* x_reg, const float* x_root, 
                         double* flops_by_class, void* stream);
 
 /* Micro-benchmark of one tensor-core conv layer (tf32 / bf16 families) on random operands: average device time of
- * `iters` back-to-back launches. Tuning aid (scripts/conv_bench.py); not used on the forward path. */
+ * `iters` back-to-back launches. with_residual: 0 / 1, or 8 = time the 8-conv branch chain kernel (hrp_basic_chain_nhwc's)
+ * on this shape (bf16, k 3, stride 1, Cin == Cout). Tuning aid (scripts/conv_bench.py); not used on the forward path. */
 int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int Cout, int k, int stride, int with_residual,
                    int iters, float* ms_per_launch, void* stream);
 

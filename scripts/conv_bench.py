@@ -19,5 +19,5 @@ ms = C.c_float()
 for H, Cin, Cout, k, stride, res in shapes:
     capi.check(capi.lib().hrp_conv_bench(capi.PREC[prec], B, H, H, Cin, Cout, k, stride, res, 20, C.byref(ms), None))
     Ho = (H + 2 * (k // 2) - k) // stride + 1
-    fl = 2.0 * B * Ho * Ho * Cout * k * k * Cin
+    fl = 2.0 * B * Ho * Ho * Cout * k * k * Cin * (8 if res == 8 else 1)      # res == 8: the 8-conv branch chain kernel
     print("%s B=%d %3dx%-3d %4d->%-4d k%d s%d res%d  %8.2f us  %7.1f TF/s" % (prec, B, H, H, Cin, Cout, k, stride, res, ms.value * 1e3, fl / ms.value / 1e9))

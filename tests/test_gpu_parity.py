@@ -240,6 +240,24 @@ def test_fused_basic_block_equals_two_convs(B, H, dev):
     assert torch.equal(out, ref), float((out - ref).abs().max())
 
 
+@pytest.mark.parametrize("B,H,C,nblocks", [(64, 16, 128, 4), (5, 16, 128, 1), (64, 8, 256, 4), (3, 8, 256, 2), (301, 8, 256, 1),
+                                            (160, 16, 128, 2), (2, 4, 256, 3), (7, 12, 128, 4)])
+def test_branch_chain_equals_layer_by_layer(B, H, C, nblocks, dev):
+    """conv_chain.cu (all BasicBlocks of a low-resolution HRNet branch in one launch, one image per CTA, activations in
+    shared memory) against the same blocks run conv by conv: same operands, K order and bf16 roundings => bit-identical."""
+    from hrp_b200.model import basic_chain_nhwc, conv2d_nhwc
+    g = torch.Generator().manual_seed(B * 11 + H + C)
+    x = torch.randn(B, H, H, C, generator=g).bfloat16().float().to(dev)
+    w = (torch.randn(2 * nblocks, C, C, 3, 3, generator=g) / (9 * C) ** 0.5 * 0.8).to(dev)
+    b = (0.3 * torch.randn(2 * nblocks, C, generator=g)).to(dev)
+    ref = x
+    for k in range(nblocks):
+        y = conv2d_nhwc(ref, w[2 * k], b[2 * k], None, 1, 1, True, "bf16")
+        ref = conv2d_nhwc(y, w[2 * k + 1], b[2 * k + 1], ref, 1, 1, True, "bf16")
+    out = basic_chain_nhwc(x, w, b)
+    assert torch.equal(out, ref), float((out - ref).abs().max())
+
+
 # ---------------------------------------------------------------------------------------------------- full network
 _models = {}
 
@@ -334,6 +352,19 @@ def test_fullnet_batch64_frames_are_independent(dev):
     check_gates(auto, ref2)
 
 
+
+
+def test_fullnet_bf16_branch_chain_and_small_batch_form_agree(dev):
+    """bf16 family: at batch 64 the low-resolution HRNet branches run through the one-launch chain kernel, at batch 3 the
+    executor runs the same convs layer by layer (one CTA per image would leave the GPU idle). Both forms are bit-identical
+    per layer, so a frame of the big batch must equal the same frame in the small batch."""
+    m = gpu_model("panda", "resnet50", dev, "bf16")
+    img, K, kv = helpers.inputs(64, 911)
+    big = m.forward_dict(img.to(dev), K.to(dev), kv.to(dev))
+    idx = [1, 30, 62]
+    small = m.forward_dict(img[idx].to(dev), K[idx].to(dev), kv[idx].to(dev))
+    for k in big:
+        assert helpers.maxdiff(big[k][idx], small[k]) < 1e-5, k
 
 
 def test_fullnet_distinct_reg_and_root_images(dev):
