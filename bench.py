@@ -274,7 +274,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic_per_step.json")
     if os.path.exists(tpath) and args.precision == "bf16" and B == BATCH_PER_GPU:
         traffic = json.load(open(tpath)).get("dram_bytes_per_step")
-    roofline = {"bound": "tensor", "kernel": "%s (conv_tc_kernel + conv_slab_kernel, %d launches per step)" % (conv_name, conv["launches"]),
+    roofline = {"bound": "tensor", "kernel": "%s (conv_tc / conv_slab / conv_block / conv_chain kernels, %d launches per step)" % (conv_name, conv["launches"]),
                 "achieved": conv_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": conv_tflops / tensor_peak, "traffic": traffic,
                 "traffic_note": "DRAM bytes of ALL kernels of one step (ncu dram__bytes_read+write, profiles/r01_launches_bf16_b64.csv); null when not profiled for this config",
