@@ -56,6 +56,7 @@ struct TcParams {
   int epi_tma;       // 1: the epilogue stages the tile in swizzled shared memory and moves it with TMA (residual in, result out)
   int chunk_bytes;   // epi_tma: bytes of one staged row chunk (128, or 64 when block_n*elem == 64)
   int n_chunks;      // epi_tma: block_n*elem / chunk_bytes
+  int res_prefetch;  // epi_tma, two staging buffers: request the residual of tile li+1 at the end of tile li
   int n_stg;         // epi_tma: staging buffers (2 when shared memory allows: the store of tile i overlaps tile i+1)
   ConvArgs a;
   int tma;           // 1: activations arrive by cp.async.bulk.tensor (one thread), 0: cp.async gather (four warps)
@@ -392,7 +393,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           if (p.n_stg == 2) bulk_wait_read1(); else bulk_wait_read0();
         }
         epi_barrier<EPI>();
-        if (has_res && eid == 0) {
+        // with two staging buffers the residual of tile li+1 is requested at the end of tile li (below), so that short-K
+        // tiles (1x1 expansions: four MMAs per tile) do not sit out a load latency each; only the first tile asks here
+        const bool prefetch = has_res && p.res_prefetch != 0;
+        if (has_res && eid == 0 && (!prefetch || li == 0)) {
           mbar_arrive_expect_tx(bar_res, (uint32_t)p.n_chunks * chunk_sz);
           for (int k = 0; k < p.n_chunks; ++k)
             tma_load_2d(tile_stg + (uint32_t)k * chunk_sz, p.tmap_res, a.out_coff + n0 + k * (int)(cbytes / ESZ), m0, bar_res);
@@ -469,6 +473,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           for (int k = 0; k < p.n_chunks; ++k)
             tma_store_2d(p.tmap_out, a.out_coff + n0 + k * (int)(cbytes / ESZ), m0, tile_stg + (uint32_t)k * chunk_sz);
           bulk_commit();
+          const int next = tile + (int)gridDim.x;
+          if (prefetch && next < p.total_tiles) {
+            bulk_wait_read1();                                 // the store of tile li-1 has finished reading the other buffer
+            const int m1 = (next / p.tiles_n) * TC_BLOCK_M, n1 = (next % p.tiles_n) * p.block_n;
+            const uint32_t stg1 = stg + (uint32_t)(sb ^ 1) * (uint32_t)(p.n_chunks * TC_BLOCK_M * p.chunk_bytes);
+            const uint32_t bar1 = bar_res - 8u * (uint32_t)sb + 8u * (uint32_t)(sb ^ 1);
+            mbar_arrive_expect_tx(bar1, (uint32_t)p.n_chunks * chunk_sz);
+            for (int k = 0; k < p.n_chunks; ++k)
+              tma_load_2d(stg1 + (uint32_t)k * chunk_sz, p.tmap_res, a.out_coff + n1 + k * (int)(cbytes / ESZ), m1, bar1);
+          }
         }
         continue;
       }
@@ -745,6 +759,8 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     // two staging buffers when at least three operand stages still fit beside them
     p.n_stg = (2048 + 2 * one + tc_tail_bytes() + 3 * tc_stage_bytes(bn, p.row_bytes) <= budget) ? 2 : 1;
     staging = (p.n_stg * one + 1023) / 1024 * 1024;
+    static const int no_prefetch = env_int("HRP_TC_NO_RES_PREFETCH", 0);
+    p.res_prefetch = (p.n_stg == 2 && a.res != nullptr && !no_prefetch) ? 1 : 0;
   }
   const size_t fixed = 2048 + staging + tc_tail_bytes();
   int smax = (int)((budget - fixed) / tc_stage_bytes(bn, p.row_bytes));
