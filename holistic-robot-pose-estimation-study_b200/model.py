@@ -242,6 +242,8 @@ class HoliRobPoseB200(torch.nn.Module):
         for t, shp in ((x_reg, (B, 3, 256, 256)), (x_root, (B, 3, 256, 256)), (K, (B, 3, 3))):
             if not t.is_cuda or tuple(t.shape) != shp:
                 raise ValueError("expected a CUDA tensor of shape %s, got %s on %s" % (shp, tuple(t.shape), t.device))
+        if B == 0:                                                           # torch modules pass empty batches through
+            return torch.empty(0, device=x_reg.device, dtype=torch.float32), [0] * (capi.NUM_FIELDS + 1)
         same = x_root is x_reg or x_root.data_ptr() == x_reg.data_ptr()
         x_reg = x_reg.float().contiguous()                                   # full_net.py:265-266
         x_root = x_reg if same else x_root.float().contiguous()

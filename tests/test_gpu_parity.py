@@ -367,6 +367,25 @@ def test_fullnet_bf16_branch_chain_and_small_batch_form_agree(dev):
         assert helpers.maxdiff(big[k][idx], small[k]) < 1e-5, k
 
 
+def test_fullnet_empty_and_single_frame_batches(dev):
+    """Edge sizes of the batch axis: an empty batch comes back as empty fields of the right trailing shapes (what the
+    reference's torch modules do), one frame equals the same frame inside a batch of five, and shape errors are loud."""
+    m = gpu_model("panda", "resnet50", dev)
+    img, K, kv = helpers.inputs(5, 77)
+    out0 = m.forward_dict(img[:0].to(dev), K[:0].to(dev), kv[:0].to(dev))
+    assert out0["joint_angles"].shape == (0, m.dof) and out0["kp2d_fk"].shape == (0, m.nkpt, 2) and out0["kp3d_int"].shape == (0, m.nkpt, 3)
+    t8 = m(img[:0].to(dev), img[:0].to(dev), kv[:0].to(dev), K=K[:0].to(dev))
+    assert len(t8) == 8 and all(t.shape[0] == 0 for t in t8)
+    five = m.forward_dict(img.to(dev), K.to(dev), kv.to(dev))
+    one = m.forward_dict(img[3:4].to(dev), K[3:4].to(dev), kv[3:4].to(dev))
+    for k in five:
+        assert helpers.maxdiff(five[k][3:4], one[k]) < 1e-5, k
+    with pytest.raises(ValueError):
+        m.forward_dict(img[:, :, :128].to(dev), K.to(dev), kv.to(dev))
+    with pytest.raises(ValueError):
+        m.forward_dict(img, K.to(dev), kv.to(dev))          # host tensor: the caller moves data, never a silent copy
+
+
 def test_fullnet_distinct_reg_and_root_images(dev):
     """The reference call takes two crops, x_reg (keypoint branch) and x_root (DepthNet), full_net.py:262-266; the callers
     usually pass the same tensor, which the graph path special-cases. Distinct tensors take the other graph and must
