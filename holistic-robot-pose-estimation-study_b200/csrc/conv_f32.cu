@@ -7,6 +7,8 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.h"
@@ -158,7 +160,95 @@ conv_igemm_f32_kernel(const ConvArgs p) {
   }
 }
 
+// ---- nn.Linear on a few rows: y[M][N] = x[M][K] . W[K][N] + b (full_net.py:214-238, the regression heads) ---------------
+// M is the batch (64 frames): one 64x64 tile per 64 output columns leaves 16-32 CTAs walking K = 1024-2048 alone, 85-300 us
+// for 0.1-0.5 GFLOP. Here a CTA owns 64 rows x 16 columns, so N/16 x ceil(M/64) CTAs share the weight matrix (each reads
+// its 16 columns once, 4-8 MB in total) and the K loop is a six-deep cp.async ring of 32-wide chunks (x: 64x32, W: 32x16),
+// enough bytes in flight to hide the L2 latency. Plain fp32 FMAs in ascending k for every output, independent of M: the
+// frames of a batch stay bit-identical to the same frames run alone. Measured (ncu, alone): 27.8 us for 1024 -> 1024 and
+// 52 us for 2048 -> 2048 at 64 rows (the 64x64-tile kernel: 67 us on average), i.e. 0.85 us per chunk -- bound by the
+// shared-memory pipe (40 LDS.128 per thread per chunk at 4 cycles each), not by the copies; a 4x4 register tile with
+// the chunk's k split over four thread groups would cut that 2.5x. The heads are off the critical path of the graph
+// (they overlap the deconv head), so neither frames/s nor the single-call latency moves.
+constexpr int LS_TM = 64, LS_TN = 16, LS_KC = 32, LS_STAGES = 6, LS_XLD = LS_KC + 4;
+constexpr int LS_STAGE_FLOATS = LS_TM * LS_XLD + LS_KC * LS_TN;
+
+__global__ void __launch_bounds__(256)
+linear_skinny_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                         int M, int K, int N, int ld_out, int relu) {
+  extern __shared__ __align__(16) float ls_smem[];
+  const int tid = threadIdx.x, tm = tid >> 2, tc = (tid & 3) * 4;
+  const int n0 = blockIdx.x * LS_TN, m0 = blockIdx.y * LS_TM;
+  const int chunks = K / LS_KC;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ls_smem);
+  auto issue = [&](int c) {
+    if (c < chunks) {
+      const int st = c % LS_STAGES, k0 = c * LS_KC;
+      const uint32_t xs = sbase + (uint32_t)(st * LS_STAGE_FLOATS) * 4u, ws = xs + (uint32_t)(LS_TM * LS_XLD) * 4u;
+#pragma unroll
+      for (int l = 0; l < LS_TM * LS_KC / 4 / 256; ++l) {          // 64 rows x 8 float4
+        const int idx = tid + l * 256, r = idx >> 3, q = idx & 7;
+        const bool ok = m0 + r < M;
+        const float* src = x + (size_t)(ok ? m0 + r : 0) * K + k0 + q * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xs + (uint32_t)(r * LS_XLD + q * 4) * 4u), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+      }
+      if (tid < LS_KC * LS_TN / 4) {                               // 32 rows x 4 float4
+        const int r = tid >> 2, q = tid & 3;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 16;" ::"r"(ws + (uint32_t)(r * LS_TN + q * 4) * 4u), "l"(w + (size_t)(k0 + r) * N + n0 + q * 4) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int c = 0; c < LS_STAGES - 1; ++c) issue(c);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < chunks; ++c) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(LS_STAGES - 2) : "memory");
+    __syncthreads();                                               // chunk c has landed; everyone is done with chunk c-1's slot
+    issue(c + LS_STAGES - 1);
+    const float* xs = ls_smem + (c % LS_STAGES) * LS_STAGE_FLOATS + tm * LS_XLD;
+    const float* ws = ls_smem + (c % LS_STAGES) * LS_STAGE_FLOATS + LS_TM * LS_XLD + tc;
+#pragma unroll
+    for (int kk = 0; kk < LS_KC; kk += 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(xs + kk);
+      const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 wv = *reinterpret_cast<const float4*>(ws + (kk + j) * LS_TN);
+        acc[0] = fmaf(xe[j], wv.x, acc[0]); acc[1] = fmaf(xe[j], wv.y, acc[1]);
+        acc[2] = fmaf(xe[j], wv.z, acc[2]); acc[3] = fmaf(xe[j], wv.w, acc[3]);
+      }
+    }
+  }
+  const int m = m0 + tm;
+  if (m < M) {
+    const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + tc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 o = make_float4(acc[0] + b4.x, acc[1] + b4.y, acc[2] + b4.z, acc[3] + b4.w);
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    *reinterpret_cast<float4*>(y + (size_t)m * ld_out + n0 + tc) = o;
+  }
+}
+
+static bool linear_skinny_ok(const ConvArgs& a) {
+  static const bool off = [] { const char* v = getenv("HRP_NO_SKINNY_LINEAR"); return v && atoi(v) != 0; }();
+  return !off && a.KH == 1 && a.KW == 1 && a.Hi == 1 && a.Wi == 1 && a.Ho == 1 && a.Wo == 1 && a.stride == 1 && a.pad_h == 0 && a.pad_w == 0 &&
+         !a.out_nchw && a.res == nullptr && a.out_sy == 1 && a.out_sx == 1 && a.out_oy == 0 && a.out_ox == 0 && a.out_coff == 0 &&
+         a.Cin % LS_KC == 0 && a.Cout % LS_TN == 0 && a.ld_out % 4 == 0 && a.Cin / LS_KC >= LS_STAGES;
+}
+
 int conv_f32_launch(const ConvArgs& a, cudaStream_t s) {
+  if (linear_skinny_ok(a) && a.B > 0) {
+    constexpr size_t smem = (size_t)LS_STAGES * LS_STAGE_FLOATS * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+      HRP_CUDA(cudaFuncSetAttribute(linear_skinny_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done = true;
+    }
+    dim3 grid(a.Cout / LS_TN, ceil_div(a.B, LS_TM));
+    linear_skinny_f32_kernel<<<grid, 256, smem, s>>>(static_cast<const float*>(a.in), static_cast<const float*>(a.w), a.bias,
+                                                     static_cast<float*>(a.out), a.B, a.Cin, a.Cout, a.ld_out, a.relu);
+    HRP_CHECK_LAUNCH("linear_skinny_f32_kernel");
+    return HRP_OK;
+  }
   if (a.Cin % CV_BK != 0) return fail(HRP_ERR_INVALID, "conv_f32: Cin=%d must be a multiple of %d", a.Cin, CV_BK);
   if (a.Cout % 4 != 0 && a.Cout > 4) return fail(HRP_ERR_INVALID, "conv_f32: Cout=%d must be a multiple of 4", a.Cout);
   const int M = a.B * a.Ho * a.Wo;

@@ -687,8 +687,12 @@ struct GraphBuilder {
       h->layers.push_back(L);
       l2[k] = (int)h->layers.size() - 1;
     }
+    // the pose and the rotation stacks only meet again in FK (full_net.py:214-238): each iterates on its own lane
+    const int lane_of[2] = {cur_lane, h->n_lanes};
+    h->n_lanes += 1;
     for (int it = 0; it < h->cfg.n_iter; ++it)
       for (int k = 0; k < 2; ++k) {
+        cur_lane = lane_of[k];
         Tn h1 = new_tensor(1, 1, Hd, 4);
         OpDesc r{};
         r.kind = OP_RANK; r.cls = CLS_HEADS; r.in = xc1.id; r.in2 = state[k]; r.out = h1.id; r.ld = 2 * Hd; r.coff = k * Hd;
@@ -707,6 +711,7 @@ struct GraphBuilder {
         push(d);
         state[k] = h->t_field[field[k]];
       }
+    cur_lane = lane_of[0];
   }
 
   int build() {

@@ -169,6 +169,24 @@ def test_conv_layer_against_torch_fp32(B, H, Cin, Cout, k, stride, dev):
     assert helpers.maxdiff(out, ref) < 2e-5 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("B,Cin,Cout,relu", [(64, 2048, 2048, False), (1, 1024, 1024, False), (5, 1024, 1024, True), (130, 2048, 1024, False),
+                                             (64, 192, 16, True)])
+def test_linear_few_rows_against_torch_fp32(B, Cin, Cout, relu, dev):
+    """nn.Linear on the batch rows (the fc stacks of the regression heads, full_net.py:214-238): the skinny fp32 kernel
+    against torch, and every row independent of how many rows travel with it."""
+    from hrp_b200.model import conv2d_nhwc
+    g = torch.Generator().manual_seed(B + Cin)
+    x = torch.randn(B, 1, 1, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5
+    b = torch.randn(Cout, generator=g)
+    ref = torch.nn.functional.linear(x.view(B, Cin).double(), w.view(Cout, Cin).double(), b.double())
+    ref = (torch.relu(ref) if relu else ref).float()
+    out = conv2d_nhwc(x.to(dev), w.to(dev), b.to(dev), None, 1, 0, relu).view(B, Cout)
+    assert helpers.maxdiff(out, ref) < 2e-5 * max(1.0, float(ref.abs().max()))
+    one = conv2d_nhwc(x[B // 2:B // 2 + 1].to(dev), w.to(dev), b.to(dev), None, 1, 0, relu).view(1, Cout)
+    assert torch.equal(one, out[B // 2:B // 2 + 1])
+
+
 def _round_like(x, prec):
     if prec == "bf16":
         return x.bfloat16().float()
