@@ -196,7 +196,8 @@ def _round_like(x, prec):
 @pytest.mark.parametrize("prec", ["bf16", "tf32"])
 @pytest.mark.parametrize("B,H,Cin,Cout,k,stride", [(1, 16, 64, 32, 1, 1), (2, 64, 32, 32, 3, 1), (3, 32, 64, 64, 3, 1),
                                                     (2, 16, 128, 128, 3, 1), (2, 8, 256, 256, 3, 1), (2, 32, 32, 64, 3, 2),
-                                                    (1, 8, 1024, 2048, 1, 1), (5, 17, 64, 96, 3, 2), (2, 64, 256, 448, 1, 1)])
+                                                    (1, 8, 1024, 2048, 1, 1), (5, 17, 64, 96, 3, 2), (2, 64, 256, 448, 1, 1),
+                                                    (40, 64, 64, 256, 1, 1), (9, 32, 128, 512, 1, 1)])
 def test_conv_layer_tensor_core_families(prec, B, H, Cin, Cout, k, stride, dev):
     """tcgen05 implicit GEMM (conv_tc.cu) against a float64 conv on operands rounded to the family's type: the only
     differences left are fp32 accumulation order and the rounding of the stored output (bf16: 2^-8, TF32: 2^-11 rel)."""
