@@ -460,29 +460,41 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
   const uint32_t y = r % (uint32_t)a.H;
   const uint32_t b = r / (uint32_t)a.H;
   const size_t o = (size_t)(i / cv) * a.C + c;
-  uint4 raw[7];
-  int n = 0;
-  for (int k = 0; k < a.n_same; ++k) raw[n++] = __ldg(reinterpret_cast<const uint4*>(static_cast<const T*>(a.same[k]) + o));
-  for (int k = 0; k < a.n_low; ++k) {
-    const int sh = a.shift[k];
-    const uint32_t h = (uint32_t)a.H >> sh, w = (uint32_t)a.W >> sh;
-    raw[n++] = __ldg(reinterpret_cast<const uint4*>(static_cast<const T*>(a.low[k]) + ((size_t)(b * h + (y >> sh)) * w + (x >> sh)) * a.C + c));
-  }
+  // every term's load is issued before the first add; the loops are unrolled over the maximum term counts with
+  // compile-time indices so that the vectors (and the argument struct) stay in registers / constant space -- run-time
+  // indexing put both into a 224-byte local-memory frame
+  uint4 rs[4], rl[3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < a.n_same) rs[k] = __ldg(reinterpret_cast<const uint4*>(static_cast<const T*>(a.same[k]) + o));
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (k < a.n_low) {
+      const int sh = a.shift[k];
+      const uint32_t h = (uint32_t)a.H >> sh, w = (uint32_t)a.W >> sh;
+      rl[k] = __ldg(reinterpret_cast<const uint4*>(static_cast<const T*>(a.low[k]) + ((size_t)(b * h + (y >> sh)) * w + (x >> sh)) * a.C + c));
+    }
   float acc[V];
 #pragma unroll
   for (int e = 0; e < V; ++e) acc[e] = 0.f;
-  for (int k = 0; k < n; ++k) {
+  auto add = [&](const uint4& v) {
     if constexpr (sizeof(T) == 4) {
-      acc[0] += __uint_as_float(raw[k].x); acc[1] += __uint_as_float(raw[k].y); acc[2] += __uint_as_float(raw[k].z); acc[3] += __uint_as_float(raw[k].w);
+      acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y); acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
     } else {
-      const uint32_t w4[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
         acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
       }
     }
-  }
+  };
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < a.n_same) add(rs[k]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (k < a.n_low) add(rl[k]);
   if (a.relu) {
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[e] = fmaxf(acc[e], 0.f);
@@ -507,7 +519,7 @@ int fuse_sum_launch(const FuseArgs& a, int bf16, cudaStream_t s) {
   const int V = bf16 ? 8 : 4;
   const long long total = (long long)a.B * a.H * a.W * (a.C / V);
   if (total <= 0) return HRP_OK;
-  if (a.C % V || total > 0x7fffffffLL || a.n_same + a.n_low > 7) return fail(HRP_ERR_INVALID, "fuse_sum: unsupported shape (C=%d, %lld vectors)", a.C, total);
+  if (a.C % V || total > 0x7fffffffLL || a.n_same > 4 || a.n_low > 3) return fail(HRP_ERR_INVALID, "fuse_sum: unsupported shape (C=%d, %lld vectors)", a.C, total);
   const unsigned blocks = (unsigned)ceil_div64(total, 256);
   if (bf16) fuse_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(a);
   else fuse_sum_kernel<float><<<blocks, 256, 0, s>>>(a);
