@@ -382,61 +382,58 @@ int stem_pack_launch(const float* in_nchw, void* out, int B, int tf32, cudaStrea
 }
 
 // ---- element-wise layers: 4 channels per thread, NHWC ---------------------------------------------------------------------
-template <typename T> struct Vec4;
-template <> struct Vec4<float> {
-  static __device__ __forceinline__ float4 ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-};
-template <> struct Vec4<__nv_bfloat16> {
-  static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) {
-    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
-    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
-    return make_float4(fa.x, fa.y, fb.x, fb.y);
-  }
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 v) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 r;
-    r.x = *reinterpret_cast<uint32_t*>(&a);
-    r.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = r;
-  }
-};
-
-// nn.MaxPool2d(3, 2, 1), Resnet.py:22,61
+// nn.MaxPool2d(3, 2, 1), Resnet.py:22,61. 16 bytes of channels per thread (8 bf16 / 4 fp32), 32-bit index arithmetic, the
+// nine taps loaded before the first max (edge taps re-read the centre pixel: max is idempotent), bf16 maxima taken in
+// bf16 (exact).
 template <typename T>
-__global__ void maxpool3x3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int Hi, int Wi, int Ho,
-                                    int Wo, int C) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c4 = C >> 2;
-  const long long total = (long long)B * Ho * Wo * c4;
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int Hi, int Wi, int Ho, int Wo, int C) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  const uint32_t cv = (uint32_t)C / V;
+  const uint32_t total = (uint32_t)B * Ho * Wo * cv;
   if (i >= total) return;
-  const int c = (int)(i % c4) * 4;
-  long long r = i / c4;
-  const int ox = (int)(r % Wo); r /= Wo;
-  const int oy = (int)(r % Ho);
-  const int b = (int)(r / Ho);
-  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  const uint32_t c = (i % cv) * V;
+  uint32_t r = i / cv;
+  const int ox = (int)(r % (uint32_t)Wo); r /= (uint32_t)Wo;
+  const int oy = (int)(r % (uint32_t)Ho);
+  const uint32_t b = r / (uint32_t)Ho;
+  const T* img = in + (size_t)b * Hi * Wi * C + c;
+  uint4 v[9];
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
-    const int iy = oy * 2 - 1 + dy;
-    if (iy < 0 || iy >= Hi) continue;
+    int iy = oy * 2 - 1 + dy;
+    if (iy < 0 || iy >= Hi) iy = oy * 2;                    // the window's centre row is always inside
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
-      const int ix = ox * 2 - 1 + dx;
-      if (ix < 0 || ix >= Wi) continue;
-      const float4 v = Vec4<T>::ld(in + (((size_t)b * Hi + iy) * Wi + ix) * C + c);
-      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      int ix = ox * 2 - 1 + dx;
+      if (ix < 0 || ix >= Wi) ix = ox * 2;
+      v[dy * 3 + dx] = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)iy * Wi + ix) * C));
     }
   }
-  Vec4<T>::st(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c, m);
+  uint4 m = v[0];
+#pragma unroll
+  for (int k = 1; k < 9; ++k) {
+    if constexpr (sizeof(T) == 4) {
+      m.x = __float_as_uint(fmaxf(__uint_as_float(m.x), __uint_as_float(v[k].x))); m.y = __float_as_uint(fmaxf(__uint_as_float(m.y), __uint_as_float(v[k].y)));
+      m.z = __float_as_uint(fmaxf(__uint_as_float(m.z), __uint_as_float(v[k].z))); m.w = __float_as_uint(fmaxf(__uint_as_float(m.w), __uint_as_float(v[k].w)));
+    } else {
+      auto mx = [](uint32_t p, uint32_t q) {
+        const __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&p), *reinterpret_cast<const __nv_bfloat162*>(&q));
+        return *reinterpret_cast<const uint32_t*>(&h);
+      };
+      m.x = mx(m.x, v[k].x); m.y = mx(m.y, v[k].y); m.z = mx(m.z, v[k].z); m.w = mx(m.w, v[k].w);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = m;
 }
 
 int maxpool3x3s2_launch(const void* in, void* out, int B, int Hi, int Wi, int C, int bf16, cudaStream_t s) {
   const int Ho = (Hi + 2 - 3) / 2 + 1, Wo = (Wi + 2 - 3) / 2 + 1;
-  const long long total = (long long)B * Ho * Wo * (C / 4);
+  const int V = bf16 ? 8 : 4;
+  const long long total = (long long)B * Ho * Wo * (C / V);
   if (total <= 0) return HRP_OK;
+  if (C % V || total > 0x7fffffffLL) return fail(HRP_ERR_INVALID, "maxpool: unsupported shape (C=%d, %lld vectors)", C, total);
   const unsigned blocks = (unsigned)ceil_div64(total, 256);
   if (bf16) maxpool3x3s2_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), B, Hi, Wi, Ho, Wo, C);
   else maxpool3x3s2_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(in), static_cast<float*>(out), B, Hi, Wi, Ho, Wo, C);
