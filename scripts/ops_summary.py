@@ -6,9 +6,11 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 tot = sum(float(r['ms']) for r in rows)
 print("total ms %.3f over %d ops" % (tot, len(rows)))
 agg = collections.OrderedDict()
-KIND = {0: "stem", 1: "conv", 2: "maxpool", 3: "fuse", 4: "avgpool", 5: "depth", 6: "rank", 7: "dec", 8: "softargmax", 9: "fk", 10: "stem_pack", 11: "block"}
+KIND = {0: "stem", 1: "conv", 2: "maxpool", 3: "fuse", 4: "avgpool", 5: "depth", 6: "rank", 7: "dec", 8: "softargmax", 9: "fk", 10: "stem_pack", 11: "block", 12: "chain"}
 for r in rows:
-    if r['kind'] != '1':
+    if r['kind'] in ('11', '12'):
+        key = (KIND[int(r['kind'])], "%sx%s" % (r['Hi'], r['Hi']), r['Cin'] + "ch")
+    elif r['kind'] != '1':
         key = (KIND[int(r['kind'])],)
     else:
         key = ("conv", "%sx%s" % (r['Hi'], r['Hi']), r['Cin'] + "->" + r['Cout'], "k" + r['k'], "s" + r['stride'], "res" + r['res'], "nchw" + r['nchw'], "cls" + r['cls'])
