@@ -575,45 +575,66 @@ int depth_head_launch(const float* feat, const float* w, const float* bias, cons
   return HRP_OK;
 }
 
-__global__ void mlp_rank_kernel(float* __restrict__ h1, const float* __restrict__ xc1, int ld,
-                                const float* __restrict__ state, int state_stride, const float* __restrict__ W1b,
-                                int B, int N, int dof) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * N) return;
-  const int n = i % N, b = i / N;
-  float v = xc1[(size_t)b * ld + n];
-  const float* st = state + (size_t)b * state_stride;
-  const float* wr = W1b + (size_t)n * dof;
-  for (int j = 0; j < dof; ++j) v = fmaf(st[j], __ldg(wr + j), v);
-  h1[i] = v;
-}
-
-int mlp_rank_launch(float* h1, const float* xc1, int ld, const float* state, int state_stride, const float* W1b, int B,
-                    int N, int dof, cudaStream_t s) {
-  if (B <= 0) return HRP_OK;
-  mlp_rank_kernel<<<ceil_div(B * N, 256), 256, 0, s>>>(h1, xc1, ld, state, state_stride, W1b, B, N, dof);
-  HRP_CHECK_LAUNCH("mlp_rank_kernel");
-  return HRP_OK;
-}
-
-__global__ void mlp_dec_kernel(float* __restrict__ state_out, const float* __restrict__ state_in, int state_stride,
-                               const float* __restrict__ h2, const float* __restrict__ Wd, const float* __restrict__ bd,
-                               int B, int N, int dof) {
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (wid >= B * dof) return;
-  const int j = wid % dof, b = wid / dof;
-  float s = 0.f;
-  for (int n = lane; n < N; n += 32) s = fmaf(h2[(size_t)b * N + n], __ldg(Wd + (size_t)j * N + n), s);
+// The pose / rotation refinement loops (full_net.py:376-394, 430-444) have no nonlinearity (dropout is the identity in eval
+// mode), so n iterations of  s <- s + dec(fc2(fc1([xf, s])))  are the affine map  s_n = G_n xf + P_n s_0 + g_n  with
+// G_n, P_n, g_n composed once in fp64 at hrp_finalize_weights (network.cu, compose_heads). One launch evaluates every
+// iterate of both heads: row r = n * (dof + 6) + j of G is the j-th state component after n + 1 iterations.
+// s0_default [dof + 6]: the module's init_pose / init_rot buffers; ovr_pose / ovr_rot [B, dof] / [B, 6]: per-call
+// overrides (full_net.py:268-272), used when non-null and (flags == null or flags[k] != 0).
+__global__ void __launch_bounds__(256)
+heads_affine_kernel(const float* __restrict__ xf, const float* __restrict__ G, const float* __restrict__ P,
+                    const float* __restrict__ g, const float* __restrict__ s0_default, const float* ovr_pose,
+                    const float* ovr_rot, const int* flags, float* __restrict__ iters, float* __restrict__ pose,
+                    float* __restrict__ rot, int F, int dof, int n_iter) {
+  extern __shared__ float hx[];                       // xf row, then the two initial states
+  const int b = blockIdx.x, R1 = dof + 6, R = n_iter * R1;
+  for (int c = threadIdx.x * 4; c < F; c += 256 * 4)
+    *reinterpret_cast<float4*>(hx + c) = __ldg(reinterpret_cast<const float4*>(xf + (size_t)b * F + c));
+  float* s0 = hx + F;
+  if (threadIdx.x < R1) {
+    const int j = threadIdx.x;
+    const bool is_rot = j >= dof;
+    const float* o = is_rot ? ovr_rot : ovr_pose;
+    const bool use = o != nullptr && (flags == nullptr || flags[is_rot ? 1 : 0] != 0);
+    s0[j] = use ? o[(size_t)b * (is_rot ? 6 : dof) + (is_rot ? j - dof : j)] : s0_default[j];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pblk = dof * dof + 36;
+  for (int r = warp; r < R; r += 8) {
+    const float4* gr = reinterpret_cast<const float4*>(G + (size_t)r * F);
+    float acc = 0.f;
+    for (int c = lane; c < F / 4; c += 32) {
+      const float4 w = __ldg(gr + c);
+      const float4 x = *reinterpret_cast<const float4*>(hx + 4 * c);
+      acc = fmaf(w.x, x.x, acc); acc = fmaf(w.y, x.y, acc); acc = fmaf(w.z, x.z, acc); acc = fmaf(w.w, x.w, acc);
+    }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (lane == 0) state_out[(size_t)b * dof + j] = (s + bd[j]) + state_in[(size_t)b * state_stride + j];   // full_net.py:394
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      const int n = r / R1, j = r - n * R1;
+      const bool is_rot = j >= dof;
+      const int w = is_rot ? 6 : dof, jj = is_rot ? j - dof : j;
+      const float* pr = P + (size_t)n * pblk + (is_rot ? dof * dof : 0) + jj * w;
+      const float* st = s0 + (is_rot ? dof : 0);
+      float v = acc + g[r];
+      for (int q = 0; q < w; ++q) v = fmaf(pr[q], st[q], v);
+      iters[(size_t)b * R + r] = v;
+      if (n == n_iter - 1) {
+        if (is_rot) rot[(size_t)b * 6 + jj] = v; else pose[(size_t)b * dof + jj] = v;
+      }
+    }
+  }
 }
 
-int mlp_dec_launch(float* state_out, const float* state_in, int state_stride, const float* h2, const float* Wd,
-                   const float* bd, int B, int N, int dof, cudaStream_t s) {
+int heads_affine_launch(const float* xf, const float* G, const float* P, const float* g, const float* s0_default,
+                        const float* ovr_pose, const float* ovr_rot, const int* flags, float* iters, float* pose, float* rot,
+                        int B, int F, int dof, int n_iter, cudaStream_t s) {
   if (B <= 0) return HRP_OK;
-  mlp_dec_kernel<<<ceil_div(B * dof * 32, 256), 256, 0, s>>>(state_out, state_in, state_stride, h2, Wd, bd, B, N, dof);
-  HRP_CHECK_LAUNCH("mlp_dec_kernel");
+  if (F % 4) return fail(HRP_ERR_INVALID, "heads_affine: feature width %d is not a multiple of 4", F);
+  heads_affine_kernel<<<B, 256, (size_t)(F + dof + 6) * sizeof(float), s>>>(xf, G, P, g, s0_default, ovr_pose, ovr_rot, flags, iters, pose,
+                                                                            rot, F, dof, n_iter);
+  HRP_CHECK_LAUNCH("heads_affine_kernel");
   return HRP_OK;
 }
 

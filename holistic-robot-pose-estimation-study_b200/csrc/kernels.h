@@ -117,12 +117,12 @@ int avgpool_launch(const void* in, float* out, int B, int HW, int C, int bf16, c
 // depth[b] = (dot(feat[b], w) + bias) * k_value[b] / 1000          full_net.py:312-336
 int depth_head_launch(const float* feat, const float* w, const float* bias, const float* k_value, float* depth, int B,
                       int C, cudaStream_t s);
-// h1[b,n] = xc1[b*ld + n] + sum_j state[b*state_stride + j] * W1b[n*dof + j]     (the state columns of fc_*_1)
-int mlp_rank_launch(float* h1, const float* xc1, int ld, const float* state, int state_stride, const float* W1b, int B,
-                    int N, int dof, cudaStream_t s);
-// state_out[b,j] = state_in[b*state_stride + j] + bd[j] + sum_n h2[b,n] * Wd[j*N + n]
-int mlp_dec_launch(float* state_out, const float* state_in, int state_stride, const float* h2, const float* Wd,
-                   const float* bd, int B, int N, int dof, cudaStream_t s);
+// Every iterate of both refinement heads as one affine map per iterate (conv_f32.cu, heads_affine_kernel):
+// iters [B, n_iter, dof+6]; pose [B,dof] / rot [B,6] receive the last iterate. G [n_iter*(dof+6), F], P per iterate
+// {dof x dof, 6 x 6}, g [n_iter*(dof+6)], s0_default [dof+6]; ovr_* optional per-frame initial states.
+int heads_affine_launch(const float* xf, const float* G, const float* P, const float* g, const float* s0_default,
+                        const float* ovr_pose, const float* ovr_rot, const int* flags, float* iters, float* pose, float* rot,
+                        int B, int F, int dof, int n_iter, cudaStream_t s);
 
 // ---- integral layer / kinematics (softargmax.cu, fk_project.cu) ----------------------------------------------------------
 size_t softargmax_workspace(int B, int K, int D, int H, int W);

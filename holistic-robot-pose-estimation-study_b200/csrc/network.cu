@@ -23,9 +23,9 @@ struct hrp_fk;  // fk_project.cu
 
 namespace hrp {
 
-enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_RANK, OP_DEC, OP_SOFTARGMAX, OP_FK, OP_STEM_PACK, OP_BLOCK, OP_CHAIN };
+enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_HEADS, OP_RESERVED, OP_SOFTARGMAX, OP_FK, OP_STEM_PACK, OP_BLOCK, OP_CHAIN };
 enum { CLS_CONV_TC = 0, CLS_CONV_F32 = 1, CLS_STEM = 2, CLS_ELEM = 3, CLS_HEADS = 4, CLS_SOFTARGMAX = 5, CLS_FK = 6 };
-enum TKind { T_WS = 0, T_XREG, T_XROOT, T_KVAL, T_KMAT, T_FIELD, T_CONST };
+enum TKind { T_WS = 0, T_XREG, T_XROOT, T_KVAL, T_KMAT, T_FIELD, T_CONST, T_INITP, T_INITR, T_FLAGS };
 
 struct TensorInfo {
   int64_t elems = 0;     // per frame
@@ -74,10 +74,15 @@ struct Plan {
   size_t ws_bytes = 0;
   char* ws = nullptr;
   std::vector<size_t> off;
-  size_t io_xreg = 0, io_xroot = 0, io_kv = 0, io_K = 0, io_out = 0, sa_ws = 0, sa_ws_bytes = 0;
-  cudaGraphExec_t exec[2] = {nullptr, nullptr};
-  cudaEvent_t done = nullptr;      // recorded after the last forward that used this plan (graph path)
+  // static staging the graph reads / writes (the images are NOT staged: the ops that read them run ahead of the graph
+  // on the caller's pointers, see run_ops' `part`)
+  size_t io_kv = 0, io_K = 0, io_out = 0, io_initp = 0, io_initr = 0, io_flags = 0, sa_ws = 0, sa_ws_bytes = 0;
+  cudaGraphExec_t exec = nullptr;
+  cudaEvent_t done = nullptr;      // recorded after the last forward that used this plan
   bool used = false;
+  int flags_state = -1;            // what io_flags currently holds (bit 0: init_pose override, bit 1: init_rot override)
+  int64_t launches = 0;            // kernels of one forward through this plan (pre-graph ops + graph nodes)
+  uint64_t stamp = 0;              // last use, for the least-recently-used trim of the plan cache
 };
 
 }  // namespace hrp
@@ -110,8 +115,11 @@ struct hrp_handle {
   std::vector<TensorInfo> tensors;
   std::vector<OpDesc> ops;
   std::map<int, std::unique_ptr<Plan>> plans;      // key = batch * 8 + slot
-  int slots = 3;                   // graph path: plans (workspace + graph) per batch size, used round-robin so that
-  int next_slot = 0;               //   consecutive forwards enqueued on DIFFERENT streams can overlap
+  int slots = 3;                   // graph path: up to this many plans (workspace + graph) per batch size; a forward that
+  int next_slot = 0;               //   arrives on a DIFFERENT stream than its predecessor takes the next one (so the two
+  cudaStream_t last_stream = nullptr; int last_B = 0, last_slot_used = 0;   //   overlap); one stream only ever allocates one
+  int max_batches = 4;             // distinct batch sizes kept in the plan cache (least recently used is dropped)
+  uint64_t clock = 0;
   std::map<int, int> last_slot;    // batch -> slot of the most recent forward (hrp_debug_tensor)
   std::unordered_map<std::string, int> debug;
   cudaStream_t capture_stream = nullptr;
@@ -126,11 +134,24 @@ struct hrp_handle {
   int lane_pct[hrp::kMaxLanes] = {};               // share of the CTA slots a conv of this lane may occupy (graph mode)
   bool lane_pct_auto = true;                       // no explicit setting: small batches (latency-bound use) get twice the share
   int64_t last_launches = 0;
-  int t_xreg = -1, t_xroot = -1, t_kval = -1, t_kmat = -1, t_field[HRP_NUM_FIELDS];
+  int t_xreg = -1, t_xroot = -1, t_kval = -1, t_kmat = -1, t_initp = -1, t_initr = -1, t_flags = -1, t_field[HRP_NUM_FIELDS];
   int field_width[HRP_NUM_FIELDS];
 };
 
 namespace {
+
+struct DeviceGuard {      // the entry points run on the handle's device and leave the caller's current device as it was
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev); else if (err == cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define HRP_ON_DEVICE(h)                                                                                   \
+  DeviceGuard _guard((h)->device);                                                                         \
+  if (_guard.err != cudaSuccess) return fail(HRP_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (h)->device, cudaGetErrorString(_guard.err))
 
 // development aid (HRP_TIMELINE=<csv path>): %globaltimer stamps around every op of the captured graph
 __global__ void stamp_kernel(unsigned long long* slot) {
@@ -625,93 +646,85 @@ struct GraphBuilder {
     return y;
   }
 
-  // nn.Linear as a 1x1 conv over a [1,1,C] map (fp32 family)
-  Tn linear_packed(const Tn& x, const std::vector<float>& w_oi, const std::vector<float>& bias, int Cout) {
-    std::vector<float> wp((size_t)x.C * Cout), bp(Cout);
-    pack_conv_f32(w_oi.data(), bias.data(), nullptr, nullptr, nullptr, nullptr, Cout, x.C, 1, 1, wp.data(), bp.data());
-    Layer L; L.Cout = Cout; L.Cin = x.C; L.KH = L.KW = 1; L.w = upload(wp); L.bias = upload(bp);
-    h->layers.push_back(L);
-    OpDesc op{};
-    op.kind = OP_CONV; op.cls = CLS_HEADS; op.layer = (int)h->layers.size() - 1;
-    op.Cin = x.C; op.Cout = Cout; op.ld = Cout;
-    Tn y = new_tensor(1, 1, Cout, 4);
-    op.in = x.id; op.out = y.id; op.flops = 2.0 * x.C * Cout;
-    push(op);
-    return y;
-  }
-
+  // The refinement loops are linear (no activation; dropout = identity in eval, full_net.py:376-394, 430-444):
+  //   s <- s + Wd (W2 (W1x xf + W1s s + b1) + b2) + bd  =  (I + M) s + A xf + c,
+  //   A = Wd W2 W1x, M = Wd W2 W1s, c = Wd (W2 b1 + b2) + bd,
+  // so iterate n is  s_n = G_n xf + P_n s_0 + g_n  with  P_n = (I+M)^n, S_n = sum_{j<n} (I+M)^j, G_n = S_n A, g_n = S_n c.
+  // Composed here in fp64, evaluated by ONE launch for every iterate of both heads (heads_affine_kernel).
   void heads(const Tn& xf) {
-    const int dof = h->dof, F = 2048, Hd = 1024;
+    const int dof = h->dof, F = 2048, Hd = 1024, nit = h->cfg.n_iter, R1 = dof + 6;
     const char* fc1[2] = {"fc_pose_1", "fc_rot_1"};
     const char* fc2[2] = {"fc_pose_2", "fc_rot_2"};
     const char* dec[2] = {"decpose", "decrot"};
     const char* init[2] = {"init_pose", "init_rot"};
-    const int sd[2] = {dof, 6};
-    const int field[2] = {HRP_F_POSE, HRP_F_ROT};
-    // feature part of both first layers in ONE GEMM (iteration-invariant): xc1 = xf . W1[:, :2048]^T + b1
-    std::vector<float> w1((size_t)2 * Hd * F), b1(2 * Hd);
-    std::vector<float> w1b[2];
+    const int sd[2] = {dof, 6}, row0[2] = {0, dof};
+    std::vector<float> G((size_t)nit * R1 * F), P((size_t)nit * (dof * dof + 36)), gv((size_t)nit * R1), s0(R1);
     for (int k = 0; k < 2; ++k) {
-      const float* w = W(std::string(fc1[k]) + ".weight");
-      const float* b = W(std::string(fc1[k]) + ".bias");
-      if (status != HRP_OK) return;
-      w1b[k].resize((size_t)Hd * sd[k]);
-      for (int n = 0; n < Hd; ++n) {
-        std::memcpy(&w1[((size_t)k * Hd + n) * F], w + (size_t)n * (F + sd[k]), F * sizeof(float));
-        std::memcpy(&w1b[k][(size_t)n * sd[k]], w + (size_t)n * (F + sd[k]) + F, sd[k] * sizeof(float));   // state columns are LAST (cat([xf, state]))
-        b1[k * Hd + n] = b[n];
-      }
-    }
-    Tn xc1 = linear_packed(xf, w1, b1, 2 * Hd);
-    int state[2];
-    for (int k = 0; k < 2; ++k) {
-      const float* s0 = W(init[k]);
-      if (status != HRP_OK) return;
-      state[k] = constant(upload(std::vector<float>(s0, s0 + sd[k])));
-    }
-    const float* w2h[2]; const float* b2h[2]; float* dw[2]; float* db[2]; float* dw1b[2];
-    for (int k = 0; k < 2; ++k) {
-      w2h[k] = W(std::string(fc2[k]) + ".weight"); b2h[k] = W(std::string(fc2[k]) + ".bias");
+      const int n = sd[k], in1 = F + n;
+      const float* w1 = W(std::string(fc1[k]) + ".weight"); const float* b1 = W(std::string(fc1[k]) + ".bias");
+      const float* w2 = W(std::string(fc2[k]) + ".weight"); const float* b2 = W(std::string(fc2[k]) + ".bias");
       const float* wd = W(std::string(dec[k]) + ".weight"); const float* bd = W(std::string(dec[k]) + ".bias");
+      const float* i0 = W(init[k]);
       if (status != HRP_OK) return;
-      dw[k] = upload(std::vector<float>(wd, wd + (size_t)sd[k] * Hd));
-      db[k] = upload(std::vector<float>(bd, bd + sd[k]));
-      dw1b[k] = upload(w1b[k]);
-    }
-    // fc2 layers are reused by every iteration: pack once
-    int l2[2];
-    for (int k = 0; k < 2; ++k) {
-      std::vector<float> wp((size_t)Hd * Hd), bp(Hd);
-      pack_conv_f32(w2h[k], b2h[k], nullptr, nullptr, nullptr, nullptr, Hd, Hd, 1, 1, wp.data(), bp.data());
-      Layer L; L.Cout = Hd; L.Cin = Hd; L.KH = L.KW = 1; L.w = upload(wp); L.bias = upload(bp);
-      h->layers.push_back(L);
-      l2[k] = (int)h->layers.size() - 1;
-    }
-    // the pose and the rotation stacks only meet again in FK (full_net.py:214-238): each iterates on its own lane
-    const int lane_of[2] = {cur_lane, h->n_lanes};
-    h->n_lanes += 1;
-    for (int it = 0; it < h->cfg.n_iter; ++it)
-      for (int k = 0; k < 2; ++k) {
-        cur_lane = lane_of[k];
-        Tn h1 = new_tensor(1, 1, Hd, 4);
-        OpDesc r{};
-        r.kind = OP_RANK; r.cls = CLS_HEADS; r.in = xc1.id; r.in2 = state[k]; r.out = h1.id; r.ld = 2 * Hd; r.coff = k * Hd;
-        r.state_stride = (it == 0) ? 0 : sd[k]; r.dof = sd[k]; r.N = Hd; r.wptr = dw1b[k];
-        r.flops = 2.0 * Hd * sd[k];
-        push(r);
-        Tn h2 = new_tensor(1, 1, Hd, 4);
-        OpDesc c{};
-        c.kind = OP_CONV; c.cls = CLS_HEADS; c.layer = l2[k]; c.in = h1.id; c.out = h2.id; c.Cin = Hd; c.Cout = Hd; c.ld = Hd;
-        c.flops = 2.0 * Hd * Hd;
-        push(c);
-        OpDesc d{};
-        d.kind = OP_DEC; d.cls = CLS_HEADS; d.in = h2.id; d.in2 = state[k]; d.out = h->t_field[field[k]];
-        d.state_stride = r.state_stride; d.dof = sd[k]; d.N = Hd; d.wptr = dw[k]; d.bptr = db[k];
-        d.flops = 2.0 * Hd * sd[k];
-        push(d);
-        state[k] = h->t_field[field[k]];
+      for (int j = 0; j < n; ++j) s0[row0[k] + j] = i0[j];
+      std::vector<double> T((size_t)n * Hd, 0.0);                       // Wd W2
+      for (int j = 0; j < n; ++j)
+        for (int m = 0; m < Hd; ++m) {
+          const double d = wd[(size_t)j * Hd + m];
+          const float* r2 = w2 + (size_t)m * Hd;
+          double* t = &T[(size_t)j * Hd];
+          for (int q = 0; q < Hd; ++q) t[q] += d * (double)r2[q];
+        }
+      std::vector<double> A((size_t)n * F, 0.0), M((size_t)n * n, 0.0), c(n, 0.0);
+      for (int j = 0; j < n; ++j) {
+        double cj = bd[j];
+        for (int m = 0; m < Hd; ++m) {
+          const double t = T[(size_t)j * Hd + m];
+          const float* r1 = w1 + (size_t)m * in1;                       // state columns are LAST (cat([xf, state]))
+          double* a = &A[(size_t)j * F];
+          for (int q = 0; q < F; ++q) a[q] += t * (double)r1[q];
+          for (int q = 0; q < n; ++q) M[(size_t)j * n + q] += t * (double)r1[F + q];
+          cj += t * (double)b1[m] + (double)wd[(size_t)j * Hd + m] * (double)b2[m];
+        }
+        c[j] = cj;
       }
-    cur_lane = lane_of[0];
+      std::vector<double> E(M), Pn((size_t)n * n, 0.0), Sn((size_t)n * n, 0.0), tmp((size_t)n * n);
+      for (int j = 0; j < n; ++j) { E[(size_t)j * n + j] += 1.0; Pn[(size_t)j * n + j] = 1.0; }
+      for (int it = 0; it < nit; ++it) {
+        for (size_t q = 0; q < Sn.size(); ++q) Sn[q] += Pn[q];          // S_{it+1} = S_it + P_it
+        for (int j = 0; j < n; ++j)                                     // P_{it+1} = E P_it
+          for (int q = 0; q < n; ++q) {
+            double v = 0.0;
+            for (int m = 0; m < n; ++m) v += E[(size_t)j * n + m] * Pn[(size_t)m * n + q];
+            tmp[(size_t)j * n + q] = v;
+          }
+        Pn = tmp;
+        for (int j = 0; j < n; ++j) {
+          const size_t r = (size_t)it * R1 + row0[k] + j;
+          double gj = 0.0;
+          std::vector<double> row(F, 0.0);
+          for (int m = 0; m < n; ++m) {
+            const double sv = Sn[(size_t)j * n + m];
+            gj += sv * c[m];
+            const double* a = &A[(size_t)m * F];
+            for (int q = 0; q < F; ++q) row[q] += sv * a[q];
+          }
+          for (int q = 0; q < F; ++q) G[r * F + q] = (float)row[q];
+          gv[r] = (float)gj;
+          float* pr = &P[(size_t)it * (dof * dof + 36) + (k ? dof * dof : 0) + (size_t)j * n];
+          for (int q = 0; q < n; ++q) pr[q] = (float)Pn[(size_t)j * n + q];
+        }
+      }
+    }
+    Tn iters = new_tensor(1, 1, nit * R1, 4, "head_iters");
+    h->tensors[iters.id].keep = true; h->debug["head_iters"] = iters.id;
+    OpDesc op{};
+    op.kind = OP_HEADS; op.cls = CLS_HEADS; op.in = xf.id; op.in2 = h->t_initp; op.in3 = h->t_initr; op.in4 = h->t_flags;
+    op.out = h->t_field[HRP_F_POSE]; op.out2 = h->t_field[HRP_F_ROT]; op.out3 = iters.id;
+    op.same[0] = constant(upload(G)); op.same[1] = constant(upload(P)); op.same[2] = constant(upload(gv)); op.same[3] = constant(upload(s0));
+    op.n_same = 4; op.Cin = F; op.dof = dof; op.N = nit;
+    op.flops = 2.0 * nit * R1 * F;
+    push(op);
   }
 
   int build() {
@@ -728,6 +741,9 @@ struct GraphBuilder {
     h->t_xroot = special(T_XROOT, 3LL * 256 * 256);
     h->t_kval = special(T_KVAL, 1);
     h->t_kmat = special(T_KMAT, 9);
+    h->t_initp = special(T_INITP, dof);
+    h->t_initr = special(T_INITR, 6);
+    h->t_flags = special(T_FLAGS, 0);
     for (int f = 0; f < HRP_NUM_FIELDS; ++f) { h->field_width[f] = fw[f]; h->t_field[f] = special(T_FIELD, fw[f], f); }
 
     // DepthNet: lanes 0-3 (one per HRNet branch); its head ends on lane 3
@@ -875,19 +891,46 @@ int64_t record_floats(const hrp_handle* h, int B, int64_t* offs) {
   return o;
 }
 
+void destroy_plan(Plan* p) {
+  if (p->used && p->done) cudaEventSynchronize(p->done);
+  if (p->exec) cudaGraphExecDestroy(p->exec);
+  if (p->done) cudaEventDestroy(p->done);
+  if (p->ws) cudaFree(p->ws);
+}
+
+// the plan cache keeps at most h->max_batches distinct batch sizes: a caller with ragged batches (detector-driven crops,
+// the last batch of an evaluation) must not grow device memory by one workspace per size it ever used
+void trim_plans(hrp_handle* h, int keep_B) {
+  for (;;) {
+    std::map<int, uint64_t> newest;                      // batch -> most recent use over its slots
+    for (auto& kv : h->plans) { auto& v = newest[kv.first / 8]; v = std::max(v, kv.second->stamp); }
+    if ((int)newest.size() < h->max_batches || (newest.size() == 1 && newest.count(keep_B))) return;
+    int victim = -1; uint64_t oldest = ~0ull;
+    for (auto& kv : newest) if (kv.first != keep_B && kv.second < oldest) { oldest = kv.second; victim = kv.first; }
+    if (victim < 0) return;
+    for (auto it = h->plans.begin(); it != h->plans.end();)
+      if (it->first / 8 == victim) { destroy_plan(it->second.get()); it = h->plans.erase(it); } else ++it;
+    h->last_slot.erase(victim);
+  }
+}
+
 int make_plan(hrp_handle* h, int B, Plan** out, int slot = 0) {
   auto it = h->plans.find(B * 8 + slot);
-  if (it != h->plans.end()) { *out = it->second.get(); return HRP_OK; }
+  if (it != h->plans.end()) { it->second->stamp = ++h->clock; *out = it->second.get(); return HRP_OK; }
+  bool known = false;
+  for (auto& kv : h->plans) known |= kv.first / 8 == B;
+  if (!known) trim_plans(h, B);
   std::unique_ptr<Plan> p(new Plan());
   p->B = B;
   p->off.assign(h->tensors.size(), 0);
   FreeList fl;
   const size_t A = 256;
   // static I/O staging (graph replays always read/write these)
-  p->io_xreg = fl.alloc(align_up((size_t)B * 3 * 256 * 256 * 4, A));
-  p->io_xroot = fl.alloc(align_up((size_t)B * 3 * 256 * 256 * 4, A));
   p->io_kv = fl.alloc(align_up((size_t)B * 4, A));
   p->io_K = fl.alloc(align_up((size_t)B * 9 * 4, A));
+  p->io_initp = fl.alloc(align_up((size_t)B * h->dof * 4, A));
+  p->io_initr = fl.alloc(align_up((size_t)B * 6 * 4, A));
+  p->io_flags = fl.alloc(A);
   p->io_out = fl.alloc(align_up((size_t)record_floats(h, B, nullptr) * 4, A));
   p->sa_ws_bytes = std::max(softargmax_workspace(B, h->nkpt, 64, 64, 64), (size_t)B * h->nkpt * (64 * 64 / 128) * 5 * sizeof(float));
   p->sa_ws = fl.alloc(align_up(p->sa_ws_bytes, A));
@@ -915,7 +958,6 @@ int make_plan(hrp_handle* h, int B, Plan** out, int slot = 0) {
   for (size_t t = 0; t < h->tensors.size(); ++t)
     if (h->tensors[t].kind == T_WS) p->off[t] += lane_base[h->tensors[t].home_lane];
   p->ws_bytes = fl.top;
-  HRP_CUDA(cudaSetDevice(h->device));
   void* ws = nullptr;
   if (cudaMalloc(&ws, p->ws_bytes) != cudaSuccess) {
     cudaGetLastError();
@@ -923,6 +965,9 @@ int make_plan(hrp_handle* h, int B, Plan** out, int slot = 0) {
   }
   p->ws = static_cast<char*>(ws);
   HRP_CUDA(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
+  HRP_CUDA(cudaMemset(p->ws + p->io_flags, 0, 8));
+  p->flags_state = 0;
+  p->stamp = ++h->clock;
   *out = p.get();
   h->plans[B * 8 + slot] = std::move(p);
   return HRP_OK;
@@ -931,7 +976,13 @@ int make_plan(hrp_handle* h, int B, Plan** out, int slot = 0) {
 struct IoPtrs {
   const float *x_reg, *x_root, *k_value, *Kmat;
   float* out;
+  const float *init_pose = nullptr, *init_rot = nullptr;   // optional per-frame initial states (full_net.py:268-272)
+  const int* flags = nullptr;                               // graph path: which of the two staged overrides are live
 };
+
+// which ops run_ops enqueues: the ops that read the caller's images (stem / stem_pack, always the first of their lane)
+// run AHEAD of the graph on the caller's pointers, so the graph holds no image staging and no 50 MB copy precedes it
+enum Part { PART_ALL = 0, PART_PRE = 1, PART_GRAPH = 2 };
 
 struct Profile {
   float* ms; int64_t* launches; double* flops;
@@ -942,7 +993,8 @@ struct Profile {
 // `lanes`: only while capturing the graph. Ops are enqueued on their lane's stream (lane 0 = `st`), cross-lane producers
 // signal through events, and every lane joins `st` at the end, so the instantiated graph carries the true dependency DAG
 // of the network instead of a serial chain. Without it (eager / profiling) everything runs in list order on `st`.
-int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* prof, bool lanes = false) {
+int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* prof, bool lanes = false, Part part = PART_ALL,
+            cudaEvent_t root_done = nullptr, int64_t* launched = nullptr) {
   const int B = p->B;
   int64_t offs[HRP_NUM_FIELDS + 1];
   record_floats(h, B, offs);
@@ -957,9 +1009,13 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
       case T_KMAT: return const_cast<float*>(io.Kmat);
       case T_FIELD: return io.out + offs[t.field];
       case T_CONST: return const_cast<void*>(t.cptr);
+      case T_INITP: return const_cast<float*>(io.init_pose);
+      case T_INITR: return const_cast<float*>(io.init_rot);
+      case T_FLAGS: return const_cast<int*>(io.flags);
     }
     return nullptr;
   };
+  auto reads_image = [&](const OpDesc& o) { return o.in == h->t_xreg || o.in == h->t_xroot; };
   int64_t launches = 0;
   const int bf16 = h->cfg.precision == HRP_PREC_BF16 ? 1 : 0, tf32 = h->cfg.precision == HRP_PREC_TF32 ? 1 : 0;
   std::vector<cudaEvent_t> op_event(h->ops.size(), nullptr);
@@ -978,9 +1034,10 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
   }
   for (size_t oi = 0; oi < h->ops.size(); ++oi) {
     const OpDesc& o = h->ops[oi];
+    if (part != PART_ALL && reads_image(o) != (part == PART_PRE)) continue;
     cudaStream_t st_op = stream_of(o.lane);
     if (lanes)
-      for (int j : h->waits[oi]) HRP_CUDA(cudaStreamWaitEvent(st_op, op_event[j], 0));
+      for (int j : h->waits[oi]) if (op_event[j]) HRP_CUDA(cudaStreamWaitEvent(st_op, op_event[j], 0));
     if (prof) HRP_CUDA(cudaEventRecord(prof->e0, st));
     if (lanes && h->timeline) stamp_kernel<<<1, 1, 0, st_op>>>(h->timeline + 2 * oi);
     int n_launch = 1;
@@ -1066,11 +1123,13 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
       case OP_DEPTH:
         HRP_TRY(depth_head_launch(static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, static_cast<const float*>(ptr(o.in2)), static_cast<float*>(ptr(o.out)), B, o.Cin, st_op));
         break;
-      case OP_RANK:
-        HRP_TRY(mlp_rank_launch(static_cast<float*>(ptr(o.out)), static_cast<const float*>(ptr(o.in)) + o.coff, o.ld, static_cast<const float*>(ptr(o.in2)), o.state_stride, o.wptr, B, o.N, o.dof, st_op));
+      case OP_HEADS:
+        HRP_TRY(heads_affine_launch(static_cast<const float*>(ptr(o.in)), static_cast<const float*>(ptr(o.same[0])), static_cast<const float*>(ptr(o.same[1])),
+                                    static_cast<const float*>(ptr(o.same[2])), static_cast<const float*>(ptr(o.same[3])), static_cast<const float*>(ptr(o.in2)),
+                                    static_cast<const float*>(ptr(o.in3)), static_cast<const int*>(ptr(o.in4)), static_cast<float*>(ptr(o.out3)),
+                                    static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)), B, o.Cin, o.dof, o.N, st_op));
         break;
-      case OP_DEC:
-        HRP_TRY(mlp_dec_launch(static_cast<float*>(ptr(o.out)), static_cast<const float*>(ptr(o.in2)), o.state_stride, static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, B, o.N, o.dof, st_op));
+      case OP_RESERVED:
         break;
       case OP_SOFTARGMAX: {
         if (h->sa_fused) {       // the heatmap conv already wrote 32 partial states per (frame, keypoint)
@@ -1093,6 +1152,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         break;
     }
     launches += n_launch;
+    if (root_done && o.kind == OP_DEPTH) HRP_CUDA(cudaEventRecord(root_done, st));   // DepthNet done (full_net.py:337-340)
     if (lanes && h->timeline) stamp_kernel<<<1, 1, 0, st_op>>>(h->timeline + 2 * oi + 1);
     if (lanes && h->signals[oi]) {
       op_event[oi] = new_event();
@@ -1117,7 +1177,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
       HRP_CUDA(cudaEventRecord(e, h->lane_stream[l]));
       HRP_CUDA(cudaStreamWaitEvent(st, e, 0));
     }
-  h->last_launches = launches;
+  if (launched) *launched = launches; else h->last_launches = launches;
   return HRP_OK;
 }
 
@@ -1172,11 +1232,7 @@ extern "C" void hrp_destroy(hrp_handle* h) {
     }
     cudaFree(h->timeline);
   }
-  for (auto& kv : h->plans) {
-    for (int i = 0; i < 2; ++i) if (kv.second->exec[i]) cudaGraphExecDestroy(kv.second->exec[i]);
-    if (kv.second->done) cudaEventDestroy(kv.second->done);
-    if (kv.second->ws) cudaFree(kv.second->ws);
-  }
+  for (auto& kv : h->plans) destroy_plan(kv.second.get());
   for (void* p : h->dev_allocs) cudaFree(p);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   for (int l = 1; l < kMaxLanes; ++l) if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
@@ -1223,7 +1279,7 @@ extern "C" int hrp_finalize_weights(hrp_handle* h) {
   if (h->finalized) return fail(HRP_ERR_STATE, "hrp_finalize_weights: already finalized");
   for (const WeightSpec& sp : h->specs)
     if (!sp.optional && !h->host.count(sp.name)) return fail(HRP_ERR_WEIGHT, "hrp_finalize_weights: tensor '%s' was never set", sp.name.c_str());
-  HRP_CUDA(cudaSetDevice(h->device));
+  HRP_ON_DEVICE(h);
   GraphBuilder gb{h};
   const int st = gb.build();
   if (st != HRP_OK) return st;
@@ -1258,6 +1314,8 @@ extern "C" int hrp_output_offsets(const hrp_handle* h, int B, int64_t* offsets) 
 
 extern "C" size_t hrp_workspace_bytes(hrp_handle* h, int B) {
   if (!h || !h->finalized || B <= 0) return 0;
+  DeviceGuard guard(h->device);
+  if (guard.err != cudaSuccess) return 0;
   Plan* p = nullptr;
   if (make_plan(h, B, &p) != HRP_OK) return 0;
   return p->ws_bytes;
@@ -1277,6 +1335,11 @@ extern "C" int hrp_set_option(hrp_handle* h, const char* name, int64_t value) {
     for (int l = 0; l < kMaxLanes; ++l) h->lane_pct[l] = (int)value;                                               // forwards; 50 gives the
     return HRP_OK;                                                                                                 // lowest single-call latency)
   }
+  if (std::strcmp(name, "max_cached_batches") == 0) {   // distinct batch sizes whose plans stay cached (default 4)
+    if (value < 1 || value > 64) return fail(HRP_ERR_INVALID, "hrp_set_option: max_cached_batches must be 1..64");
+    h->max_batches = (int)value;
+    return HRP_OK;
+  }
   if (std::strcmp(name, "lanes") == 0) {         // multi-stream graph (default 1); takes effect for graphs not yet captured
     h->use_lanes = value != 0;
     return HRP_OK;
@@ -1286,52 +1349,111 @@ extern "C" int hrp_set_option(hrp_handle* h, const char* name, int64_t value) {
 
 extern "C" int64_t hrp_launch_count(const hrp_handle* h) { return h ? h->last_launches : 0; }
 
-extern "C" int hrp_forward(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
-                           int B, float* out, void* stream) {
+namespace {
+int forward_impl(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
+                 const float* init_pose, const float* init_rot, int B, float* out, cudaStream_t st, float* ms3) {
   HRP_TRY(check_forward_args(h, x_reg, x_root, k_value, Kmat, B, out));
-  HRP_CUDA(cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)stream;
+  HRP_ON_DEVICE(h);
   Plan* p = nullptr;
-  const int slot = h->use_graph ? h->next_slot : 0;
-  if (h->use_graph) h->next_slot = (h->next_slot + 1) % h->slots;
+  const bool graph = h->use_graph && ms3 == nullptr;
+  int slot = 0;
+  if (graph) {
+    // a forward on the same stream as its predecessor cannot overlap it anyway: it reuses that plan, so a caller with one
+    // stream only ever pays for one workspace; a forward on another stream takes the next plan
+    if (h->last_B == B && st == h->last_stream) slot = h->last_slot_used;
+    else { slot = h->next_slot; h->next_slot = (h->next_slot + 1) % h->slots; }
+    h->last_stream = st; h->last_B = B; h->last_slot_used = slot;
+  }
   HRP_TRY(make_plan(h, B, &p, slot));
   h->last_slot[B] = slot;
-  if (!h->use_graph) {
-    if (p->used) HRP_CUDA(cudaStreamWaitEvent(st, p->done, 0));
-    const int rs = run_ops(h, p, IoPtrs{x_reg, x_root, k_value, Kmat, out}, st, nullptr);
+  // whatever stream used this plan last must be done with its workspace before this forward touches it
+  if (p->used) HRP_CUDA(cudaStreamWaitEvent(st, p->done, 0));
+  if (!graph) {
+    IoPtrs io{x_reg, x_root, k_value, Kmat, out, init_pose, init_rot, nullptr};
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    if (ms3) {
+      HRP_CUDA(cudaEventCreate(&e0)); HRP_CUDA(cudaEventCreate(&e1)); HRP_CUDA(cudaEventCreate(&e2));
+      HRP_CUDA(cudaEventRecord(e0, st));
+    }
+    int rs = run_ops(h, p, io, st, nullptr, false, PART_ALL, e1);
+    if (ms3 && rs == HRP_OK) {
+      // the reference synchronises its stream after the DepthNet and at the end of the forward (full_net.py:337-340,
+      // 452-457) and reports (time_root, time_other, time_whole); here: device time between events, list order = DepthNet first
+      cudaEventRecord(e2, st);
+      if (cudaEventSynchronize(e2) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_forward_timed: %s", cudaGetErrorString(cudaGetLastError()));
+      else { cudaEventElapsedTime(&ms3[0], e0, e1); cudaEventElapsedTime(&ms3[1], e1, e2); cudaEventElapsedTime(&ms3[2], e0, e2); }
+    }
+    if (ms3) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
     HRP_CUDA(cudaEventRecord(p->done, st));
     p->used = true;
     return rs;
   }
-  // whatever stream used this plan last must be done with its workspace before this forward touches it
-  if (p->used) HRP_CUDA(cudaStreamWaitEvent(st, p->done, 0));
-  // graph path: the graph reads/writes the plan's static staging buffers, so one instantiation serves every call
-  const int same = (x_reg == x_root) ? 1 : 0;
-  float* s_xreg = reinterpret_cast<float*>(p->ws + p->io_xreg);
-  float* s_xroot = same ? s_xreg : reinterpret_cast<float*>(p->ws + p->io_xroot);
+  // graph path: the graph reads / writes the plan's static staging (camera, initial states, output record), so one
+  // instantiation serves every call; the images are consumed by the pre-graph ops straight from the caller's buffers
   float* s_kv = reinterpret_cast<float*>(p->ws + p->io_kv);
   float* s_K = reinterpret_cast<float*>(p->ws + p->io_K);
   float* s_out = reinterpret_cast<float*>(p->ws + p->io_out);
-  if (!p->exec[same]) {
+  float* s_ip = reinterpret_cast<float*>(p->ws + p->io_initp);
+  float* s_ir = reinterpret_cast<float*>(p->ws + p->io_initr);
+  int* s_flags = reinterpret_cast<int*>(p->ws + p->io_flags);
+  if (!p->exec) {
     cudaGraph_t g = nullptr;
+    int64_t n_graph = 0;
     HRP_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
-    const int rs = run_ops(h, p, IoPtrs{s_xreg, s_xroot, s_kv, s_K, s_out}, h->capture_stream, nullptr, h->use_lanes && h->n_lanes > 1);
+    const int rs = run_ops(h, p, IoPtrs{nullptr, nullptr, s_kv, s_K, s_out, s_ip, s_ir, s_flags}, h->capture_stream, nullptr,
+                           h->use_lanes && h->n_lanes > 1, PART_GRAPH, nullptr, &n_graph);
     cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &g);
     if (rs != HRP_OK) { if (g) cudaGraphDestroy(g); return rs; }
     if (ce != cudaSuccess) return fail(HRP_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-    ce = cudaGraphInstantiate(&p->exec[same], g, 0);
+    ce = cudaGraphInstantiate(&p->exec, g, 0);
     cudaGraphDestroy(g);
     if (ce != cudaSuccess) return fail(HRP_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ce));
+    p->launches = n_graph;
   }
-  const size_t img = (size_t)B * 3 * 256 * 256 * sizeof(float);
-  HRP_CUDA(cudaMemcpyAsync(s_xreg, x_reg, img, cudaMemcpyDeviceToDevice, st));
-  if (!same) HRP_CUDA(cudaMemcpyAsync(s_xroot, x_root, img, cudaMemcpyDeviceToDevice, st));
+  int64_t n_pre = 0;
+  HRP_TRY(run_ops(h, p, IoPtrs{x_reg, x_root, nullptr, nullptr, nullptr}, st, nullptr, false, PART_PRE, nullptr, &n_pre));
   HRP_CUDA(cudaMemcpyAsync(s_kv, k_value, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
   HRP_CUDA(cudaMemcpyAsync(s_K, Kmat, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  HRP_CUDA(cudaGraphLaunch(p->exec[same], st));
+  if (init_pose) HRP_CUDA(cudaMemcpyAsync(s_ip, init_pose, (size_t)B * h->dof * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (init_rot) HRP_CUDA(cudaMemcpyAsync(s_ir, init_rot, (size_t)B * 6 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const int want = (init_pose ? 1 : 0) | (init_rot ? 2 : 0);
+  if (p->flags_state != want) {
+    HRP_CUDA(cudaMemsetAsync(s_flags, init_pose ? 1 : 0, 4, st));
+    HRP_CUDA(cudaMemsetAsync(s_flags + 1, init_rot ? 1 : 0, 4, st));
+    p->flags_state = want;
+  }
+  HRP_CUDA(cudaGraphLaunch(p->exec, st));
   HRP_CUDA(cudaMemcpyAsync(out, s_out, (size_t)record_floats(h, B, nullptr) * sizeof(float), cudaMemcpyDeviceToDevice, st));
   HRP_CUDA(cudaEventRecord(p->done, st));
   p->used = true;
+  h->last_launches = p->launches + n_pre;
+  return HRP_OK;
+}
+}  // namespace
+
+extern "C" int hrp_forward(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
+                           int B, float* out, void* stream) {
+  return forward_impl(h, x_reg, x_root, k_value, Kmat, nullptr, nullptr, B, out, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int hrp_forward_ex(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
+                              const float* init_pose, const float* init_rot, int B, float* out, void* stream) {
+  return forward_impl(h, x_reg, x_root, k_value, Kmat, init_pose, init_rot, B, out, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int hrp_forward_timed(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
+                                 const float* init_pose, const float* init_rot, int B, float* out, float* ms3, void* stream) {
+  if (!ms3) return fail(HRP_ERR_INVALID, "hrp_forward_timed: null timing output");
+  return forward_impl(h, x_reg, x_root, k_value, Kmat, init_pose, init_rot, B, out, (cudaStream_t)stream, ms3);
+}
+
+extern "C" int hrp_release_plans(hrp_handle* h) {
+  if (!h) return fail(HRP_ERR_INVALID, "hrp_release_plans: null handle");
+  HRP_ON_DEVICE(h);
+  for (auto& kv : h->plans) destroy_plan(kv.second.get());
+  h->plans.clear();
+  h->last_slot.clear();
+  h->last_B = 0; h->last_stream = nullptr; h->next_slot = 0;
   return HRP_OK;
 }
 
@@ -1340,7 +1462,7 @@ extern "C" int hrp_forward_profile(hrp_handle* h, const float* x_reg, const floa
                                    double* flops_by_class, void* stream) {
   HRP_TRY(check_forward_args(h, x_reg, x_root, k_value, Kmat, B, out));
   if (!ms_by_class || !launches_by_class || !flops_by_class) return fail(HRP_ERR_INVALID, "hrp_forward_profile: null output");
-  HRP_CUDA(cudaSetDevice(h->device));
+  HRP_ON_DEVICE(h);
   Plan* p = nullptr;
   HRP_TRY(make_plan(h, B, &p));
   for (int c = 0; c < HRP_NUM_CLASSES; ++c) { ms_by_class[c] = 0.f; launches_by_class[c] = 0; flops_by_class[c] = 0.0; }
@@ -1361,7 +1483,7 @@ extern "C" int hrp_forward_profile(hrp_handle* h, const float* x_reg, const floa
 extern "C" int hrp_debug_tensor(hrp_handle* h, const char* name, int B, float* dst_device, int64_t* numel, void* stream) {
   if (!h || !name || !numel) return fail(HRP_ERR_INVALID, "hrp_debug_tensor: null argument");
   auto it = h->debug.find(name);
-  if (it == h->debug.end()) return fail(HRP_ERR_INVALID, "hrp_debug_tensor: unknown tensor '%s' (xf, img_feat, logits)", name);
+  if (it == h->debug.end()) return fail(HRP_ERR_INVALID, "hrp_debug_tensor: unknown tensor '%s' (xf, img_feat, logits, head_iters)", name);
   auto ls = h->last_slot.find(B);
   auto pit = ls == h->last_slot.end() ? h->plans.end() : h->plans.find(B * 8 + ls->second);
   if (pit == h->plans.end()) return fail(HRP_ERR_STATE, "hrp_debug_tensor: no forward has run for batch %d", B);

@@ -164,6 +164,10 @@ class HoliRobPoseB200(torch.nn.Module):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cuda", 0)
         self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("HoliRobPoseB200 runs on CUDA devices only (got %s); there is no CPU fallback" % self.device)
+        if self.device.index is None:                                    # 'cuda' = the process's CURRENT device, not GPU 0
+            self.device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         parsed = urdf.Robot(open(consts.urdf_path(robot_type)).read())
         self.program = urdf.compile_program(parsed, urdf.keypoint_frames(robot_type, parsed), self.reference_keypoint_id,
                                             spec["joints"])
@@ -172,7 +176,7 @@ class HoliRobPoseB200(torch.nn.Module):
         self._cfg = capi.Config(capi.BACKBONE[self.backbone_name], capi.PREC[precision], self.n_iter, int(self.fix_root),
                                 self.image_size, depth_factor)
         h = C.c_void_p()
-        capi.check(capi.lib().hrp_create(C.byref(self._cfg), C.byref(self._prog_struct), self.device.index or 0, C.byref(h)))
+        capi.check(capi.lib().hrp_create(C.byref(self._cfg), C.byref(self._prog_struct), self.device.index, C.byref(h)))
         self._h = h
         self._finalized = False
         self._out = {}
@@ -202,7 +206,7 @@ class HoliRobPoseB200(torch.nn.Module):
             raise RuntimeError("weights are already loaded; build a new HoliRobPoseB200 to load another checkpoint")
         L = capi.lib()
         expected = dict(self.expected_tensors())
-        seen = set()
+        seen = self.__dict__.setdefault("_seen", set())     # accumulates over strict=False loads (pretrained DepthNet, then the rest)
         unexpected = []
         for k, v in state_dict.items():
             if k.startswith("module."):
@@ -221,9 +225,44 @@ class HoliRobPoseB200(torch.nn.Module):
         missing = [k for k in expected if k not in seen and not k.endswith("num_batches_tracked")]
         if strict and (missing or unexpected):
             raise RuntimeError("load_state_dict: missing %s, unexpected %s" % (missing[:5], unexpected[:5]))
+        if missing:
+            # strict=False on a torch module leaves absent tensors at their constructor values; this handle has no
+            # constructor values (weights only ever come from a checkpoint), so it stays open for the next load
+            self._pending_missing = missing
+            return missing, unexpected
         capi.check(L.hrp_finalize_weights(self._h))
         self._finalized = True
+        self._pending_missing = []
         return missing, unexpected
+
+    @staticmethod
+    def read_checkpoint(path_or_dict, map_location="cpu"):
+        """Reference checkpoint file -> plain state dict. Accepts what `save_checkpoint` writes
+        (lib/utils/utils.py:248-254: {'epoch', 'auc_add', 'model_state_dict', 'optimizer_state_dict',
+        'lr_scheduler_last_epoch'}), a bare state dict, DataParallel / DDP `module.` prefixes
+        (scripts/fullnet_test.py:193-198)."""
+        ck = path_or_dict
+        if not isinstance(ck, dict):
+            ck = torch.load(path_or_dict, map_location=map_location, weights_only=False)
+        sd = ck["model_state_dict"] if "model_state_dict" in ck else ck
+        return {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd.items()}
+
+    def load_checkpoint(self, path_or_dict, pretrained_rootnet=None, strict=True):
+        """`torch.load(path)['model_state_dict']` + `load_state_dict` as the reference's evaluators do
+        (scripts/test.py, scripts/fullnet_test.py:186-198, lib/utils/utils.py:198-200).
+
+        pretrained_rootnet: optional DepthNet pre-training checkpoint (lib/models/depth_net.py `RootNet`), merged the way
+        the factory does (full_net.py:486-500): keys `backbone.*` are re-keyed to `rootnet_backbone.*`, everything is
+        loaded with strict=False semantics, i.e. only names this network has are taken (`depth_layer.*` among them) and
+        they override the same names of the main checkpoint."""
+        sd = dict(self.read_checkpoint(path_or_dict))
+        if pretrained_rootnet is not None:
+            expected = dict(self.expected_tensors())
+            for k, v in self.read_checkpoint(pretrained_rootnet).items():
+                nk = k.replace("backbone", "rootnet_backbone") if k.startswith("backbone") else k   # full_net.py:494-498
+                if nk in expected:
+                    sd[nk] = v
+        return self.load_state_dict(sd, strict=strict)
 
     # ---- forward -----------------------------------------------------------------------------------------------------
     def _record(self, B, device):
@@ -234,26 +273,50 @@ class HoliRobPoseB200(torch.nn.Module):
             self._out[key] = list(offs)
         return self._out[key]
 
-    def forward_record(self, x_reg, x_root, k_value, K):
-        """Runs the network; returns (flat fp32 record tensor, field offsets)."""
+    def forward_record(self, x_reg, x_root, k_value, K, init_pose=None, init_rot=None, times=None):
+        """Runs the network; returns (flat fp32 record tensor, field offsets). init_pose [B,dof] / init_rot [B,6]:
+        optional initial states of the refinement heads (full_net.py:268-272). times: a list that receives
+        (time_root, time_other, time_whole) in seconds -- the reference's test_fps mode, which synchronises."""
         if not self._finalized:
-            raise RuntimeError("forward before load_state_dict")
+            raise RuntimeError("forward before load_state_dict" + (
+                " (the last load left tensors missing: %s ...)" % self._pending_missing[:3] if getattr(self, "_pending_missing", None) else ""))
         B = x_reg.shape[0]
         for t, shp in ((x_reg, (B, 3, 256, 256)), (x_root, (B, 3, 256, 256)), (K, (B, 3, 3))):
             if not t.is_cuda or tuple(t.shape) != shp:
                 raise ValueError("expected a CUDA tensor of shape %s, got %s on %s" % (shp, tuple(t.shape), t.device))
+            if t.device != self.device:
+                raise ValueError("input lives on %s but this model was built for %s" % (t.device, self.device))
         if B == 0:                                                           # torch modules pass empty batches through
+            if times is not None:
+                times.append((0.0, 0.0, 0.0))
             return torch.empty(0, device=x_reg.device, dtype=torch.float32), [0] * (capi.NUM_FIELDS + 1)
-        same = x_root is x_reg or x_root.data_ptr() == x_reg.data_ptr()
+        same = x_root is x_reg                                               # views that merely START at the same address differ
         x_reg = x_reg.float().contiguous()                                   # full_net.py:265-266
         x_root = x_reg if same else x_root.float().contiguous()
         k_value = torch.as_tensor(k_value, device=x_reg.device).float().reshape(B).contiguous()
         K = K.float().contiguous()
+        null = C.c_void_p(0)
+        ip = ir = null
+        if init_pose is not None:
+            init_pose = torch.as_tensor(init_pose, device=x_reg.device).float().expand(B, self.dof).contiguous()
+            ip = _ptr(init_pose)
+        if init_rot is not None:
+            init_rot = torch.as_tensor(init_rot, device=x_reg.device).float().expand(B, 6).contiguous()
+            ir = _ptr(init_rot)
         offs = self._record(B, x_reg.device)
         rec = torch.empty(offs[-1], device=x_reg.device, dtype=torch.float32)
         st = torch.cuda.current_stream(x_reg.device).cuda_stream
-        capi.check(capi.lib().hrp_forward(self._h, _ptr(x_reg), _ptr(x_root), _ptr(k_value), _ptr(K), B, _ptr(rec),
-                                          C.c_void_p(st)))
+        L = capi.lib()
+        if times is not None:
+            ms = (C.c_float * 3)()
+            capi.check(L.hrp_forward_timed(self._h, _ptr(x_reg), _ptr(x_root), _ptr(k_value), _ptr(K), ip, ir, B, _ptr(rec), ms,
+                                           C.c_void_p(st)))
+            times.append(tuple(1e-3 * v for v in ms))
+        elif init_pose is not None or init_rot is not None:
+            capi.check(L.hrp_forward_ex(self._h, _ptr(x_reg), _ptr(x_root), _ptr(k_value), _ptr(K), ip, ir, B, _ptr(rec),
+                                        C.c_void_p(st)))
+        else:
+            capi.check(L.hrp_forward(self._h, _ptr(x_reg), _ptr(x_root), _ptr(k_value), _ptr(K), B, _ptr(rec), C.c_void_p(st)))
         return rec, offs
 
     def _fields(self, rec, offs, B):
@@ -270,17 +333,18 @@ class HoliRobPoseB200(torch.nn.Module):
 
     def forward(self, x_reg_input, x_root_input=None, k_value=None, K=None, init_pose=None, init_rot=None,
                 test_fps=False):
-        """Reference signature -> 8-tuple (full_net.py:262, 466). `model(images, K)` / `model(images, K=K)` -> dict."""
-        if init_pose is not None or init_rot is not None or test_fps:
-            raise NotImplementedError("init_pose / init_rot / test_fps are not supported by the B200 path")
+        """Reference signature -> 8-tuple (full_net.py:262, 466), or 9 values with test_fps=True: the 8 tensors and
+        (time_root, time_other, time_whole) in seconds (full_net.py:459-460, unpacked by scripts/test.py:161-162).
+        `model(images, K)` / `model(images, K=K)` -> dict."""
         if K is None and (k_value is None) and x_root_input is not None and x_root_input.dim() == 3:
             return self.forward_dict(x_reg_input, x_root_input)              # model(images, K)
         if x_root_input is None:
             return self.forward_dict(x_reg_input, K, k_value)
         B = x_reg_input.shape[0]
-        rec, offs = self.forward_record(x_reg_input, x_root_input, k_value, K)
+        times = [] if test_fps else None
+        rec, offs = self.forward_record(x_reg_input, x_root_input, k_value, K, init_pose, init_rot, times)
         f = self._fields(rec, offs, B)
-        return tuple(f[:8])
+        return tuple(f[:8]) + ((times[0],) if test_fps else ())
 
     def forward_dict(self, images, K, k_value=None):
         """north_star convenience: dict of 2-D/3-D keypoints, joint angles, root depth and camera-frame pose."""
@@ -295,6 +359,10 @@ class HoliRobPoseB200(torch.nn.Module):
 
     def set_option(self, name, value):
         capi.check(capi.lib().hrp_set_option(self._h, name.encode(), int(value)))
+
+    def release_plans(self):
+        """Free every cached per-batch-size plan (workspace + CUDA graph); the next forward re-plans."""
+        capi.check(capi.lib().hrp_release_plans(self._h))
 
     def debug_tensor(self, name, B):
         n = C.c_int64()

@@ -24,6 +24,7 @@ import numpy as np
 from . import arch, consts
 
 CALIB_FILE = os.path.join(consts.DATA_DIR, "bn_calib_v2.npz")
+CALIB_FILE_UNDAMPED = os.path.join(consts.DATA_DIR, "bn_calib_undamped.npz")   # recipe="undamped" (SURVEY 8d as written)
 _RESIDUAL_TAIL = re.compile(r"(layer\d\.\d+\.bn3|incre_modules\.\d\.0\.bn3|branches\.\d\.\d\.bn2)\.weight$")
 CALIB_IMAGE_SEED = 7
 CALIB_BATCH = 8
@@ -33,7 +34,7 @@ def _rng(seed, name):
     return np.random.Generator(np.random.PCG64([int(seed), zlib.crc32(name.encode())]))
 
 
-def _draw(name, shape, kind, seed, robot):
+def _draw(name, shape, kind, seed, robot, damped=True):
     g = _rng(seed, name)
     f32 = np.float32
     if kind == "conv_w":
@@ -52,7 +53,7 @@ def _draw(name, shape, kind, seed, robot):
             return np.full(shape, 0.8, f32)                 # depth ~ 0.8*k/1000 m
         return (g.standard_normal(shape) * 0.05).astype(f32)
     if kind == "bn_w":
-        if _RESIDUAL_TAIL.search(name):
+        if damped and _RESIDUAL_TAIL.search(name):
             return g.uniform(0.05, 0.2, shape).astype(f32)  # damped residual branch (module docstring)
         return g.uniform(0.6, 1.4, shape).astype(f32)
     if kind == "bn_b":
@@ -81,27 +82,49 @@ def _draw(name, shape, kind, seed, robot):
 _calib_cache = {}
 
 
-def _calib(backbone):
-    if "z" not in _calib_cache:
-        _calib_cache["z"] = np.load(CALIB_FILE) if os.path.exists(CALIB_FILE) else None
-    return _calib_cache["z"]
+def _calib(recipe):
+    if recipe not in _calib_cache:
+        path = CALIB_FILE if recipe == "damped" else CALIB_FILE_UNDAMPED
+        _calib_cache[recipe] = np.load(path) if os.path.exists(path) else None
+    return _calib_cache[recipe]
 
 
-def make_state_dict(robot, backbone="resnet50", seed=1234, calibrated=True):
-    """Ordered dict name -> numpy array in the reference's state-dict format."""
+def make_state_dict(robot, backbone="resnet50", seed=1234, calibrated=True, recipe="damped"):
+    """Ordered dict name -> numpy array in the reference's state-dict format.
+
+    recipe "damped" (default, module docstring) or "undamped": every BatchNorm gain U(0.6, 1.4), i.e. SURVEY.md 8d's
+    recipe as written. The undamped network is chaotic (it amplifies operand rounding); it is kept to REPORT how far each
+    precision family is from the gates there and to exercise BN folding on different running statistics."""
+    if recipe not in ("damped", "undamped"):
+        raise ValueError(recipe)
     variant = "resnet50" if backbone in ("resnet", "resnet50") else "hrnet32"
-    z = _calib(variant) if calibrated else None
+    z = _calib(recipe) if calibrated else None
     if calibrated and z is None:
-        raise FileNotFoundError("%s missing: run scripts/make_bn_calib.py" % CALIB_FILE)
+        raise FileNotFoundError("BN calibration file for recipe %r missing: run scripts/make_bn_calib.py" % recipe)
     sd = {}
     for name, shape, kind in arch.full_net(robot, backbone):
-        t = _draw(name, shape, kind, seed, robot)
+        t = _draw(name, shape, kind, seed, robot, damped=recipe == "damped")
         if z is not None and kind in ("bn_mean", "bn_var"):
             key = "%d/%s/%s" % (seed, variant if name.startswith(("reg_backbone", "deconv")) else "rootnet", name)
             t = z[key].astype(np.float32)
             assert t.shape == tuple(shape), (name, t.shape, shape)
         sd[name] = t
     return sd
+
+
+def make_pretrained_rootnet_state(sd):
+    """A DepthNet pre-training checkpoint (lib/models/depth_net.py RootNet naming: `backbone.*`, `depth_layer.*`) that
+    differs measurably from the rootnet tensors of `sd`: same convolutions, other depth head, last BN gain scaled."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("rootnet_backbone."):
+            out["backbone." + k[len("rootnet_backbone."):]] = np.array(v, copy=True)
+    out["backbone.final_feat_layer.1.weight"] = out["backbone.final_feat_layer.1.weight"] * np.float32(0.9)
+    g = np.random.Generator(np.random.PCG64(77))
+    out["depth_layer.weight"] = (sd["depth_layer.weight"] + 2e-4 * g.standard_normal(sd["depth_layer.weight"].shape)).astype(np.float32)
+    out["depth_layer.bias"] = np.full_like(sd["depth_layer.bias"], 0.7)
+    out["xy_layer.weight"] = np.zeros((1, 256, 1, 1), np.float32)      # a tensor the full network does not have (strict=False)
+    return out
 
 
 def make_images(batch, seed):

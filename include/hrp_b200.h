@@ -169,16 +169,37 @@ size_t hrp_workspace_bytes(hrp_handle* h, int B);
 int hrp_forward(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
                 int B, float* out, void* stream);
 
+/* The same forward with per-frame initial states for the two refinement heads -- the reference's `init_pose` /
+ * `init_rot` keyword arguments (full_net.py:262, 268-272): init_pose [B,dof], init_rot [B,6] device fp32, either may be
+ * NULL (then the module's `init_pose` / `init_rot` buffers are used, as in the reference). */
+int hrp_forward_ex(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
+                   const float* init_pose, const float* init_rot, int B, float* out, void* stream);
+
+/* The reference's `test_fps=True` mode (full_net.py:277-279, 337-345, 452-460; called by scripts/test.py:161-162): the
+ * forward runs un-graphed in list order (DepthNet first) and SYNCHRONISES the stream, like the reference does, then
+ * reports ms3 = {time_root, time_other, time_whole} in MILLISECONDS of device time (CUDA events: start -> depth head done
+ * -> end of FK). init_pose / init_rot as in hrp_forward_ex. */
+int hrp_forward_timed(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
+                      const float* init_pose, const float* init_rot, int B, float* out, float* ms3 /*[3]*/, void* stream);
+
+/* Plans (workspace + CUDA graph) are cached per batch size: at most "max_cached_batches" distinct sizes (default 4, least
+ * recently used dropped first), and a second / third plan of a size only when forwards of that size arrive on different
+ * streams. hrp_release_plans frees every cached plan now (waits for the forwards that use them); the next forward
+ * re-plans. */
+int hrp_release_plans(hrp_handle* h);
+
 /* Options: "cuda_graph" (0/1, default 1: replay one graph per batch size), "lanes" (0/1, default 1: capture the graph
  * over several streams so independent sub-networks overlap), "slots" (1..4, default 3: plans = workspace + graph kept per
  * batch size and used round-robin, so consecutive forwards enqueued on different streams overlap), "lane_share_pct"
  * (5..100: share of the CTA slots one conv launch may take; default 25 for batches of 32 frames and more -- it maximises
  * the throughput of overlapping forwards -- and 50 below, where the latency of a single forward matters). Graph-shaping options take effect for graphs not yet captured.
- * Unknown option -> HRP_ERR_INVALID. */
+ * "max_cached_batches" (1..64, default 4): see hrp_release_plans. Unknown option -> HRP_ERR_INVALID. */
 int hrp_set_option(hrp_handle* h, const char* name, int64_t value);
 
 /* Introspection for the bench / tests. */
-int64_t hrp_launch_count(const hrp_handle* h);            /* kernels enqueued by the most recent hrp_forward */
+int64_t hrp_launch_count(const hrp_handle* h);            /* kernels one forward enqueues (plan of the most recent hrp_forward) */
+/* name: "xf", "img_feat" [B,2048]; "logits" (fp32 family) [B,nkpt*64,64,64]; "head_iters" [B,n_iter,dof+6]: every iterate of
+ * the pose (first dof columns) and rot6d refinement (full_net.py:381-394, 431-444). */
 int hrp_debug_tensor(hrp_handle* h, const char* name, int B, float* dst_device, int64_t* numel, void* stream);
 /* Per-kernel-class device time of one un-graphed forward (CUDA events around every launch; for profiling only).
  * classes: 0 conv-tensor, 1 conv-fp32, 2 stem, 3 pool/fuse elementwise, 4 heads, 5 softargmax, 6 fk. */

@@ -48,7 +48,7 @@ class OracleModel:
                                     np.asarray(trans, np.float32), self.ref)
 
     @torch.no_grad()
-    def forward(self, x_reg, x_root, k_value, K, calib=None, trace=None):
+    def forward(self, x_reg, x_root, k_value, K, calib=None, trace=None, init_pose=None, init_rot=None):
         sd = self.sd
         x_reg, x_root = x_reg.float(), x_root.float()
         B = x_reg.shape[0]
@@ -67,10 +67,10 @@ class OracleModel:
         trans = integral.uvz_to_xyz(root_uv, depth, K)
         tp = [] if trace is not None else None
         tr = [] if trace is not None else None
-        pose = network.iterative_head(xf, sd["init_pose"].expand(B, -1), sd, "fc_pose_1", "fc_pose_2", "decpose",
-                                      self.n_iter, tp)
-        rot = network.iterative_head(xf, sd["init_rot"].expand(B, -1), sd, "fc_rot_1", "fc_rot_2", "decrot",
-                                     self.n_iter, tr)
+        p0 = sd["init_pose"].expand(B, -1) if init_pose is None else init_pose        # full_net.py:268-272
+        r0 = sd["init_rot"].expand(B, -1) if init_rot is None else init_rot
+        pose = network.iterative_head(xf, p0, sd, "fc_pose_1", "fc_pose_2", "decpose", self.n_iter, tp)
+        rot = network.iterative_head(xf, r0, sd, "fc_rot_1", "fc_rot_2", "decrot", self.n_iter, tr)
         xyz_fk = torch.from_numpy(self.fk(pose.numpy(), rot.numpy(), trans.numpy()))
         if trace is not None:
             trace.update(logits=logits, xf=xf, img_feat=img_feat, pose_iters=tp, rot_iters=tr)

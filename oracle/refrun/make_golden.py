@@ -5,6 +5,10 @@ Fixtures (inputs are re-derivable from the recorded seeds through hrp_b200.synth
                                   plus stage-boundary probes captured with forward hooks (xf, img_feat, a strided
                                   sample of the heatmap logits);
   softargmax_<path>_k<nkpt>_<mode>.npz   HeatmapIntegralPose (integral.py:102-208) on adversarial heatmaps;
+  fullnet_<robot>_<backbone>_undamped.npz   the same on synth's "undamped" weight recipe;
+  fullnet_panda_resnet50_ckpt.npz the factory path get_rootNetwithRegInt_model with `pretrained_rootnet` (full_net.py:470-505:
+                                  torch.load, `backbone.` -> `rootnet_backbone.` re-key, strict=False) followed by the evaluator's
+                                  checkpoint load (fullnet_test.py:186-198), and a forward with init_pose / init_rot overrides;
   fk_<robot>.npz                  URDFRobot.get_keypoints[_root] (urdf_robot.py:95-118,193-223) +
                                   point_projection_from_3d_tensor (transforms.py:17-21) over the joint-bound sweep.
 Usage: python -m oracle.refrun.make_golden
@@ -25,7 +29,9 @@ from oracle.refrun import harness  # noqa: E402
 OUT = os.path.join(REPO, "tests", "golden")
 WEIGHT_SEED = 1234
 FULLNET = [("panda", "resnet50", 2, 2024), ("kuka", "resnet50", 2, 2025), ("baxter", "resnet50", 2, 2026),
-           ("panda", "hrnet32", 2, 2027), ("baxter", "hrnet32", 1, 2028)]
+           ("panda", "hrnet32", 2, 2027), ("baxter", "hrnet32", 1, 2028), ("kuka", "hrnet32", 1, 2029)]
+# recipe="undamped" weights (SURVEY 8d as written): reported per family, gated for fp32 only
+UNDAMPED = [("panda", "resnet50", 2, 2031), ("panda", "hrnet32", 1, 2032)]
 LOGIT_STRIDES = (37, 5, 7)
 FK_N, FK_SEED = 512, 99
 SA_CASES = [("resnet50", 7, "blobs", 2, 11), ("resnet50", 7, "extreme", 2, 12), ("resnet50", 17, "noise", 1, 13),
@@ -36,9 +42,12 @@ def t(a):
     return torch.from_numpy(np.ascontiguousarray(a))
 
 
-def fullnet():
-    for robot, bb, B, seed in FULLNET:
-        sd = synth.make_state_dict(robot, bb, WEIGHT_SEED)
+def fullnet(cases=None, recipe="damped", only=None):
+    for robot, bb, B, seed in (cases or FULLNET):
+        name = "fullnet_%s_%s%s.npz" % (robot, bb, "" if recipe == "damped" else "_" + recipe)
+        if only and name not in only:
+            continue
+        sd = synth.make_state_dict(robot, bb, WEIGHT_SEED, recipe=recipe)
         model, _ = harness.build_model(robot, bb)
         model.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
         probes = {}
@@ -62,7 +71,7 @@ def fullnet():
         out["probe_logits_sample"] = lg[:, ::s[0], ::s[1], ::s[2]].numpy()
         out["probe_logits_std"] = np.asarray(lg.std().item(), np.float32)
         out["meta"] = np.asarray([WEIGHT_SEED, seed, B], np.int64)
-        np.savez_compressed(os.path.join(OUT, "fullnet_%s_%s.npz" % (robot, bb)), **out)
+        np.savez_compressed(os.path.join(OUT, name), **out)
         print("fullnet", robot, bb, {k: tuple(v.shape) for k, v in out.items() if k.startswith(("joint", "kp2d_fk"))},
               "logit std %.3f" % lg.std().item())
 
@@ -104,9 +113,59 @@ def fk():
         print("fk", robot, xyz.shape, "link_names", list(r.link_names)[:4], "...")
 
 
+def checkpoint():
+    """Factory + pretrained DepthNet re-key + evaluator-style checkpoint load, through the reference's own code."""
+    import collections
+    import tempfile
+    ns = harness.setup()
+    robot, bb, B, seed = "panda", "resnet50", 2, 2033
+    sd = synth.make_state_dict(robot, bb, WEIGHT_SEED, recipe="undamped")
+    pre = synth.make_pretrained_rootnet_state(sd)
+    tmp = tempfile.mkdtemp(prefix="hrp_ckpt_")
+    pre_path = os.path.join(tmp, "depthnet.pk")
+    torch.save({"epoch": 3, "model_state_dict": collections.OrderedDict((k, t(v)) for k, v in pre.items())}, pre_path)
+    cfg = harness.make_cfg(robot, bb)
+    cfg.pretrained_rootnet = pre_path
+    init = {"robot_type": robot, "pose_params": ns.const.INITIAL_JOINT_ANGLE, "cam_params": np.eye(4, dtype=float),
+            "init_pose_from_mean": True}
+    model = ns.full_net.get_rootNetwithRegInt_model(init, cfg)            # full_net.py:470-505
+    # the evaluator then loads its checkpoint (DataParallel-prefixed keys, fullnet_test.py:186-198); here a checkpoint
+    # of the keypoint branch + heads only, so the pretrained DepthNet stays in place
+    main = collections.OrderedDict(("module." + k, t(v)) for k, v in sd.items()
+                                   if not k.startswith(("rootnet_backbone.", "depth_layer.")))
+    new_sd = collections.OrderedDict((k.replace("module.", "") if k.startswith("module.") else k, v) for k, v in main.items())
+    model.load_state_dict(new_sd, strict=False)
+    model.eval()
+    img, K, kv = synth.make_inputs(B, seed)
+    res = harness.forward(model, t(img), t(img), t(kv), t(K))
+    out = {k: v.numpy() for k, v in res.items()}
+    # init_pose / init_rot overrides (full_net.py:262, 268-272)
+    g = np.random.Generator(np.random.PCG64(5))
+    ip = (np.asarray(consts.ROBOTS[robot]["init_pose"], np.float32)[None] + 0.3 * g.standard_normal((B, 8))).astype(np.float32)
+    ir = (np.asarray(consts.INIT_ROT6D, np.float32)[None] + 0.2 * g.standard_normal((B, 6))).astype(np.float32)
+    with torch.no_grad():
+        o2 = model(t(img), t(img), t(kv), t(K), init_pose=t(ip), init_rot=t(ir))
+    out["init_pose"], out["init_rot"] = ip, ir
+    out["ovr_joint_angles"], out["ovr_rot6d"], out["ovr_kp3d_fk"] = o2[0].numpy(), o2[1].numpy(), o2[7].numpy()
+    out["meta"] = np.asarray([WEIGHT_SEED, seed, B], np.int64)
+    np.savez_compressed(os.path.join(OUT, "fullnet_panda_resnet50_ckpt.npz"), **out)
+    print("checkpoint", {k: tuple(v.shape) for k, v in out.items() if k.startswith(("joint", "ovr"))},
+          "depth", out["root_depth"].ravel())
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    fk()
-    softargmax()
-    fullnet()
+    what = sys.argv[1:] or ["fk", "softargmax", "fullnet", "undamped", "checkpoint"]
+    if "fk" in what:
+        fk()
+    if "softargmax" in what:
+        softargmax()
+    if "fullnet" in what:
+        fullnet()
+    if "fullnet_new" in what:
+        fullnet(only={"fullnet_kuka_hrnet32.npz"})
+    if "undamped" in what:
+        fullnet(UNDAMPED, recipe="undamped")
+    if "checkpoint" in what:
+        checkpoint()

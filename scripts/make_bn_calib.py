@@ -3,6 +3,7 @@
 For each weight seed and each sub-network (ResNet-50 + deconv keypoint branch, HRNet-W32 keypoint branch, HRNet-W32
 DepthNet) run the oracle forward once over CALIB_BATCH seeded noise images with BN in batch-statistics mode and store
 (mean, unbiased var) per BN layer. Keys: "<seed>/<resnet50|hrnet32|rootnet>/<state-dict name>".
+usage: make_bn_calib.py [damped|undamped]  (undamped -> data/bn_calib_undamped.npz, see synth.make_state_dict)
 """
 import os
 import sys
@@ -19,14 +20,14 @@ from oracle import network  # noqa: E402
 SEEDS = (1234,)
 
 
-def main():
+def main(recipe="damped"):
     torch.manual_seed(0)
     out = {}
     x = torch.from_numpy(synth.make_images(synth.CALIB_BATCH, synth.CALIB_IMAGE_SEED))
     for seed in SEEDS:
         for variant in ("resnet50", "hrnet32"):
             sd = {k: torch.from_numpy(np.asarray(v)) for k, v in
-                  synth.make_state_dict("panda", variant, seed, calibrated=False).items()}
+                  synth.make_state_dict("panda", variant, seed, calibrated=False, recipe=recipe).items()}
             with torch.no_grad():
                 c = network.Calib()
                 if variant == "resnet50":
@@ -41,9 +42,10 @@ def main():
                 for k, v in c.stats.items():
                     out["%d/%s/%s" % (seed, variant, k)] = v.numpy()
             print(seed, variant, len(out))
-    np.savez_compressed(synth.CALIB_FILE, **out)
-    print("wrote", synth.CALIB_FILE, os.path.getsize(synth.CALIB_FILE), "bytes")
+    path = synth.CALIB_FILE if recipe == "damped" else synth.CALIB_FILE_UNDAMPED
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else "damped")

@@ -9,19 +9,39 @@ from oracle import model as omodel
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FULLNET_CASES = [("panda", "resnet50"), ("kuka", "resnet50"), ("baxter", "resnet50"), ("panda", "hrnet32"),
-                 ("baxter", "hrnet32")]
+                 ("baxter", "hrnet32"), ("kuka", "hrnet32")]
+UNDAMPED_CASES = [("panda", "resnet50"), ("panda", "hrnet32")]
 # north_star parity gates (fp32 / TF32 parity mode)
 TOL_PX, TOL_RAD, TOL_DEPTH_M = 0.5, 1e-3, 1e-3
 
 _oracles = {}
 
 
-def oracle_for(robot, backbone, seed=1234):
-    key = (robot, backbone, seed)
+def oracle_for(robot, backbone, seed=1234, recipe="damped"):
+    key = (robot, backbone, seed, recipe)
     if key not in _oracles:
-        sd = synth.make_state_dict(robot, backbone, seed)
+        sd = synth.make_state_dict(robot, backbone, seed, recipe=recipe)
         _oracles[key] = (omodel.OracleModel(robot, sd, open(consts.urdf_path(robot)).read(), backbone), sd)
     return _oracles[key]
+
+
+def checkpoint_case():
+    """The weights of tests/golden/fullnet_panda_resnet50_ckpt.npz as the two reference-format checkpoints it was made
+    from (oracle/refrun/make_golden.py checkpoint()): (main checkpoint dict with DataParallel-prefixed keys and no DepthNet
+    tensors, DepthNet pre-training checkpoint dict in lib/models/depth_net.py naming, merged plain state dict)."""
+    import collections
+    sd = synth.make_state_dict("panda", "resnet50", 1234, recipe="undamped")
+    pre = synth.make_pretrained_rootnet_state(sd)
+    main = collections.OrderedDict(("module." + k, torch.from_numpy(np.asarray(v))) for k, v in sd.items()
+                                   if not k.startswith(("rootnet_backbone.", "depth_layer.")))
+    merged = dict(sd)
+    for k, v in pre.items():
+        nk = k.replace("backbone", "rootnet_backbone") if k.startswith("backbone") else k
+        if nk in merged:
+            merged[nk] = v
+    ck_main = {"epoch": 7, "auc_add": 0.5, "model_state_dict": main, "optimizer_state_dict": {}, "lr_scheduler_last_epoch": -1}
+    ck_pre = {"epoch": 3, "model_state_dict": collections.OrderedDict((k, torch.from_numpy(v)) for k, v in pre.items())}
+    return ck_main, ck_pre, merged
 
 
 def load_golden(name):

@@ -81,3 +81,36 @@ def test_fullnet_matches_reference(robot, backbone):
     # the fixture is non-trivial: peaked-but-not-one-hot heatmaps, metre-scale depths, radians-scale angles
     assert 1.0 < float(g["probe_logits_std"]) < 5.0
     assert 0.3 < float(np.abs(g["root_depth"]).max()) < 10.0
+
+
+@pytest.mark.parametrize("robot,backbone", helpers.UNDAMPED_CASES)
+def test_fullnet_undamped_weights_match_reference(robot, backbone):
+    """The SURVEY 8d weight recipe as written (unit-gain residual branches, its own BN calibration)."""
+    g = helpers.load_golden("fullnet_%s_%s_undamped.npz" % (robot, backbone))
+    wseed, seed, B = (int(v) for v in g["meta"])
+    om, _ = helpers.oracle_for(robot, backbone, wseed, recipe="undamped")
+    img, K, kv = helpers.inputs(B, seed)
+    res = om.forward_dict(img, img, kv, K)
+    for k, t in dict(joint_angles=2e-5, rot6d=2e-5, root_depth=2e-5, uvd=2e-5, kp3d_fk=2e-5, kp2d_int=1e-2, kp2d_fk=1e-2).items():
+        assert helpers.maxdiff(res[k], g[k]) < t, (k, helpers.maxdiff(res[k], g[k]))
+
+
+def test_checkpoint_merge_and_init_overrides_match_reference():
+    """Golden made by the reference's factory with `pretrained_rootnet` (torch.load + `backbone.` -> `rootnet_backbone.`
+    re-key + strict=False, full_net.py:486-500) followed by the evaluator's `module.`-stripping load
+    (fullnet_test.py:186-198); plus a forward with init_pose / init_rot (full_net.py:268-272)."""
+    g = helpers.load_golden("fullnet_panda_resnet50_ckpt.npz")
+    wseed, seed, B = (int(v) for v in g["meta"])
+    _, _, merged = helpers.checkpoint_case()
+    from oracle import model as omodel
+    om = omodel.OracleModel("panda", merged, open(consts.urdf_path("panda")).read(), "resnet50")
+    img, K, kv = helpers.inputs(B, seed)
+    res = om.forward_dict(img, img, kv, K)
+    for k, t in dict(joint_angles=2e-5, rot6d=2e-5, root_depth=2e-5, kp3d_fk=2e-5, kp2d_fk=1e-2).items():
+        assert helpers.maxdiff(res[k], g[k]) < t, (k, helpers.maxdiff(res[k], g[k]))
+    trace = {}
+    o2 = om.forward(img, img, kv, K, trace=trace, init_pose=torch.from_numpy(g["init_pose"]), init_rot=torch.from_numpy(g["init_rot"]))
+    assert helpers.maxdiff(o2[0], g["ovr_joint_angles"]) < 2e-5 and helpers.maxdiff(o2[1], g["ovr_rot6d"]) < 2e-5
+    assert helpers.maxdiff(o2[7], g["ovr_kp3d_fk"]) < 2e-5
+    assert helpers.maxdiff(o2[0], res["joint_angles"]) > 1e-2          # the override matters
+    assert len(trace["pose_iters"]) == 4
