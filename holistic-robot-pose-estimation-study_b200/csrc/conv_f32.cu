@@ -342,7 +342,7 @@ int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, vo
 // NCHW fp32 image -> zero-padded NHWC4 operand image of the tensor-core stems (kernels.h). One thread per padded pixel;
 // the three plane reads are coalesced along x, the write is one 8- or 16-byte store. Borders are rewritten every
 // forward because the arena recycles this memory.
-template <bool TF32>
+template <int MODE>      // 0 bf16, 1 fp32 rounded to TF32, 2 fp32 as is
 __global__ void stem_pack_kernel(const float* __restrict__ in, void* __restrict__ out, int B) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * STEM_HP * STEM_WP;
@@ -356,7 +356,9 @@ __global__ void stem_pack_kernel(const float* __restrict__ in, void* __restrict_
     const float* ip = in + ((size_t)b * 3 * 256 + y) * 256 + x;
     v0 = __ldg(ip); v1 = __ldg(ip + 256 * 256); v2 = __ldg(ip + 2 * 256 * 256);
   }
-  if constexpr (TF32) {
+  if constexpr (MODE == 2) {
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), 0u);
+  } else if constexpr (MODE == 1) {
     uint32_t r0, r1, r2;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(v0));
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v1));
@@ -375,8 +377,9 @@ int stem_pack_launch(const float* in_nchw, void* out, int B, int tf32, cudaStrea
   const long long total = (long long)B * STEM_HP * STEM_WP;
   if (total <= 0) return HRP_OK;
   const unsigned blocks = (unsigned)ceil_div64(total, 256);
-  if (tf32) stem_pack_kernel<true><<<blocks, 256, 0, s>>>(in_nchw, out, B);
-  else stem_pack_kernel<false><<<blocks, 256, 0, s>>>(in_nchw, out, B);
+  if (tf32 == 2) stem_pack_kernel<2><<<blocks, 256, 0, s>>>(in_nchw, out, B);
+  else if (tf32) stem_pack_kernel<1><<<blocks, 256, 0, s>>>(in_nchw, out, B);
+  else stem_pack_kernel<0><<<blocks, 256, 0, s>>>(in_nchw, out, B);
   HRP_CHECK_LAUNCH("stem_pack_kernel");
   return HRP_OK;
 }

@@ -73,6 +73,7 @@ struct TcParams {
   int bar_off;       // byte offset of the barrier block
   int cpr_log;       // log2 of 16-byte chunks per staged tile row (block_n * elem / 16)
   int round_tf32;    // round fp32 NHWC outputs to TF32 (nearest, ties away) so the next MMA sees exact operands
+  int x3;            // TF32 only: 3xTF32 -- operands split into hi + lo TF32 halves, D += Ahi Whi + Alo Whi + Ahi Wlo (fp32-grade products)
 };
 
 using namespace tc;
@@ -90,6 +91,25 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {      // cp.async.wait
   }
 }
 
+// 3xTF32 operand split of one 16-byte chunk (4 fp32) in shared memory: hi = the top 19 bits (exactly what kind::tf32 reads),
+// written back in place; lo = x - hi (exact in fp32), itself cut to TF32 (error 2^-22 |x|), written `lo_off` bytes further.
+__device__ __forceinline__ void split_chunk(uint32_t addr, uint32_t lo_off) {
+  uint32_t v[4], h[4], l[4];
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = v[e] & 0xffffe000u;
+    l[e] = __float_as_uint(__uint_as_float(v[e]) - __uint_as_float(h[e])) & 0xffffe000u;
+  }
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr + lo_off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+}
+// gather mode: the eight chunks this producer thread copied into a stage (conv_tc_kernel, producers)
+__device__ __forceinline__ void split_own_chunks(uint32_t row0, uint32_t sw_even, uint32_t sw_odd, uint32_t lo_off) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_chunk(row0 + ((i & 1) ? sw_odd : sw_even) + (uint32_t)i * (4 * TC_ROW_BYTES), lo_off);
+}
+
 // Persistent, warp-specialised: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (N tile fastest, so
 // co-resident CTAs share the activation rows they gather). The operand ring and both pipelines run across tile
 // boundaries: producers are already gathering tile i+1 while the MMA warp finishes tile i and the epilogue warps drain
@@ -105,13 +125,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
-  const int a_stage = TC_BLOCK_M * p.row_bytes, b_stage = p.block_n * p.row_bytes;
+  // 3xTF32: every stage holds the operand tile twice, [hi | lo]. The activation tile arrives as raw fp32; warps 0-3 split
+  // it in place (hi = the 19 bits the MMA reads, lo = the remainder, itself exact in TF32 to 2^-22) before the MMA warp sees it
+  const bool x3 = TF32 && p.x3 != 0;
+  const int a_half = TC_BLOCK_M * p.row_bytes, b_half = p.block_n * p.row_bytes;
+  const int a_stage = x3 ? 2 * a_half : a_half, b_stage = x3 ? 2 * b_half : b_half;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + (uint32_t)(S * a_stage);
   const uint32_t stg = smem_base + (uint32_t)p.stg_off;   // epilogue staging tile: 128 rows x (block_n*ESZ + 16) bytes
   const uint32_t sBar = smem_base + (uint32_t)p.bar_off;  // full[S], empty[S], acc_full[2], acc_empty[2], tmem slot, row offsets
   const uint32_t bar_full = sBar, bar_empty = sBar + 8u * TC_MAX_STAGES, bar_accf = sBar + 16u * TC_MAX_STAGES,
-                 bar_acce = bar_accf + 16u, tmem_slot = bar_acce + 16u, s_rowoff = tmem_slot + 16u;
+                 bar_acce = bar_accf + 16u, tmem_slot = bar_acce + 16u, s_rowoff = tmem_slot + 16u,
+                 bar_split = sBar + 16u * TC_MAX_STAGES + 48u + 16u * TC_BLOCK_M + 16u;   // 3xTF32, TMA mode: stage s has been split
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const ConvArgs& a = p.a;
@@ -120,6 +145,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8u * s, p.tma ? 1 : TC_PRODUCERS + 1);
       mbar_init(bar_empty + 8u * s, 1);
+      mbar_init(bar_split + 8u * s, TC_PRODUCERS);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8u * i, 1); mbar_init(bar_acce + 8u * i, 1); }
     for (int i = 0; i < 2; ++i) mbar_init(sBar + 16u * TC_MAX_STAGES + 48u + 16u * TC_BLOCK_M + 8u * i, 1);   // residual boxes landed (epi_tma)
@@ -199,6 +225,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         if (++s == S) { s = 0; ph ^= 1u; }
         if (it >= lag) {
           cp_async_wait_dyn<TC_MAX_LAG>(lag);
+          if (x3) split_own_chunks(sA + (uint32_t)(as * a_stage) + dst0, sw_even, sw_odd, (uint32_t)a_half);
           fence_proxy_async();
           mbar_arrive(bar_full + 8u * as);
           if (++as == S) as = 0;
@@ -206,8 +233,26 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       }
     }
     cp_async_wait<0>();
-    fence_proxy_async();
-    for (int k = max(it - lag, 0); k < it; ++k) { mbar_arrive(bar_full + 8u * as); if (++as == S) as = 0; }
+    for (int k = max(it - lag, 0); k < it; ++k) {
+      if (x3) split_own_chunks(sA + (uint32_t)(as * a_stage) + dst0, sw_even, sw_odd, (uint32_t)a_half);
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8u * as);
+      if (++as == S) as = 0;
+    }
+    } else if (x3) {
+      // ===== 3xTF32 splitters (TMA mode): the stage's activation tile has landed -> hi in place, lo beside it ==========
+      const uint32_t n16 = (uint32_t)a_half >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(bar_full + 8u * s, ph);
+          const uint32_t base = sA + (uint32_t)(s * a_stage);
+          for (uint32_t i = (uint32_t)tid; i < n16; i += TC_PRODUCERS) split_chunk(base + (i << 4), (uint32_t)a_half);
+          fence_proxy_async();                                  // generic-proxy writes -> visible to tcgen05.mma
+          mbar_arrive(bar_split + 8u * s);
+          if (++s == S) { s = 0; ph ^= 1u; }
+        }
     }
   } else if (warp == 4) {
     // ===== MMA issuer: all lanes walk the loops (uniform operands), one elected lane issues (tc_ptx.h: elect_one) ========
@@ -225,11 +270,19 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.block_n);
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(bar_full + 8u * s, ph);
+        mbar_wait(((x3 && p.tma) ? bar_split : bar_full) + 8u * s, ph);
         tc_fence_after();
         const int kleft = p.Ktot - kb * kbe;
         const int nk = (kleft >= kbe ? kbe : kleft) / UK;
         const uint32_t aa = sA + (uint32_t)(s * a_stage), bb = sB + (uint32_t)(s * b_stage);
+        if (x3) {
+          for (int kk = 0; kk < nk; ++kk)
+            if (leader) {                                        // small terms first, the leading product last
+              umma<TF32>(tmem_d, umma_desc_at(aa + (uint32_t)a_half + 32u * kk, dhi), umma_desc_at(bb + 32u * kk, dhi), idesc, (kb | kk) != 0);
+              umma<TF32>(tmem_d, umma_desc_at(aa + 32u * kk, dhi), umma_desc_at(bb + (uint32_t)b_half + 32u * kk, dhi), idesc, 1u);
+              umma<TF32>(tmem_d, umma_desc_at(aa + 32u * kk, dhi), umma_desc_at(bb + 32u * kk, dhi), idesc, 1u);
+            }
+        } else
         for (int kk = 0; kk < nk; ++kk)
           if (leader) umma<TF32>(tmem_d, umma_desc_at(aa + 32u * kk, dhi), umma_desc_at(bb + 32u * kk, dhi), idesc, (kb | kk) != 0);
         if (leader) {
@@ -246,9 +299,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     // All lanes walk the loops, one elected lane issues (uniform operands; tc_ptx.h: elect_one) ============================
     {
       const bool leader = elect_one();
-      const size_t kb_stride = (size_t)a.Cout * p.row_bytes;
+      const size_t kb_stride = (size_t)a.Cout * p.row_bytes * (x3 ? 2 : 1);    // 3xTF32 image: [kb][hi | lo][Cout][row]
       const int kbe = p.row_bytes / ESZ;
-      const uint32_t tx = (uint32_t)b_stage + (p.tma ? (uint32_t)a_stage : 0u);
+      const uint32_t tx = (uint32_t)b_stage + (p.tma ? (uint32_t)a_half : 0u);
       int it = 0, s = 0;
       uint32_t ph = 1;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -263,7 +316,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           if (leader) {
             mbar_arrive_expect_tx(bar, tx);
             if (p.tma) tma_load_4d(sA + (uint32_t)(s * a_stage), p.tmap, c, x0 + fs, y0 + fr, b0, bar);
-            bulk_g2s(sB + (uint32_t)(s * b_stage), wsrc + kb * kb_stride, (uint32_t)b_stage, bar);
+            bulk_g2s(sB + (uint32_t)(s * b_stage), wsrc + kb * kb_stride, (uint32_t)b_half, bar);
+            if (x3) bulk_g2s(sB + (uint32_t)(s * b_stage + b_half), wsrc + kb * kb_stride + (size_t)a.Cout * p.row_bytes, (uint32_t)b_half, bar);
           }
           if (p.tma) {
             c += kbe;
@@ -611,7 +665,7 @@ __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restric
 
 size_t tc_stage_bytes(int block_n, int row_bytes) { return (size_t)(TC_BLOCK_M + block_n) * row_bytes; }
 size_t tc_staging_bytes(int block_n, int esz) { return ((size_t)TC_BLOCK_M * (block_n * esz + 16) + 127) / 128 * 128; }
-size_t tc_tail_bytes() { return 16 * TC_MAX_STAGES + 16 + 16 + 16 + 8 * TC_BLOCK_M + 8 * TC_BLOCK_M + 64; }
+size_t tc_tail_bytes() { return 16 * TC_MAX_STAGES + 16 + 16 + 16 + 8 * TC_BLOCK_M + 8 * TC_BLOCK_M + 16 + 8 * TC_MAX_STAGES + 48; }
 
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -678,9 +732,12 @@ int conv_tc_row_bytes(const ConvArgs& a, int tf32, int* use_tma) {
 int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st) {
   if (!conv_tc_supported(a, tf32))
     return fail(HRP_ERR_INVALID, "conv_tc: unsupported shape Cin=%d Cout=%d ld=%d coff=%d", a.Cin, a.Cout, a.ld_out, a.out_coff);
-  if (!a.tma_custom && conv_slab_supported(a, tf32)) return conv_slab_launch(a, tf32, round_tf32, st);
+  const bool x3 = tf32 && a.x3;
+  if (!a.tma_custom && !x3 && conv_slab_supported(a, tf32)) return conv_slab_launch(a, tf32, round_tf32, st);
   TcParams p{};
   p.a = a;
+  p.x3 = x3 ? 1 : 0;
+  const int opnd = x3 ? 2 : 1;                              // operand tiles per stage
   p.M = a.B * a.Ho * a.Wo;
   if (p.M <= 0) return HRP_OK;
   const int esz = tf32 ? 4 : 2;
@@ -762,21 +819,21 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     // the store of tile li drain under tile li+1 (64->256 @64x64: 78 -> 70.5 us with residual, 46.8 -> 39.1 us without).
     static const int no_short_stg = env_int("HRP_TC_NO_SHORT_STG2", 0);
     const int min_stages = (short_k && !no_short_stg) ? 1 : 3;
-    p.n_stg = (2048 + 2 * one + tc_tail_bytes() + min_stages * tc_stage_bytes(bn, p.row_bytes) <= budget) ? 2 : 1;
+    p.n_stg = (2048 + 2 * one + tc_tail_bytes() + min_stages * opnd * tc_stage_bytes(bn, p.row_bytes) <= budget) ? 2 : 1;
     staging = (p.n_stg * one + 1023) / 1024 * 1024;
     static const int no_prefetch = env_int("HRP_TC_NO_RES_PREFETCH", 0);
     p.res_prefetch = (p.n_stg == 2 && a.res != nullptr && !no_prefetch) ? 1 : 0;
   }
   const size_t fixed = 2048 + staging + tc_tail_bytes();
-  int smax = (int)((budget - fixed) / tc_stage_bytes(bn, p.row_bytes));
+  int smax = (int)((budget - fixed) / (opnd * tc_stage_bytes(bn, p.row_bytes)));
   smax = std::max(1, std::min(smax, TC_MAX_STAGES));
   if (force_stages) smax = std::max(1, std::min(force_stages, smax));
   p.stages = smax;                                          // the ring runs across tiles, so depth is not tied to num_kb
   const long long kb_per_cta = (long long)p.num_kb * ceil_div(p.total_tiles, sms * ctas);
   if (kb_per_cta < p.stages) p.stages = (int)std::max(1LL, kb_per_cta);
   p.lag = std::min(TC_MAX_LAG, p.stages - 1);
-  p.round_tf32 = round_tf32;
-  p.stg_off = (int)((p.stages * tc_stage_bytes(bn, p.row_bytes) + 1023) / 1024 * 1024);
+  p.round_tf32 = x3 ? 0 : round_tf32;                       // 3xTF32 layers exchange full fp32 activations
+  p.stg_off = (int)((p.stages * opnd * tc_stage_bytes(bn, p.row_bytes) + 1023) / 1024 * 1024);
   p.bar_off = p.stg_off + (int)staging;
   int cl = 0;
   while ((16 << cl) < bn * esz) ++cl;
@@ -822,16 +879,21 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
 // [K][Cout] fp32 (BN folded, k = (r*KW+s)*Cin + c) -> [num_kb][Cout][row_bytes] K-major rows, 16-byte chunks XOR-swizzled
 // exactly as the SWIZZLE_128B (chunk ^ (row & 7)) / SWIZZLE_64B (chunk ^ ((row >> 1) & 3)) operand layouts expect; K
 // zero-padded to a whole k-block.
-size_t pack_conv_tc_bytes(int K, int Cout, int tf32, int row_bytes) { return (size_t)ceil_div(K, row_bytes / (tf32 ? 4 : 2)) * Cout * row_bytes; }
+// tf32 == 2: the 3xTF32 image [num_kb][hi | lo][Cout][row_bytes], hi = rna_tf32(w), lo = rna_tf32(w - hi).
+size_t pack_conv_tc_bytes(int K, int Cout, int tf32, int row_bytes) {
+  return (size_t)ceil_div(K, row_bytes / (tf32 ? 4 : 2)) * Cout * row_bytes * (tf32 == 2 ? 2 : 1);
+}
 
 void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, void* out) {
   const int ce = tf32 ? 4 : 8, chunks = row_bytes / 16, kb_elems = chunks * ce;
   const int num_kb = ceil_div(K, kb_elems);
   uint8_t* o = static_cast<uint8_t*>(out);
   std::memset(o, 0, pack_conv_tc_bytes(K, Cout, tf32, row_bytes));
+  const bool x3 = tf32 == 2;
+  auto rna = [](float v) { uint32_t u; std::memcpy(&u, &v, 4); if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & ~0x1fffu; float r; std::memcpy(&r, &u, 4); return r; };
   for (int kb = 0; kb < num_kb; ++kb)
     for (int n = 0; n < Cout; ++n) {
-      uint8_t* row = o + ((size_t)kb * Cout + n) * row_bytes;
+      uint8_t* row = o + ((size_t)kb * (x3 ? 2 : 1) * Cout + n) * row_bytes;
       const int sw = row_bytes == 128 ? (n & 7) : ((n >> 1) & 3);
       for (int j = 0; j < chunks; ++j) {
         uint8_t* chunk = row + ((j ^ sw) << 4);
@@ -840,10 +902,9 @@ void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, v
           if (k >= K) continue;
           const float v = w_kn[(size_t)k * Cout + n];
           if (tf32) {
-            uint32_t u;
-            std::memcpy(&u, &v, 4);
-            if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & ~0x1fffu;     // cvt.rna.tf32
-            std::memcpy(chunk + e * 4, &u, 4);
+            const float hi = rna(v);                                                  // cvt.rna.tf32
+            std::memcpy(chunk + e * 4, &hi, 4);
+            if (x3) { const float lo = rna(v - hi); std::memcpy(chunk + (size_t)Cout * row_bytes + e * 4, &lo, 4); }
           } else {
             uint32_t u;
             std::memcpy(&u, &v, 4);

@@ -539,7 +539,7 @@ extern "C" int hrp_fk_create(const hrp_fk_program* p, hrp_fk** out) {
     else if (fk_matches(T, fk_raw_kuka)) fk->robot = FK_KUKA;
     else if (fk_matches(T, fk_raw_baxter)) fk->robot = FK_BAXTER;
   }
-  if (fk->smem > 200 * 1024) { delete fk; return fail(HRP_ERR_INVALID, "hrp_fk_create: program needs %zu B shared memory", fk->smem); }
+  if (fk->smem > 200 * 1024) { const size_t need = fk->smem; delete fk; return fail(HRP_ERR_INVALID, "hrp_fk_create: program needs %zu B shared memory", need); }
   if (fk->smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(fk_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk->smem);
     if (e != cudaSuccess) {

@@ -34,6 +34,8 @@ struct ConvArgs {
   // storing logits, each 128-pixel x 64-bin tile reduces its own online-softmax state and writes one 5-float partial to
   // sa_partial[(frame*keypoints + keypoint) * (Ho*Wo/128) + tile] for softargmax_finalize_launch. `out` is not written.
   float* sa_partial;
+  // TF32 family only: 3xTF32 (conv_tc.cu). `w` is the pack_conv_tc(tf32 = 2) image, `in` / `res` / `out` are full fp32.
+  int x3;
 };
 
 int conv_f32_launch(const ConvArgs& a, cudaStream_t s);
@@ -51,7 +53,7 @@ int conv_slab_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s
 // whether its activations will arrive by TMA tensor copies or by the cp.async gather.
 int conv_tc_row_bytes(const ConvArgs& a, int tf32, int* use_tma);
 size_t pack_conv_tc_bytes(int K, int Cout, int tf32, int row_bytes);
-void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, void* out);   // from pack_conv_f32's [K][Cout]
+void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, void* out);   // from pack_conv_f32's [K][Cout]; tf32 = 2: 3xTF32 image
 // One whole BasicBlock (two 3x3/s1/p1 convs, Cin == Cout == C, BN folded, ReLU, identity residual) in one launch
 // (conv_block.cu): bf16 NHWC in/out, w1/w2 = pack_conv_tc images (64-byte operand rows), b1/b2 folded biases.
 struct BlockArgs {
@@ -93,7 +95,7 @@ int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, vo
 // 32 elements = one 64-byte (bf16) / 128-byte (TF32) operand row, fetched by TMA through a view whose "ox" dimension
 // has a 2-pixel byte stride (overlapping windows). Taps s >= K and channel 3 carry zero weights.
 constexpr int STEM_PAD = 3, STEM_HP = 256 + 2 * STEM_PAD, STEM_WP = 264;
-int stem_pack_launch(const float* in_nchw, void* out, int B, int tf32, cudaStream_t s);
+int stem_pack_launch(const float* in_nchw, void* out, int B, int tf32 /*0 bf16, 1 fp32 rounded to TF32, 2 fp32 as is (3xTF32)*/, cudaStream_t s);
 
 int maxpool3x3s2_launch(const void* in, void* out, int B, int Hi, int Wi, int C, int bf16, cudaStream_t s);
 

@@ -58,6 +58,7 @@ struct OpDesc {
   int Hi = 1, Wi = 1, Cin = 0, Ho = 1, Wo = 1, Cout = 0, KH = 1, KW = 1, stride = 1, pad_h = 0, pad_w = 0;
   int out_sy = 1, out_sx = 1, out_oy = 0, out_ox = 0, Ho_full = 1, Wo_full = 1, relu = 0, out_nchw = 0;
   int res_after_act = 0;
+  int x3 = 0;            // TF32 families: this layer runs as 3xTF32 (hi/lo operand split, conv_tc.cu) on full-fp32 activations
   int stem_tc = 0;       // OP_CONV over the packed stem image (custom TMA view); KH = real kernel size, pad_h = real padding
   int same[4] = {-1, -1, -1, -1}, low[3] = {-1, -1, -1}, shift[3] = {0, 0, 0}, n_same = 0, n_low = 0;
   int ld = 0, coff = 0, state_stride = 0, dof = 0, N = 0;
@@ -287,9 +288,10 @@ struct GraphBuilder {
   int prec = HRP_PREC_FP32;
   int cur_lane = 0;
   int phase_lane0 = 0;   // first of three extra lanes for the deconv phases (0: keep them on the caller's lane)
-  void push(OpDesc op) { op.lane = cur_lane; h->ops.push_back(op); }
+  bool x3 = false;       // the sub-network being built runs its convs as 3xTF32 (set per backbone in build())
+  void push(OpDesc op) { op.lane = cur_lane; op.x3 = x3 ? 1 : 0; h->ops.push_back(op); }
   bool tc() const { return prec != HRP_PREC_FP32; }
-  bool tf32() const { return prec == HRP_PREC_TF32; }
+  bool tf32() const { return prec == HRP_PREC_TF32 || prec == HRP_PREC_TF32X3; }
 
   const float* W(const std::string& name) {
     auto it = h->host.find(name);
@@ -334,8 +336,9 @@ struct GraphBuilder {
     Layer L; L.Cout = Cout; L.Cin = Cin; L.KH = KH; L.KW = KW; L.bias = dbias;
     if (tc()) {
       const int rb = conv_tc_row_bytes(g, tf32(), nullptr);
-      std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32(), rb));
-      pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32(), rb, img.data());
+      const int mode = tf32() ? (x3 ? 2 : 1) : 0;
+      std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, mode, rb));
+      pack_conv_tc(wp.data(), KH * KW * Cin, Cout, mode, rb, img.data());
       L.w_tc = upload_bytes(img);
     } else {
       L.w = upload(wp);
@@ -746,6 +749,13 @@ struct GraphBuilder {
     h->t_flags = special(T_FLAGS, 0);
     for (int f = 0; f < HRP_NUM_FIELDS; ++f) { h->field_width[f] = fw[f]; h->t_field[f] = special(T_FIELD, fw[f], f); }
 
+    // 3xTF32: everywhere in the tf32x3 family; in the tf32 family on the layers of an HRNet-W32 KEYPOINT
+    // backbone, whose ~110 sequential single-pass TF32 layers in front of the joint-angle heads measured 1.8e-3 rad against
+    // the 1e-3 rad gate (the ResNet-50 keypoint backbone and the DepthNet stay single-pass: 5.4e-4 rad, 0.2 mm)
+    const bool x3_all = prec == HRP_PREC_TF32X3;
+    bool x3_kp = x3_all || (prec == HRP_PREC_TF32 && h->cfg.backbone == HRP_BACKBONE_HRNET32);
+    if (const char* e = getenv("HRP_TF32_X3_KEYPOINT")) x3_kp = x3_all || (prec == HRP_PREC_TF32 && atoi(e) != 0);
+    x3 = x3_all;
     // DepthNet: lanes 0-3 (one per HRNet branch); its head ends on lane 3
     Tn img_feat = hrnet(h->t_xroot, "rootnet_backbone.", 0, nullptr, 0);
     h->tensors[img_feat.id].keep = true; h->debug["img_feat"] = img_feat.id;
@@ -762,6 +772,7 @@ struct GraphBuilder {
     // regression heads and FK run on their own lane beside the deconv head
     Tn xf, logits;
     int kp_lane = 4, head_lane = 5;
+    x3 = x3_kp;
     if (h->cfg.backbone == HRP_BACKBONE_RESNET50) {
       cur_lane = kp_lane;
       Tn x = resnet50(h->t_xreg, "reg_backbone.");
@@ -777,6 +788,7 @@ struct GraphBuilder {
       xf = hrnet(h->t_xreg, "reg_backbone.", nk * 64, &logits, 4);
       head_lane = 8;                       // xf ends on lane 7, the logits on lane 4
     }
+    x3 = false;
     h->n_lanes = head_lane + 1 + (phase_lane0 > 0 ? 3 : 0);
     if (status != HRP_OK) return status;
     cur_lane = kp_lane;
@@ -1017,7 +1029,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
   };
   auto reads_image = [&](const OpDesc& o) { return o.in == h->t_xreg || o.in == h->t_xroot; };
   int64_t launches = 0;
-  const int bf16 = h->cfg.precision == HRP_PREC_BF16 ? 1 : 0, tf32 = h->cfg.precision == HRP_PREC_TF32 ? 1 : 0;
+  const int bf16 = h->cfg.precision == HRP_PREC_BF16 ? 1 : 0, tf32 = (h->cfg.precision == HRP_PREC_TF32 || h->cfg.precision == HRP_PREC_TF32X3) ? 1 : 0;
   std::vector<cudaEvent_t> op_event(h->ops.size(), nullptr);
   auto new_event = [&]() -> cudaEvent_t {
     cudaEvent_t e = nullptr;
@@ -1054,7 +1066,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         a.B = B; a.Hi = o.Hi; a.Wi = o.Wi; a.Cin = o.Cin; a.Ho = o.Ho; a.Wo = o.Wo; a.Cout = o.Cout;
         a.KH = o.KH; a.KW = o.KW; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w;
         a.out_sy = o.out_sy; a.out_sx = o.out_sx; a.out_oy = o.out_oy; a.out_ox = o.out_ox; a.Ho_full = o.Ho_full; a.Wo_full = o.Wo_full;
-        a.relu = o.relu; a.out_nchw = o.out_nchw; a.ld_out = o.ld; a.out_coff = 0; a.res_after_act = o.res_after_act;
+        a.relu = o.relu; a.out_nchw = o.out_nchw; a.ld_out = o.ld; a.out_coff = 0; a.res_after_act = o.res_after_act; a.x3 = o.x3;
         if (o.stem_tc) {
           // view of the packed image: {window 32 el, ox (2-pixel stride), padded row, frame}; the window of output
           // column ox starts at padded x = 2*ox + STEM_PAD - pad (o.pad_w carries the real padding)
@@ -1104,7 +1116,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         break;
       }
       case OP_STEM_PACK:
-        HRP_TRY(stem_pack_launch(static_cast<const float*>(ptr(o.in)), ptr(o.out), B, tf32, st_op));
+        HRP_TRY(stem_pack_launch(static_cast<const float*>(ptr(o.in)), ptr(o.out), B, tf32 ? (o.x3 ? 2 : 1) : 0, st_op));
         break;
       case OP_MAXPOOL:
         HRP_TRY(maxpool3x3s2_launch(ptr(o.in), ptr(o.out), B, o.Hi, o.Wi, o.Cin, bf16, st_op));
@@ -1113,7 +1125,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         FuseArgs a{};
         for (int k = 0; k < o.n_same; ++k) a.same[k] = ptr(o.same[k]);
         for (int k = 0; k < o.n_low; ++k) { a.low[k] = ptr(o.low[k]); a.shift[k] = o.shift[k]; }
-        a.n_same = o.n_same; a.n_low = o.n_low; a.out = ptr(o.out); a.B = B; a.H = o.Ho; a.W = o.Wo; a.C = o.Cout; a.relu = o.relu; a.round_tf32 = tf32;
+        a.n_same = o.n_same; a.n_low = o.n_low; a.out = ptr(o.out); a.B = B; a.H = o.Ho; a.W = o.Wo; a.C = o.Cout; a.relu = o.relu; a.round_tf32 = tf32 && !o.x3;
         HRP_TRY(fuse_sum_launch(a, bf16, st_op));
         break;
       }
@@ -1198,8 +1210,8 @@ extern "C" int hrp_create(const hrp_config* cfg, const hrp_fk_program* robot, in
   if (!cfg || !robot || !out) return fail(HRP_ERR_INVALID, "hrp_create: null argument");
   if (cfg->backbone != HRP_BACKBONE_RESNET50 && cfg->backbone != HRP_BACKBONE_HRNET32)
     return fail(HRP_ERR_INVALID, "hrp_create: unsupported backbone %d (resnet50 or hrnet32)", cfg->backbone);
-  if (cfg->precision != HRP_PREC_FP32 && cfg->precision != HRP_PREC_TF32 && cfg->precision != HRP_PREC_BF16)
-    return fail(HRP_ERR_INVALID, "hrp_create: unknown precision %d (0 fp32, 1 tf32, 2 bf16)", cfg->precision);
+  if (cfg->precision != HRP_PREC_FP32 && cfg->precision != HRP_PREC_TF32 && cfg->precision != HRP_PREC_BF16 && cfg->precision != HRP_PREC_TF32X3)
+    return fail(HRP_ERR_INVALID, "hrp_create: unknown precision %d (0 fp32, 1 tf32, 2 bf16, 3 tf32x3)", cfg->precision);
   if (cfg->n_iter < 1 || cfg->n_iter > 16) return fail(HRP_ERR_INVALID, "hrp_create: n_iter %d out of range", cfg->n_iter);
   if (cfg->image_size != 256.0f) return fail(HRP_ERR_INVALID, "hrp_create: only 256x256 inputs are supported (got %g)", cfg->image_size);
   std::unique_ptr<hrp_handle> h(new hrp_handle());
@@ -1498,7 +1510,7 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
                                int B, int Hi, int Wi, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu,
                                int precision, void* stream) {
   if (!in || !weight_oihw || !out) return fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: null argument");
-  if (precision != HRP_PREC_FP32 && precision != HRP_PREC_TF32 && precision != HRP_PREC_BF16)
+  if (precision != HRP_PREC_FP32 && precision != HRP_PREC_TF32 && precision != HRP_PREC_BF16 && precision != HRP_PREC_TF32X3)
     return fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: unknown precision %d", precision);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nw = (size_t)Cout * Cin * KH * KW;
@@ -1532,11 +1544,13 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
     if (rs == HRP_OK) rs = conv_f32_launch(a, st);
   } else if (rs == HRP_OK) {
     // tensor-core families: operands converted to the family's activation type exactly as a producing layer would
-    const int tf32 = precision == HRP_PREC_TF32;
+    const int x3 = precision == HRP_PREC_TF32X3;                // 3xTF32: full-fp32 operands, hi/lo split inside the kernel
+    const int tf32 = precision == HRP_PREC_TF32 || x3;
+    a.x3 = x3;
     if (!conv_tc_supported(a, tf32)) rs = fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: shape not supported by the tensor-core family (Cin %% %d, Cout %% 16)", tf32 ? 16 : 32);
     const int rb = conv_tc_row_bytes(a, tf32, nullptr);
-    std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32, rb));
-    pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32, rb, img.data());
+    std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32 ? 1 + x3 : 0, rb));
+    pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32 ? 1 + x3 : 0, rb, img.data());
     void* dw = dalloc(img.size());
     const size_t es = tf32 ? 4 : 2;
     void* din = dalloc(n_in * es);
@@ -1544,8 +1558,10 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
     void* dout = tf32 ? static_cast<void*>(out) : dalloc(n_out * es);
     if (rs == HRP_OK && (!dw || !din || !dout || (residual && !dres))) rs = fail(HRP_ERR_NOMEM, "hrp_conv2d_nhwc: out of device memory");
     if (rs == HRP_OK && cudaMemcpyAsync(dw, img.data(), img.size(), cudaMemcpyHostToDevice, st) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: copy failed");
-    if (rs == HRP_OK) rs = tf32 ? round_tf32_launch(in, static_cast<float*>(din), n_in, st) : cast_f32_to_bf16_launch(in, din, n_in, st);
-    if (rs == HRP_OK && residual) rs = tf32 ? round_tf32_launch(residual, static_cast<float*>(dres), n_out, st) : cast_f32_to_bf16_launch(residual, dres, n_out, st);
+    if (rs == HRP_OK && x3 && cudaMemcpyAsync(din, in, n_in * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: copy failed");
+    if (rs == HRP_OK && x3 && residual && cudaMemcpyAsync(dres, residual, n_out * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: copy failed");
+    if (rs == HRP_OK && !x3) rs = tf32 ? round_tf32_launch(in, static_cast<float*>(din), n_in, st) : cast_f32_to_bf16_launch(in, din, n_in, st);
+    if (rs == HRP_OK && !x3 && residual) rs = tf32 ? round_tf32_launch(residual, static_cast<float*>(dres), n_out, st) : cast_f32_to_bf16_launch(residual, dres, n_out, st);
     a.in = din; a.w = dw; a.res = dres; a.out = dout;
     if (rs == HRP_OK) rs = conv_tc_launch(a, tf32, tf32, st);
     if (rs == HRP_OK && !tf32) rs = cast_bf16_to_f32_launch(dout, out, n_out, st);

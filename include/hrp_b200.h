@@ -38,8 +38,12 @@ typedef enum { HRP_F32 = 0, HRP_I64 = 1 } hrp_dtype;
 typedef enum {
   HRP_PREC_FP32 = 0,        /* fp32 FFMA implicit GEMM: parity mode for every configuration */
   HRP_PREC_TF32 = 1,        /* tcgen05 kind::tf32, operands rounded to nearest TF32, fp32 accumulate in TMEM: parity
-                               mode on the shipped configuration */
-  HRP_PREC_BF16 = 2         /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+                               mode; single-pass on the ResNet-50 keypoint backbone and the DepthNet, 3xTF32 (below) on
+                               the layers of an HRNet-W32 keypoint backbone */
+  HRP_PREC_BF16 = 2,        /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+  HRP_PREC_TF32X3 = 3       /* 3xTF32 on every conv layer: operands split into hi + lo TF32 halves, three tcgen05 products
+                               per k-step (Ahi Whi + Alo Whi + Ahi Wlo), fp32-grade results at a third of the TF32 rate.
+                               HRP_PREC_TF32 itself uses it on the layers of an HRNet-W32 KEYPOINT backbone */
 } hrp_precision;
 
 typedef enum { HRP_BACKBONE_RESNET50 = 0, HRP_BACKBONE_HRNET32 = 1 } hrp_backbone;
