@@ -18,7 +18,7 @@ EXPORTS = (
     "hrp_fk_create", "hrp_fk_destroy", "hrp_fk_project", "hrp_softargmax3d_workspace", "hrp_softargmax3d",
     "hrp_conv2d_nhwc", "hrp_basic_block_nhwc", "hrp_basic_chain_nhwc", "hrp_create", "hrp_destroy", "hrp_num_weights", "hrp_weight_name", "hrp_weight_shape",
     "hrp_set_weight", "hrp_finalize_weights", "hrp_output_offsets", "hrp_workspace_bytes", "hrp_forward", "hrp_forward_ex",
-    "hrp_forward_timed", "hrp_release_plans",
+    "hrp_forward_timed", "hrp_release_plans", "hrp_forward_u8", "hrp_crop_resize_u8",
     "hrp_set_option", "hrp_launch_count", "hrp_debug_tensor", "hrp_forward_profile", "hrp_conv_bench", "hrp_last_error",
     "hrp_version",
 )
@@ -78,6 +78,8 @@ def lib():
         L.hrp_forward_ex.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, i32, f32p, vp]
         L.hrp_forward_timed.argtypes = [vp, f32p, f32p, f32p, f32p, f32p, f32p, i32, f32p, C.POINTER(C.c_float), vp]
         L.hrp_release_plans.argtypes = [vp]
+        L.hrp_forward_u8.argtypes = [vp, f32p, f32p, f32p, f32p, i32, f32p, vp]
+        L.hrp_crop_resize_u8.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         L.hrp_set_option.argtypes = [vp, C.c_char_p, i64]
         L.hrp_launch_count.argtypes = [vp]
         L.hrp_launch_count.restype = i64

@@ -97,6 +97,11 @@ int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, vo
 constexpr int STEM_PAD = 3, STEM_HP = 256 + 2 * STEM_PAD, STEM_WP = 264;
 int stem_pack_launch(const float* in_nchw, void* out, int B, int tf32 /*0 bf16, 1 fp32 rounded to TF32, 2 fp32 as is (3xTF32)*/, cudaStream_t s);
 
+// Same from uint8 NCHW images with the `/ 255.` of scripts/test.py:93-96 folded in (preprocess.cu); u8 -> fp32 NCHW for the
+// fp32 family's direct stem.
+int stem_pack_u8_launch(const uint8_t* in_nchw, void* out, int B, int mode, cudaStream_t s);
+int u8_to_f32_launch(const uint8_t* in, float* out, size_t n, cudaStream_t s);
+
 int maxpool3x3s2_launch(const void* in, void* out, int B, int Hi, int Wi, int C, int bf16, cudaStream_t s);
 
 // out = relu( sum_i same[i] + sum_j nearest_up(low[j], 2^shift[j]) ), NHWC, up to 4 + 3 terms (HRNet fusion).

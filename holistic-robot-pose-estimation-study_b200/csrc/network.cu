@@ -78,6 +78,7 @@ struct Plan {
   // static staging the graph reads / writes (the images are NOT staged: the ops that read them run ahead of the graph
   // on the caller's pointers, see run_ops' `part`)
   size_t io_kv = 0, io_K = 0, io_out = 0, io_initp = 0, io_initr = 0, io_flags = 0, sa_ws = 0, sa_ws_bytes = 0;
+  size_t io_xf32 = 0;              // fp32 family only: 2 x [B,3,256,256] fp32 for uint8 inputs (the direct stem reads fp32)
   cudaGraphExec_t exec = nullptr;
   cudaEvent_t done = nullptr;      // recorded after the last forward that used this plan
   bool used = false;
@@ -943,6 +944,7 @@ int make_plan(hrp_handle* h, int B, Plan** out, int slot = 0) {
   p->io_initp = fl.alloc(align_up((size_t)B * h->dof * 4, A));
   p->io_initr = fl.alloc(align_up((size_t)B * 6 * 4, A));
   p->io_flags = fl.alloc(A);
+  if (h->cfg.precision == HRP_PREC_FP32) p->io_xf32 = fl.alloc(align_up((size_t)2 * B * 3 * 256 * 256 * 4, A));
   p->io_out = fl.alloc(align_up((size_t)record_floats(h, B, nullptr) * 4, A));
   p->sa_ws_bytes = std::max(softargmax_workspace(B, h->nkpt, 64, 64, 64), (size_t)B * h->nkpt * (64 * 64 / 128) * 5 * sizeof(float));
   p->sa_ws = fl.alloc(align_up(p->sa_ws_bytes, A));
@@ -990,6 +992,7 @@ struct IoPtrs {
   float* out;
   const float *init_pose = nullptr, *init_rot = nullptr;   // optional per-frame initial states (full_net.py:268-272)
   const int* flags = nullptr;                               // graph path: which of the two staged overrides are live
+  const uint8_t *x_reg_u8 = nullptr, *x_root_u8 = nullptr;  // uint8 NCHW crops instead of x_reg / x_root (hrp_forward_u8): `/ 255.` on device
 };
 
 // which ops run_ops enqueues: the ops that read the caller's images (stem / stem_pack, always the first of their lane)
@@ -1056,7 +1059,14 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
     switch (o.kind) {
       case OP_STEM: {
         const Layer& L = h->layers[o.layer];
-        HRP_TRY(stem_conv_launch(static_cast<const float*>(ptr(o.in)), L.w, L.bias, ptr(o.out), B, o.Hi, o.Wi, o.Ho, o.Wo, o.KH, o.KW, o.pad_h, bf16 ? 1 : (tf32 ? 2 : 0), st_op));
+        const float* x = static_cast<const float*>(ptr(o.in));
+        if (io.x_reg_u8) {                                   // uint8 crops: / 255. into the plan's fp32 staging first
+          const bool root = o.in == h->t_xroot;
+          float* dst = reinterpret_cast<float*>(p->ws + p->io_xf32) + (root ? (size_t)B * 3 * 256 * 256 : 0);
+          HRP_TRY(u8_to_f32_launch(root ? io.x_root_u8 : io.x_reg_u8, dst, (size_t)B * 3 * 256 * 256, st_op));
+          x = dst; ++n_launch;
+        }
+        HRP_TRY(stem_conv_launch(x, L.w, L.bias, ptr(o.out), B, o.Hi, o.Wi, o.Ho, o.Wo, o.KH, o.KW, o.pad_h, bf16 ? 1 : (tf32 ? 2 : 0), st_op));
         break;
       }
       case OP_CONV: {
@@ -1116,7 +1126,8 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         break;
       }
       case OP_STEM_PACK:
-        HRP_TRY(stem_pack_launch(static_cast<const float*>(ptr(o.in)), ptr(o.out), B, tf32 ? (o.x3 ? 2 : 1) : 0, st_op));
+        if (io.x_reg_u8) HRP_TRY(stem_pack_u8_launch(o.in == h->t_xroot ? io.x_root_u8 : io.x_reg_u8, ptr(o.out), B, tf32 ? (o.x3 ? 2 : 1) : 0, st_op));
+        else HRP_TRY(stem_pack_launch(static_cast<const float*>(ptr(o.in)), ptr(o.out), B, tf32 ? (o.x3 ? 2 : 1) : 0, st_op));
         break;
       case OP_MAXPOOL:
         HRP_TRY(maxpool3x3s2_launch(ptr(o.in), ptr(o.out), B, o.Hi, o.Wi, o.Cin, bf16, st_op));
@@ -1363,8 +1374,14 @@ extern "C" int64_t hrp_launch_count(const hrp_handle* h) { return h ? h->last_la
 
 namespace {
 int forward_impl(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
-                 const float* init_pose, const float* init_rot, int B, float* out, cudaStream_t st, float* ms3) {
+                 const float* init_pose, const float* init_rot, int B, float* out, cudaStream_t st, float* ms3,
+                 const uint8_t* x_reg_u8 = nullptr, const uint8_t* x_root_u8 = nullptr) {
+  if (x_reg_u8) {                  // the float pointers only serve the null check below
+    x_reg = reinterpret_cast<const float*>(x_reg_u8);
+    x_root = reinterpret_cast<const float*>(x_root_u8);
+  }
   HRP_TRY(check_forward_args(h, x_reg, x_root, k_value, Kmat, B, out));
+  if (x_reg_u8) { x_reg = nullptr; x_root = nullptr; }
   HRP_ON_DEVICE(h);
   Plan* p = nullptr;
   const bool graph = h->use_graph && ms3 == nullptr;
@@ -1381,7 +1398,7 @@ int forward_impl(hrp_handle* h, const float* x_reg, const float* x_root, const f
   // whatever stream used this plan last must be done with its workspace before this forward touches it
   if (p->used) HRP_CUDA(cudaStreamWaitEvent(st, p->done, 0));
   if (!graph) {
-    IoPtrs io{x_reg, x_root, k_value, Kmat, out, init_pose, init_rot, nullptr};
+    IoPtrs io{x_reg, x_root, k_value, Kmat, out, init_pose, init_rot, nullptr, x_reg_u8, x_root_u8};
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     if (ms3) {
       HRP_CUDA(cudaEventCreate(&e0)); HRP_CUDA(cudaEventCreate(&e1)); HRP_CUDA(cudaEventCreate(&e2));
@@ -1423,7 +1440,7 @@ int forward_impl(hrp_handle* h, const float* x_reg, const float* x_root, const f
     p->launches = n_graph;
   }
   int64_t n_pre = 0;
-  HRP_TRY(run_ops(h, p, IoPtrs{x_reg, x_root, nullptr, nullptr, nullptr}, st, nullptr, false, PART_PRE, nullptr, &n_pre));
+  HRP_TRY(run_ops(h, p, IoPtrs{x_reg, x_root, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, x_reg_u8, x_root_u8}, st, nullptr, false, PART_PRE, nullptr, &n_pre));
   HRP_CUDA(cudaMemcpyAsync(s_kv, k_value, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
   HRP_CUDA(cudaMemcpyAsync(s_K, Kmat, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (init_pose) HRP_CUDA(cudaMemcpyAsync(s_ip, init_pose, (size_t)B * h->dof * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1457,6 +1474,12 @@ extern "C" int hrp_forward_timed(hrp_handle* h, const float* x_reg, const float*
                                  const float* init_pose, const float* init_rot, int B, float* out, float* ms3, void* stream) {
   if (!ms3) return fail(HRP_ERR_INVALID, "hrp_forward_timed: null timing output");
   return forward_impl(h, x_reg, x_root, k_value, Kmat, init_pose, init_rot, B, out, (cudaStream_t)stream, ms3);
+}
+
+extern "C" int hrp_forward_u8(hrp_handle* h, const uint8_t* x_reg, const uint8_t* x_root, const float* k_value, const float* Kmat,
+                              int B, float* out, void* stream) {
+  if (!x_reg || !x_root) return fail(HRP_ERR_INVALID, "hrp_forward_u8: null pointer");
+  return forward_impl(h, nullptr, nullptr, k_value, Kmat, nullptr, nullptr, B, out, (cudaStream_t)stream, nullptr, x_reg, x_root);
 }
 
 extern "C" int hrp_release_plans(hrp_handle* h) {

@@ -89,6 +89,36 @@ def soft_argmax(heatmap, nkpt, K=None, root_z=None, depth_factor=1.3, image_size
     return uvd, xyz
 
 
+def crop_resize(frames, crop_box, K, k_box=None):
+    """Input side of the boundary on the device (the reference does this on the CPU in its DataLoader:
+    lib/dataset/dream.py:415-449, roboutils.py:142-171,248-263, augmentations.py:189-262, geometries.py:360-402,
+    lib/core/function.py:98-110).
+
+    frames [B,Hf,Wf,3] uint8 CUDA (HWC camera images), crop_box [B,4] int32 (wmin,hmin,wmax,hmax), K [B,3,3] fp32,
+    k_box [B,4] fp32 strict robot box in frame coordinates (optional)
+    -> (crops [B,3,256,256] uint8 -- feed them to forward_dict / HostPipeline, which apply the `/255.` --, K' [B,3,3],
+        k_value [B] or None)."""
+    if not (frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3):
+        raise ValueError("crop_resize: frames must be a CUDA uint8 tensor [B,H,W,3]")
+    B, Hf, Wf, _ = frames.shape
+    dev = frames.device
+    frames = frames.contiguous()
+    crop_box = torch.as_tensor(crop_box, device=dev).to(torch.int32).reshape(B, 4).contiguous()
+    K = torch.as_tensor(K, device=dev).float().reshape(B, 3, 3).contiguous()
+    crops = torch.empty(B, 3, 256, 256, device=dev, dtype=torch.uint8)
+    K_out = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
+    kv, kb = None, C.c_void_p(0)
+    kvp = C.c_void_p(0)
+    if k_box is not None:
+        k_box = torch.as_tensor(k_box, device=dev).float().reshape(B, 4).contiguous()
+        kv = torch.empty(B, device=dev, dtype=torch.float32)
+        kb, kvp = _ptr(k_box), _ptr(kv)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    capi.check(capi.lib().hrp_crop_resize_u8(_ptr(frames), B, Hf, Wf, _ptr(crop_box), kb, _ptr(K), _ptr(crops), _ptr(K_out), kvp,
+                                              C.c_void_p(st)))
+    return crops, K_out, kv
+
+
 def conv2d_nhwc(x, weight, bias=None, residual=None, stride=1, pad=0, relu=False, precision="fp32"):
     """Single conv through the library (layer-level parity tests). x NHWC, weight OIHW, CUDA fp32."""
     B, Hi, Wi, Cin = x.shape
@@ -291,8 +321,16 @@ class HoliRobPoseB200(torch.nn.Module):
                 times.append((0.0, 0.0, 0.0))
             return torch.empty(0, device=x_reg.device, dtype=torch.float32), [0] * (capi.NUM_FIELDS + 1)
         same = x_root is x_reg                                               # views that merely START at the same address differ
-        x_reg = x_reg.float().contiguous()                                   # full_net.py:265-266
-        x_root = x_reg if same else x_root.float().contiguous()
+        u8 = x_reg.dtype == torch.uint8 and x_root.dtype == torch.uint8 and init_pose is None and init_rot is None and times is None
+        if u8:           # the DataLoader's uint8 crops: `/ 255.` (scripts/test.py:93-96) happens inside the stem's input pack
+            x_reg = x_reg.contiguous()
+            x_root = x_reg if same else x_root.contiguous()
+        else:
+            if x_reg.dtype == torch.uint8 or x_root.dtype == torch.uint8:
+                raise ValueError("uint8 images are taken by forward_dict / forward_record / HostPipeline without init_pose / init_rot / "
+                                 "test_fps; the reference-signature call expects float images already divided by 255 (scripts/test.py:93-96)")
+            x_reg = x_reg.float().contiguous()                               # full_net.py:265-266
+            x_root = x_reg if same else x_root.float().contiguous()
         k_value = torch.as_tensor(k_value, device=x_reg.device).float().reshape(B).contiguous()
         K = K.float().contiguous()
         null = C.c_void_p(0)
@@ -307,7 +345,9 @@ class HoliRobPoseB200(torch.nn.Module):
         rec = torch.empty(offs[-1], device=x_reg.device, dtype=torch.float32)
         st = torch.cuda.current_stream(x_reg.device).cuda_stream
         L = capi.lib()
-        if times is not None:
+        if u8:
+            capi.check(L.hrp_forward_u8(self._h, _ptr(x_reg), _ptr(x_root), _ptr(k_value), _ptr(K), B, _ptr(rec), C.c_void_p(st)))
+        elif times is not None:
             ms = (C.c_float * 3)()
             capi.check(L.hrp_forward_timed(self._h, _ptr(x_reg), _ptr(x_root), _ptr(k_value), _ptr(K), ip, ir, B, _ptr(rec), ms,
                                            C.c_void_p(st)))
@@ -347,7 +387,8 @@ class HoliRobPoseB200(torch.nn.Module):
         return tuple(f[:8]) + ((times[0],) if test_fps else ())
 
     def forward_dict(self, images, K, k_value=None):
-        """north_star convenience: dict of 2-D/3-D keypoints, joint angles, root depth and camera-frame pose."""
+        """north_star convenience: dict of 2-D/3-D keypoints, joint angles, root depth and camera-frame pose.
+        images: float [B,3,256,256] in [0,1], or the DataLoader's uint8 crops (then `/ 255.` happens on the device)."""
         B = images.shape[0]
         if k_value is None:                                                  # scripts/real_test.py:285-289, full-frame bbox
             k_value = torch.sqrt(K[:, 0, 0] * K[:, 1, 1] * 1000.0 * 1000.0 / (self.image_size * self.image_size))
@@ -397,7 +438,7 @@ class HostPipeline:
     pinned (`torch.Tensor.pin_memory()`), otherwise the copies serialise with the host.
 
         pipe = HostPipeline(model, batch=64)
-        t = pipe.submit(images, K, k_value)          # images [B,3,256,256] fp32 in [0,1] (x_reg == x_root, real_test.py:282)
+        t = pipe.submit(images, K, k_value)          # images [B,3,256,256] fp32 in [0,1] or uint8 crops (x_reg == x_root, real_test.py:282)
         out = pipe.result(t)                         # dict of pinned-host views, valid until the slot is reused
     """
 
@@ -408,7 +449,7 @@ class HostPipeline:
         # one compute stream per slot: the library keeps two plans (workspace + graph) per batch size and uses them
         # round-robin, so forwards enqueued on different streams overlap (the tail of batch i with the head of batch i+1)
         self.compute = [torch.cuda.Stream(dev) for _ in range(depth)]
-        self.img = [torch.empty(self.B, 3, 256, 256, device=dev) for _ in range(depth)]
+        self.img = [None] * depth             # device staging, allocated on first use in the dtype the caller submits (fp32 or uint8)
         self.K = [torch.empty(self.B, 3, 3, device=dev) for _ in range(depth)]
         self.kv = [torch.empty(self.B, device=dev) for _ in range(depth)]
         self.offs = model._record(self.B, dev)
@@ -428,6 +469,8 @@ class HostPipeline:
         with torch.cuda.stream(self.copy_stream):
             if self.ev_free[s] is not None:
                 self.copy_stream.wait_event(self.ev_free[s])
+            if self.img[s] is None or self.img[s].dtype != images.dtype:
+                self.img[s] = torch.empty(self.B, 3, 256, 256, device=self.model.device, dtype=images.dtype)
             self.img[s].copy_(images, non_blocking=True)
             self.K[s].copy_(K, non_blocking=True)
             self.kv[s].copy_(k_value, non_blocking=True)

@@ -155,6 +155,35 @@ def make_inputs(batch, seed):
     return make_images(batch, seed), K, kv
 
 
+def make_frames(n, seed, h=480, w=640):
+    """Raw camera frames + boxes for the input-side op (hrp_crop_resize_u8): uint8 HWC [n,h,w,3] (smooth structure plus
+    pixel noise, so bilinear weights matter), integer crop boxes inside the frame (smaller and larger than the 256-pixel
+    crop, non-square), strict robot boxes inside them, and cameras in the range of the datasets' intrinsics."""
+    g = np.random.Generator(np.random.PCG64([int(seed), 9]))
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    frames = np.empty((n, h, w, 3), np.uint8)
+    crop = np.empty((n, 4), np.int32)
+    kbox = np.empty((n, 4), np.float32)
+    K = np.zeros((n, 3, 3), np.float32)
+    for i in range(n):
+        img = np.zeros((h, w, 3), np.float32)
+        for c in range(3):
+            a, b2, ph = g.uniform(0.01, 0.06, 2), g.uniform(0.01, 0.05, 2), g.uniform(0, 6.28, 2)
+            img[..., c] = 110 + 60 * np.sin(a[0] * xx + b2[0] * yy + ph[0]) + 40 * np.cos(a[1] * xx - b2[1] * yy + ph[1])
+        img += g.normal(0, 12, img.shape)
+        frames[i] = np.clip(img, 0, 255).astype(np.uint8)
+        bw, bh = int(g.integers(90, 470)), int(g.integers(90, 470))
+        x0, y0 = int(g.integers(0, w - bw + 1)), int(g.integers(0, h - bh + 1))
+        crop[i] = (x0, y0, x0 + bw, y0 + bh)
+        mx, my = g.uniform(0.05, 0.2, 2) * (bw, bh)
+        kbox[i] = (x0 + mx, y0 + my, x0 + bw - mx * g.uniform(0.5, 1.5), y0 + bh - my * g.uniform(0.5, 1.5))
+        f = g.uniform(500.0, 650.0)
+        K[i] = [[f, 0, w / 2 + g.uniform(-10, 10)], [0, f * g.uniform(0.98, 1.02), h / 2 + g.uniform(-10, 10)], [0, 0, 1]]
+    crop[0] = (100, 50, 356, 306)                # exactly 256 x 256: the reference skips the resize (augmentations.py:193-195)
+    kbox[0] = (120.0, 70.0, 330.0, 290.0)
+    return frames, crop, kbox, K
+
+
 def make_fk_inputs(robot, n, seed):
     """Pose-sweep inputs: q ~ U(JOINT_BOUNDS), noisy rot6d of a random rotation, trans, K."""
     spec = consts.ROBOTS[robot]

@@ -186,6 +186,24 @@ int hrp_forward_ex(hrp_handle* h, const float* x_reg, const float* x_root, const
 int hrp_forward_timed(hrp_handle* h, const float* x_reg, const float* x_root, const float* k_value, const float* Kmat,
                       const float* init_pose, const float* init_rot, int B, float* out, float* ms3 /*[3]*/, void* stream);
 
+/* The forward fed with what the reference's DataLoader hands to the device: uint8 NCHW crops [B,3,256,256]
+ * (`input_batch["root"]["images"]`, lib/dataset/dream.py:441-443); the `.float() / 255.` of scripts/test.py:93-96 /
+ * lib/core/function.py happens on the device inside the stem's input pack. A quarter of the host->device bytes of
+ * hrp_forward; results are bit-identical to hrp_forward on x = u8 / 255. */
+int hrp_forward_u8(hrp_handle* h, const uint8_t* x_reg, const uint8_t* x_root, const float* k_value, const float* Kmat,
+                   int B, float* out, void* stream);
+
+/* Input side of the boundary on the device, replacing the reference's CPU data preparation for
+ * inference: frames [B,Hf,Wf,3] uint8 HWC camera images, crop_box [B,4] int32 (wmin,hmin,wmax,hmax) inside the frame ->
+ * crops [B,3,256,256] uint8 NCHW exactly as the DataLoader builds them: the box pasted into a zero square
+ * (lib/dataset/roboutils.py:142-171), bilinear resize with align_corners=False on /255 floats, truncated back to uint8
+ * (lib/dataset/augmentations.py:189-262); K_in [B,3,3] -> K_out through the paste shift + get_K_crop_resize
+ * (lib/utils/geometries.py:360-402); and, when k_value != NULL, k_box [B,4] float (the strict robot box in FRAME
+ * coordinates) -> bbox_transform + clipping (lib/dataset/dream.py:445-449, roboutils.py:248-263) ->
+ * k_value[b] = sqrt(fx fy 1000^2 / max(|dx|,|dy|)^2) with the new fx, fy (lib/core/function.py:98-110). All device. */
+int hrp_crop_resize_u8(const uint8_t* frames, int B, int Hf, int Wf, const int32_t* crop_box, const float* k_box,
+                       const float* K_in, uint8_t* crops, float* K_out, float* k_value, void* stream);
+
 /* Plans (workspace + CUDA graph) are cached per batch size: at most "max_cached_batches" distinct sizes (default 4, least
  * recently used dropped first), and a second / third plan of a size only when forwards of that size arrive on different
  * streams. hrp_release_plans frees every cached plan now (waits for the forwards that use them); the next forward

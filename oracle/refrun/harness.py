@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY. Used by the golden-vector generator scripts (oracle/refrun/make_golden*.py) to pin the
 oracle port (oracle/*.py) and, through the committed fixtures in tests/golden/, the CUDA path. `/root/reference` does not
-exist on the GPU box, so nothing here may be imported by `-m gpu` tests, `smoke()` or `bench.py`.
+exist on the GPU box, so nothing here may be imported by `-m gpu` tests or `smoke()`; bench.py's reference arm / cpu_baseline
+leg (the one place allowed to execute oracle/ besides the tests) runs it from the travelling copy baseline/_ref/ (see REF).
 
 What it does (recipe from SURVEY.md §8c, nothing in the reference tree is modified or copied):
   * builds a scratch working directory (`data/`, `lib -> /root/reference/lib`, kinematics-only URDFs at the paths
@@ -23,20 +24,27 @@ import tempfile
 import numpy as np
 import torch
 
-REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
+# the reference tree: the read-only original in the build container, else the git-ignored copy of its lib/ + configs/ that
+# __graft_entry__.build() leaves under baseline/_ref/ (it travels to the GPU box with the snapshot; bench.py --impl reference
+# and the cpu_baseline leg time the reference's own forward from it). Never imported by the product package.
+REF = "/root/reference" if os.path.isdir("/root/reference/lib") else os.path.join(REPO, "baseline", "_ref")
 URDF_DIR = os.path.join(REPO, "holistic-robot-pose-estimation-study_b200", "data", "urdf")
 
 _state = {}
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "lib")) and os.path.isdir(os.path.join(REF, "configs"))
 
 
 def setup():
     """Idempotent. Returns a namespace with the reference modules."""
     if _state:
         return _state["ns"]
-    if not os.path.isdir(REF):
-        raise RuntimeError("reference tree not present (this harness only runs in the build container)")
+    if not available():
+        raise RuntimeError("reference tree not present (neither /root/reference nor baseline/_ref)")
     sys.dont_write_bytecode = True
     work = tempfile.mkdtemp(prefix="hrp_refrun_")
     os.makedirs(os.path.join(work, "data", "deps", "panda-description", "patched_urdf"))

@@ -9,6 +9,7 @@ Fixtures (inputs are re-derivable from the recorded seeds through hrp_b200.synth
   fullnet_panda_resnet50_ckpt.npz the factory path get_rootNetwithRegInt_model with `pretrained_rootnet` (full_net.py:470-505:
                                   torch.load, `backbone.` -> `rootnet_backbone.` re-key, strict=False) followed by the evaluator's
                                   checkpoint load (fullnet_test.py:186-198), and a forward with init_pose / init_rot overrides;
+  preprocess.npz                  the input side (8f N2): resize_image + CropResizeToAspectAugmentation + bbox_transform + k_value;
   fk_<robot>.npz                  URDFRobot.get_keypoints[_root] (urdf_robot.py:95-118,193-223) +
                                   point_projection_from_3d_tensor (transforms.py:17-21) over the joint-bound sweep.
 Usage: python -m oracle.refrun.make_golden
@@ -153,10 +154,43 @@ def checkpoint():
           "depth", out["root_depth"].ravel())
 
 
+def preprocess():
+    """The reference's own data-preparation functions on synthetic frames: lib/dataset/roboutils.py resize_image +
+    bbox_transform, lib/dataset/augmentations.py CropResizeToAspectAugmentation (-> get_K_crop_resize), then the k_value
+    expression of lib/core/function.py:98-110, strung together as lib/dataset/dream.py:415-449 does."""
+    import copy
+    harness.setup()
+    from dataset import roboutils, augmentations
+    n, seed = 6, 41
+    frames, crop, kbox, K = synth.make_frames(n, seed)
+    crops, Ks, kvs = [], [], []
+    for i in range(n):
+        state = {"camera": {"K": np.array(K[i], np.float64), "resolution": (640, 480)},
+                 "objects": [{"keypoints_2d": np.zeros((1, 3)), "TCO_keypoints_3d": np.array([[0.1, 0.1, 1.0]]), "bbox": crop[i].copy()}]}
+        K_original = copy.deepcopy(state["camera"]["K"])
+        mask = np.zeros(frames[i].shape[:2], np.uint8)
+        rgb, mask, state = roboutils.resize_image(np.asarray(frames[i]), crop[i], mask, state)
+        m2 = np.ones(rgb.shape[:2], np.uint8)
+        rgb, _, state = augmentations.CropResizeToAspectAugmentation(resize=(256, 256))(rgb, m2, state)
+        rgb = augmentations.to_torch_uint8(rgb).permute(2, 0, 1)
+        K_r = np.asarray(state["camera"]["K"])
+        t = roboutils.bbox_transform(kbox[i], np.linalg.inv(K_original), K_r, resize_hw=(256, 256))
+        t = torch.FloatTensor(np.array([max(0, t[0]), max(0, t[1]), min(256, t[2]), min(256, t[3])]))
+        root_K = torch.FloatTensor(K_r)
+        fx, fy = root_K[0, 0], root_K[1, 1]
+        real_bbox = torch.tensor([1000.0, 1000.0]).to(torch.float32)
+        area = torch.max(torch.abs(t[2] - t[0]), torch.abs(t[3] - t[1])) ** 2
+        kv = torch.sqrt(fx * fy * real_bbox[0] * real_bbox[1] / area)
+        crops.append(rgb.numpy()); Ks.append(root_K.numpy()); kvs.append(float(kv))
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), crops=np.stack(crops), K=np.stack(Ks), k_value=np.asarray(kvs, np.float32),
+                        meta=np.asarray([seed, n], np.int64))
+    print("preprocess", np.stack(crops).shape, "k_value", kvs)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    what = sys.argv[1:] or ["fk", "softargmax", "fullnet", "undamped", "checkpoint"]
+    what = sys.argv[1:] or ["fk", "softargmax", "fullnet", "undamped", "checkpoint", "preprocess"]
     if "fk" in what:
         fk()
     if "softargmax" in what:
@@ -169,3 +203,5 @@ if __name__ == "__main__":
         fullnet(UNDAMPED, recipe="undamped")
     if "checkpoint" in what:
         checkpoint()
+    if "preprocess" in what:
+        preprocess()

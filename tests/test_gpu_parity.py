@@ -621,6 +621,69 @@ def capi_ws(m, B):
     return int(capi.lib().hrp_workspace_bytes(m._h, B))
 
 
+# ---------------------------------------------------------------------------------------------------- input side (8f N2)
+def test_crop_resize_against_reference_golden(dev):
+    """hrp_crop_resize_u8 against what the reference's own data-preparation functions produced on the same frames
+    (tests/golden/preprocess.npz): the no-resize branch is bit-exact; resampled crops differ from ATen's CPU bilinear by at
+    most one uint8 level on a handful of pixels (fused multiply-adds in ATen's vectorised loop), K' and k_value to fp32
+    rounding."""
+    from hrp_b200.model import crop_resize
+    g = helpers.load_golden("preprocess.npz")
+    seed, n = (int(v) for v in g["meta"])
+    frames, crop, kbox, K = synth.make_frames(n, seed)
+    crops, Kn, kv = crop_resize(cu(frames, dev), cu(crop, dev), cu(K, dev), cu(kbox, dev))
+    assert crops.dtype == torch.uint8 and crops.shape == (n, 3, 256, 256)
+    d = (crops.cpu().numpy().astype(np.int32) - g["crops"].astype(np.int32))
+    assert np.array_equal(crops[0].cpu().numpy(), g["crops"][0])                      # 256 x 256 box: copied, not resampled
+    assert np.abs(d).max() <= 1 and (d != 0).mean() < 2e-3, (np.abs(d).max(), (d != 0).mean())
+    assert helpers.maxdiff(Kn, g["K"]) < 2e-4
+    np.testing.assert_allclose(kv.cpu().numpy(), g["k_value"], rtol=2e-6)
+    c2, K2, none = crop_resize(cu(frames, dev), cu(crop, dev), cu(K, dev))            # without the strict box
+    assert none is None and torch.equal(c2, crops) and torch.equal(K2, Kn)
+    # more boxes than the fixture holds, against the oracle port (which the CPU suite pins to the fixture)
+    from oracle import preprocess
+    frames, crop, kbox, K = synth.make_frames(12, 7)
+    crops, Kn, kv = crop_resize(cu(frames, dev), cu(crop, dev), cu(K, dev), cu(kbox, dev))
+    for i in range(12):
+        c, Kr, kr = preprocess.crop_resize_one(frames[i], crop[i], K[i], kbox[i])
+        dd = crops[i].cpu().numpy().astype(np.int32) - c.astype(np.int32)
+        assert np.abs(dd).max() <= 1 and (dd != 0).mean() < 2e-3, i
+        assert helpers.maxdiff(Kn[i], Kr) < 2e-4 and abs(float(kv[i]) - float(kr)) < 2e-6 * float(kr)
+    e = crop_resize(cu(frames[:0], dev), cu(crop[:0], dev), cu(K[:0], dev))
+    assert e[0].shape == (0, 3, 256, 256)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "tf32"])
+def test_forward_from_uint8_crops_equals_forward_on_divided_floats(prec, dev):
+    """hrp_forward_u8: the DataLoader's uint8 crops with the `/ 255.` of scripts/test.py:93-96 folded into the stem's input
+    pack -- bit-identical to the float path on x = u8 / 255, through forward_dict and through HostPipeline; and the whole
+    input side chained (frames -> crop_resize -> forward) against the oracle end to end."""
+    from hrp_b200.model import HostPipeline, crop_resize
+    m = gpu_model("panda", "resnet50", dev, prec)
+    frames, crop, kbox, K = synth.make_frames(5, 23)
+    crops, Kn, kv = crop_resize(cu(frames, dev), cu(crop, dev), cu(K, dev), cu(kbox, dev))
+    a = m.forward_dict(crops, Kn, kv)
+    b = m.forward_dict(crops.float() / 255.0, Kn, kv)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    a2 = m.forward_record(crops, crops.clone(), kv, Kn)[0]                            # distinct reg / root buffers
+    assert torch.equal(a2, m.forward_record(crops.float() / 255.0, crops.float() / 255.0, kv, Kn)[0])
+    pipe = HostPipeline(m, 5)
+    t = pipe.submit(crops.cpu().pin_memory(), Kn.cpu().pin_memory(), kv.cpu().pin_memory())
+    got = pipe.result(t)
+    for k in a:
+        assert torch.equal(a[k].cpu(), got[k]), k
+    with pytest.raises(ValueError, match="uint8"):
+        m(crops, crops, kv, Kn, test_fps=True)
+    if prec == "fp32":
+        from oracle import preprocess
+        om, _ = helpers.oracle_for("panda", "resnet50")
+        ref_in = [preprocess.crop_resize_one(frames[i], crop[i], K[i], kbox[i]) for i in range(5)]
+        x = torch.from_numpy(np.stack([r[0] for r in ref_in])).float() / 255.0
+        ref = om.forward_dict(x, x, torch.from_numpy(np.stack([r[2] for r in ref_in])), torch.from_numpy(np.stack([r[1] for r in ref_in])))
+        check_gates(a, ref)
+
+
 # ---------------------------------------------------------------------------------------------------- families at config scale
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
 @pytest.mark.parametrize("robot,B", [("panda", 64), ("kuka", 256), ("baxter", 128)])

@@ -114,3 +114,18 @@ def test_checkpoint_merge_and_init_overrides_match_reference():
     assert helpers.maxdiff(o2[7], g["ovr_kp3d_fk"]) < 2e-5
     assert helpers.maxdiff(o2[0], res["joint_angles"]) > 1e-2          # the override matters
     assert len(trace["pose_iters"]) == 4
+
+
+def test_preprocess_matches_reference():
+    """Input side (8f N2): the port of resize_image + CropResizeToAspectAugmentation + get_K_crop_resize + bbox_transform +
+    k_value against what the reference's own functions produced (bit-exact crops: same torch CPU interpolate)."""
+    from oracle import preprocess
+    g = helpers.load_golden("preprocess.npz")
+    seed, n = (int(v) for v in g["meta"])
+    frames, crop, kbox, K = synth.make_frames(n, seed)
+    for i in range(n):
+        c, Kn, kv = preprocess.crop_resize_one(frames[i], crop[i], K[i], kbox[i])
+        assert np.array_equal(c, g["crops"][i]), i
+        np.testing.assert_allclose(Kn, g["K"][i], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(kv, g["k_value"][i], rtol=1e-6)
+    assert crop[0][2] - crop[0][0] == 256          # the no-resize branch is part of the fixture
