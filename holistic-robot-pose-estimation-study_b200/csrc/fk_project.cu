@@ -331,14 +331,17 @@ fk_gen_kernel(const float* __restrict__ q, const float* __restrict__ rot6d, cons
   const int t = threadIdx.x;
   const long long ntiles = (N + FK_THREADS - 1) / FK_THREADS;
 
+  // (no pointer / count arrays here: indexing them, even in an unrolled loop, put a 32-byte frame into local memory)
+  auto copy_in = [&](float* dst, const float* src, int n16) {
+    for (int i = t; i < n16; i += FK_THREADS) fk_cp_async16(dst + 4 * i, src + 4 * i);
+  };
   auto prefetch = [&](long long tile) {      // full tiles only; always commits a group so the counting stays uniform
     if (async_ok && tile < ntiles && (tile + 1) * FK_THREADS <= N) {
       const long long base = tile * FK_THREADS;
-      const float* src[4] = {q + base * DOF, rot6d + base * 6, trans + base * 3, Kmat + base * 9};
-      const int off[4] = {IN_Q, IN_ROT, IN_TR, IN_K}, cnt[4] = {FK_THREADS * DOF / 4, FK_THREADS * 6 / 4, FK_THREADS * 3 / 4, FK_THREADS * 9 / 4};
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-        for (int i = t; i < cnt[a]; i += FK_THREADS) fk_cp_async16(smem + off[a] + 4 * i, src[a] + 4 * i);
+      copy_in(smem + IN_Q, q + base * DOF, FK_THREADS * DOF / 4);
+      copy_in(smem + IN_ROT, rot6d + base * 6, FK_THREADS * 6 / 4);
+      copy_in(smem + IN_TR, trans + base * 3, FK_THREADS * 3 / 4);
+      copy_in(smem + IN_K, Kmat + base * 9, FK_THREADS * 9 / 4);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };

@@ -250,7 +250,7 @@ def generate():
         parts.append(gen_raw(name, P))
         parts.append("template <> struct FkGen<FK_%s> {" % name.upper())
         # CTAs of 128 poses that fit one SM's 227 KB with one input tile + one output staging tile each (register budget follows)
-        min_ctas = min(8, (227 * 1024) // (128 * 4 * (P.dof + 18 + P.nkpt * 5) + 1024))
+        min_ctas = min(5, (227 * 1024) // (128 * 4 * (P.dof + 18 + P.nkpt * 5) + 1024))
         parts.append("  static constexpr int DOF = %d, NK = %d, ROOT_KP = %d, MIN_CTAS = %d;" % (P.dof, P.nkpt, P.root_kp, min_ctas))
         parts.append("  static __device__ __forceinline__ void chain(const float (&q)[DOF], float (&kp)[NK * 3], float (&Tr)[12]) { fk_chain_%s(q, kp, Tr); }" % name)
         parts.append("};")

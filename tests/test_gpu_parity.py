@@ -663,11 +663,13 @@ def test_forward_from_uint8_crops_equals_forward_on_divided_floats(prec, dev):
     frames, crop, kbox, K = synth.make_frames(5, 23)
     crops, Kn, kv = crop_resize(cu(frames, dev), cu(crop, dev), cu(K, dev), cu(kbox, dev))
     a = m.forward_dict(crops, Kn, kv)
-    b = m.forward_dict(crops.float() / 255.0, Kn, kv)
+    # IEEE division like the kernel (and the CPU reference); torch's CUDA `x / 255.` multiplies by the reciprocal instead
+    xf = torch.from_numpy(crops.cpu().numpy().astype(np.float32) / np.float32(255.0)).to(dev)
+    b = m.forward_dict(xf, Kn, kv)
     for k in a:
         assert torch.equal(a[k], b[k]), k
     a2 = m.forward_record(crops, crops.clone(), kv, Kn)[0]                            # distinct reg / root buffers
-    assert torch.equal(a2, m.forward_record(crops.float() / 255.0, crops.float() / 255.0, kv, Kn)[0])
+    assert torch.equal(a2, m.forward_record(xf, xf.clone(), kv, Kn)[0])
     pipe = HostPipeline(m, 5)
     t = pipe.submit(crops.cpu().pin_memory(), Kn.cpu().pin_memory(), kv.cpu().pin_memory())
     got = pipe.result(t)
