@@ -36,6 +36,11 @@ namespace {
 using namespace tc;
 
 constexpr int CH_EPI_WARPS = 8;
+// MMA issuer warps: one elected thread needs ~100 clk of issue slots per tcgen05.mma (descriptor arithmetic, R2UR moves),
+// more than the 64 clk an M128 N128 K16 MMA occupies the tensor pipe (conv_roll.cu measured this). The MT tiles of an
+// image have separate accumulators, so issuer w takes tiles w, w + 3, ... and the instruction streams interleave.
+constexpr int CH_ISSUERS = 3;
+constexpr int CH_THREADS = 32 * (1 + CH_ISSUERS + CH_EPI_WARPS);
 constexpr int CH_MAX_STAGES = 6;
 constexpr int CH_SMEM_LIMIT = 227 * 1024;
 
@@ -48,7 +53,7 @@ struct ChainParams {
 
 // barrier block (8-byte slots): x_full | x_free | acc_full | epi_done | w_full[6] | w_empty[6] | tmem slot
 template <int PLANES>
-__global__ void __launch_bounds__(64 + 32 * CH_EPI_WARPS, 1)
+__global__ void __launch_bounds__(CH_THREADS, 1)
 conv_chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr int C = 64 * PLANES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -62,8 +67,8 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
   const uint32_t plane_bytes = (uint32_t)p.plane_bytes, kb_bytes = (uint32_t)p.kb_bytes, margin_b = (uint32_t)p.margin * 128u;
 
   if (tid == 0) {
-    mbar_init(bar_xfull, 1); mbar_init(bar_xfree, 1); mbar_init(bar_acc, 1); mbar_init(bar_epi, CH_EPI_WARPS);
-    for (int i = 0; i < S; ++i) { mbar_init(bar_wf + 8u * i, 1); mbar_init(bar_we + 8u * i, 1); }
+    mbar_init(bar_xfull, 1); mbar_init(bar_xfree, 1); mbar_init(bar_acc, CH_ISSUERS); mbar_init(bar_epi, CH_EPI_WARPS);
+    for (int i = 0; i < S; ++i) { mbar_init(bar_wf + 8u * i, 1); mbar_init(bar_we + 8u * i, CH_ISSUERS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -110,9 +115,10 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (all lanes walk the loops, one elected lane issues; tc_ptx.h) =======================================
+  } else if (warp <= CH_ISSUERS) {
+    // ===== MMA issuers (all lanes walk the loops, one elected lane issues; tc_ptx.h): issuer iw owns tiles iw, iw + 3, ... =====
     const bool leader = elect_one();
+    const int iw = warp - 1;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t dhi = umma_desc_hi(128);
     int s = 0, use = 0, li = 0, nc = 0;
@@ -131,7 +137,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
             tc_fence_after();
             const uint32_t a16 = a_base + (uint32_t)pl * (plane_bytes >> 4) + tap16;
             const uint32_t b16 = ((sW + (uint32_t)s * kb_bytes) >> 4) | (1u << 16);
-            for (int m = 0; m < MT; ++m) {
+            for (int m = iw; m < MT; m += CH_ISSUERS) {
               const uint32_t tm = tmem_base + (uint32_t)(m * C), am = a16 + (uint32_t)m * 1024u;
               if (leader) {
 #pragma unroll
@@ -150,7 +156,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
     }
   } else {
     // ===== epilogue: warp e owns TMEM lane quarter (warp & 3) and column half (e >> 2) of every tile =======================
-    const int e = warp - 2, quarter = warp & 3, half = e >> 2;
+    const int e = warp - 1 - CH_ISSUERS, quarter = warp & 3, half = e >> 2;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int c_lo = half * (C / 2), c_hi = c_lo + C / 2;
     int nc = 0;
@@ -304,7 +310,7 @@ int chain_launch_t(const ChainParams& p, int grid, size_t smem, cudaStream_t st)
     HRP_CUDA(cudaFuncSetAttribute(conv_chain_kernel<PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_LIMIT));
     attr_done = true;
   }
-  conv_chain_kernel<PLANES><<<grid, 64 + 32 * CH_EPI_WARPS, smem, st>>>(p);
+  conv_chain_kernel<PLANES><<<grid, CH_THREADS, smem, st>>>(p);
   HRP_CHECK_LAUNCH("conv_chain_kernel");
   return HRP_OK;
 }

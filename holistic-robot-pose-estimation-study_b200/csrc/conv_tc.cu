@@ -771,10 +771,11 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   // N tile: every CTA re-reads its activation rows, so wide tiles cut that traffic; take the widest that still
   // leaves about one tile per SM, else the narrowest. (TF32: <= 128 so the fp32 staging tile fits beside the stages.)
   static const int force_bn = env_int("HRP_TC_BN", 0), force_stages = env_int("HRP_TC_STAGES", 0), force_ctas = env_int("HRP_TC_CTAS", 0);
+  static const int budget_kb = env_int("HRP_TC_BUDGET_KB", 0), bn_max = env_int("HRP_TC_BN_MAX", 256);
   const int cand[4] = {256, 128, 64, 32};
   int bn = 0;
   for (int i = tf32 ? 1 : 0; i < 4; ++i) {
-    if (a.Cout % cand[i]) continue;
+    if (a.Cout % cand[i] || cand[i] > bn_max) continue;
     bn = cand[i];
     if ((long long)mtiles * (a.Cout / cand[i]) >= (sms * 4) / 5) break;
   }
@@ -803,7 +804,8 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   if (a.sa_partial != nullptr) epi = 4;
   int ctas = (epi == 4 && p.total_tiles >= 2 * sms && tm <= 256) ? 2 : 1;
   if (force_ctas) ctas = (epi == 4 && force_ctas == 2 && tm <= 256) ? 2 : 1;
-  const size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 1024 : 0);
+  size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 1024 : 0);
+  if (budget_kb > 0 && a.grid_pct > 0) budget = std::min(budget, (size_t)budget_kb * 1024);   // experiment: leave room for a CTA of another lane's kernel
   // TMA epilogue: dense NHWC output whose tile rows are consecutive rows of the [M][Cout] matrix
   static const int no_epi_tma = env_int("HRP_TC_NO_EPI_TMA", 0);
   p.epi_tma = !no_epi_tma && !a.out_nchw && a.out_sy == 1 && a.out_sx == 1 && a.out_oy == 0 && a.out_ox == 0 && a.Ho_full == a.Ho &&

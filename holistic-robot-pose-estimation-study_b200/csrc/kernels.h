@@ -79,6 +79,11 @@ struct ChainArgs {
 };
 bool conv_chain_supported(const ChainArgs& a);
 int conv_chain_launch(const ChainArgs& a, cudaStream_t s);
+// The same for the 64-channel branch (32x32 map), whose two ping-pong buffers would not fit: one shared-memory buffer, every
+// conv writes its output in place a few rows further up (conv_roll.cu). w[j] = pack_conv_tc images with 128-byte rows;
+// scratch0 / scratch1: [B,H,W,64] bf16 buffers for the outputs of the inner blocks.
+bool conv_roll_supported(const ChainArgs& a);
+int conv_roll_launch(const ChainArgs& a, void* scratch0, void* scratch1, cudaStream_t s);
 
 int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t s);
 int cast_bf16_to_f32_launch(const void* in, float* out, size_t n, cudaStream_t s);

@@ -495,7 +495,7 @@ struct GraphBuilder {
   bool branch_chain(Tn* x, const std::string& p) {
     ChainArgs probe{};
     probe.B = 1; probe.H = x->H; probe.W = x->W; probe.C = x->C; probe.nconv = 8;
-    if (prec != HRP_PREC_BF16 || !conv_chain_supported(probe)) return false;
+    if (prec != HRP_PREC_BF16 || !(conv_chain_supported(probe) || conv_roll_supported(probe))) return false;
     OpDesc op{};
     op.kind = OP_CHAIN; op.cls = CLS_CONV_TC;
     op.Hi = op.Ho = op.Ho_full = x->H; op.Wi = op.Wo = op.Wo_full = x->W; op.Cin = op.Cout = x->C; op.KH = op.KW = 3; op.stride = 1; op.pad_h = op.pad_w = 1;
@@ -1109,7 +1109,11 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         for (int k = 0; k < o.n_chain; ++k) { a.w[k] = h->layers[o.chain[k]].w_tc; a.b[k] = h->layers[o.chain[k]].bias; }
         a.B = B; a.H = o.Hi; a.W = o.Wi; a.C = o.Cin;
         static const int min_b = [] { const char* v = getenv("HRP_CHAIN_MIN_B"); return v ? atoi(v) : 8; }();
-        if (B >= min_b) { HRP_TRY(conv_chain_launch(a, st_op)); break; }
+        if (B >= min_b) {
+          if (conv_chain_supported(a)) HRP_TRY(conv_chain_launch(a, st_op));
+          else HRP_TRY(conv_roll_launch(a, ptr(o.out2), ptr(o.out3), st_op));     // 64 channels: in-place rolling buffer (conv_roll.cu)
+          break;
+        }
         // small batch: the same eight convs as separate launches, x -> T -> U -> T -> V -> T -> U -> T -> out
         void* T = ptr(o.out2);
         void* blk[5] = {ptr(o.in), ptr(o.out3), ptr(o.out4), ptr(o.out3), ptr(o.out)};
@@ -1641,9 +1645,12 @@ extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int C
     if (chain) {
       ch.x = din; ch.out = dout; ch.nconv = 8; ch.B = B; ch.H = H; ch.W = W; ch.C = Cin;
       for (int j = 0; j < 8; ++j) { ch.w[j] = dw; ch.b[j] = static_cast<const float*>(db); }
-      if (k != 3 || stride != 1 || Cin != Cout || tf32 || !conv_chain_supported(ch)) rs = fail(HRP_ERR_INVALID, "hrp_conv_bench: shape not taken by the chain kernel");
+      if (k != 3 || stride != 1 || Cin != Cout || tf32 || !(conv_chain_supported(ch) || conv_roll_supported(ch))) rs = fail(HRP_ERR_INVALID, "hrp_conv_bench: shape not taken by the chain kernels");
     }
-    auto launch = [&](cudaStream_t s_) { return chain ? conv_chain_launch(ch, s_) : conv_tc_launch(a, tf32, tf32, s_); };
+    void *sc0 = nullptr, *sc1 = nullptr;
+    const bool roll = chain && rs == HRP_OK && !conv_chain_supported(ch);
+    if (roll) { A(&sc0, n_out * es); A(&sc1, n_out * es); }
+    auto launch = [&](cudaStream_t s_) { return chain ? (roll ? conv_roll_launch(ch, sc0, sc1, s_) : conv_chain_launch(ch, s_)) : conv_tc_launch(a, tf32, tf32, s_); };
     for (int i = 0; i < 3 && rs == HRP_OK; ++i) rs = launch(st);
     // the timed launches replay from a CUDA graph so that host-side launch cost (tensor-map encoding, ~15 us) is not what
     // gets measured for kernels shorter than that
@@ -1668,6 +1675,8 @@ extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int C
     if (ge) cudaGraphExecDestroy(ge);
     if (g) cudaGraphDestroy(g);
     if (cs) cudaStreamDestroy(cs);
+    if (sc0) cudaFree(sc0);
+    if (sc1) cudaFree(sc1);
   }
   for (void* d : {dw, din, dout, dres, db, (void*)tmp}) if (d) cudaFree(d);
   return rs;
@@ -1727,8 +1736,9 @@ extern "C" int hrp_basic_chain_nhwc(const float* x, const float* w_oihw, const f
   cudaStream_t st = (cudaStream_t)stream;
   ChainArgs a{};
   a.B = B; a.H = H; a.W = W; a.C = C; a.nconv = 2 * nblocks;
-  if (nblocks < 1 || nblocks > 4 || !conv_chain_supported(a))
-    return fail(HRP_ERR_INVALID, "hrp_basic_chain_nhwc: chain not supported by the fused kernel (C=%d, %dx%d, %d blocks)", C, H, W, nblocks);
+  const bool roll = nblocks >= 1 && nblocks <= 4 && !conv_chain_supported(a) && conv_roll_supported(a);
+  if (nblocks < 1 || nblocks > 4 || !(conv_chain_supported(a) || roll))
+    return fail(HRP_ERR_INVALID, "hrp_basic_chain_nhwc: chain not supported by the fused kernels (C=%d, %dx%d, %d blocks)", C, H, W, nblocks);
   const size_t nw = (size_t)C * C * 9, n = (size_t)B * H * W * C;
   std::vector<float> w(nw), bb(C), wp(nw), bp(C);
   std::vector<void*> tmp;
@@ -1753,7 +1763,10 @@ extern "C" int hrp_basic_chain_nhwc(const float* x, const float* w_oihw, const f
   if (rs == HRP_OK && (!dx || !dout)) rs = fail(HRP_ERR_NOMEM, "hrp_basic_chain_nhwc: out of device memory");
   if (rs == HRP_OK) rs = cast_f32_to_bf16_launch(x, dx, n, st);
   a.x = dx; a.out = dout;
-  if (rs == HRP_OK) rs = conv_chain_launch(a, st);
+  void* sc0 = roll ? dalloc(n * 2) : nullptr;
+  void* sc1 = roll ? dalloc(n * 2) : nullptr;
+  if (rs == HRP_OK && roll && (!sc0 || !sc1)) rs = fail(HRP_ERR_NOMEM, "hrp_basic_chain_nhwc: out of device memory");
+  if (rs == HRP_OK) rs = roll ? conv_roll_launch(a, sc0, sc1, st) : conv_chain_launch(a, st);
   if (rs == HRP_OK) rs = cast_bf16_to_f32_launch(dout, out, n, st);
   if (cudaStreamSynchronize(st) != cudaSuccess && rs == HRP_OK) rs = fail(HRP_ERR_CUDA, "hrp_basic_chain_nhwc: %s", cudaGetErrorString(cudaGetLastError()));
   for (void* d : tmp) cudaFree(d);

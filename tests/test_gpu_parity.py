@@ -286,10 +286,14 @@ def test_fused_basic_block_equals_two_convs(B, H, dev):
 
 
 @pytest.mark.parametrize("B,H,C,nblocks", [(64, 16, 128, 4), (5, 16, 128, 1), (64, 8, 256, 4), (3, 8, 256, 2), (301, 8, 256, 1),
-                                            (160, 16, 128, 2), (2, 4, 256, 3), (7, 12, 128, 4)])
+                                            (160, 16, 128, 2), (2, 4, 256, 3), (7, 12, 128, 4),
+                                            (64, 32, 64, 4), (3, 32, 64, 1), (150, 32, 64, 2), (5, 32, 64, 3), (2, 16, 64, 4), (9, 24, 64, 4),
+                                            (4, 5, 64, 2), (300, 8, 64, 1)])
 def test_branch_chain_equals_layer_by_layer(B, H, C, nblocks, dev):
     """conv_chain.cu (all BasicBlocks of a low-resolution HRNet branch in one launch, one image per CTA, activations in
-    shared memory) against the same blocks run conv by conv: same operands, K order and bf16 roundings => bit-identical."""
+    shared memory; C = 128 / 256) and conv_roll.cu (C = 64: a single shared-memory buffer that every conv rewrites in place
+    a few rows further up; several images per CTA, one / two / three passes per conv, maps that leave grid positions behind
+    the last tile) against the same blocks run conv by conv: same operands, K order and bf16 roundings => bit-identical."""
     from hrp_b200.model import basic_chain_nhwc, conv2d_nhwc
     g = torch.Generator().manual_seed(B * 11 + H + C)
     x = torch.randn(B, H, H, C, generator=g).bfloat16().float().to(dev)
