@@ -30,6 +30,10 @@ def main():
     ap.add_argument("--gather", action="store_true", help="also time FK + NCCL all-gather of the outputs (N > 1)")
     ap.add_argument("--cpu", action="store_true", help="also time the reference algorithm on the host cores (rank 0)")
     args = ap.parse_args()
+    # one JSON object per stdout line: whatever libraries print while initialising (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import hrp_b200  # noqa: F401
@@ -40,6 +44,10 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if world > 1:
+        dist.barrier()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
     for robot in args.robots.split(","):
         spec = consts.ROBOTS[robot]
