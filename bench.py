@@ -208,7 +208,7 @@ def main():
         h = [u8.pin_memory(), torch.from_numpy(K).pin_memory(), torch.from_numpy(kv).pin_memory()]
         sets_host.append(h)
         sets_dev.append([u8.to(dev).float() / 255.0, h[1].to(dev), h[2].to(dev)])
-    n_side = int(os.environ.get("HRP_SLOTS", "3"))
+    n_side = int(os.environ.get("HRP_SLOTS", "4"))
     state_dict = synth.make_state_dict(ROBOT, args.backbone, WEIGHT_SEED)
 
     def gathered(rec):

@@ -66,6 +66,13 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane < 3) asm volatile("prefetch.tensormap [%0];" ::"l"(p.tmap[lane]) : "memory");
+  // both bias vectors go to shared memory once per CTA (b1 at +0, b2 at +4C bytes): a global load per channel pair inside the
+  // drain loops keeps the in-order epilogue warps on the long scoreboard
+  const uint32_t s_bias = sBar + 256u;
+  if (tid >= 64 && tid - 64 < 2 * C) {
+    const float bvv = __ldg((tid - 64 < C ? a.b1 : a.b2 - C) + (tid - 64));
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias + 4u * (uint32_t)(tid - 64)), "f"(bvv) : "memory");
+  }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -213,7 +220,8 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
                 uint32_t w[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const float2 bq = __ldg(reinterpret_cast<const float2*>(a.b1 + c0 + q2 * 8 + k * 2));
+                  float2 bq;
+                  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(bq.x), "=f"(bq.y) : "r"(s_bias + 4u * (uint32_t)(c0 + q2 * 8 + k * 2)));
                   const float f0 = ok ? fmaxf(__uint_as_float(v[q2 * 8 + k * 2]) + bq.x, 0.f) : 0.f;
                   const float f1 = ok ? fmaxf(__uint_as_float(v[q2 * 8 + k * 2 + 1]) + bq.y, 0.f) : 0.f;
                   const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
@@ -252,7 +260,8 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
                 asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(my + (uint32_t)c0 * 2u + 16u * q2));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const float2 bq = __ldg(reinterpret_cast<const float2*>(a.b2 + c0 + q2 * 8 + k * 2));
+                  float2 bq;
+                  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(bq.x), "=f"(bq.y) : "r"(s_bias + 4u * (uint32_t)(C + c0 + q2 * 8 + k * 2)));
                   const float2 rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
                   const float f0 = fmaxf(__uint_as_float(v[q2 * 8 + k * 2]) + bq.x + rr.x, 0.f);
                   const float f1 = fmaxf(__uint_as_float(v[q2 * 8 + k * 2 + 1]) + bq.y + rr.y, 0.f);

@@ -83,6 +83,13 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
   }
   for (uint32_t i = (uint32_t)tid * 16u; i < (uint32_t)PLANES * plane_bytes; i += blockDim.x * 16u)
     asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sY + i), "r"(0u) : "memory");
+  // every conv's bias vector goes to shared memory once per CTA: a global load per channel pair inside the drain loop keeps
+  // the in-order epilogue warps on the long scoreboard (measured on conv_roll.cu)
+  const uint32_t s_bias = sBar + 256u;
+  for (int i = tid; i < nconv * C; i += blockDim.x) {
+    const float bvv = __ldg(a.b[i / C] + (i % C));
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias + 4u * (uint32_t)i), "f"(bvv) : "memory");
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -162,8 +169,8 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
     int nc = 0;
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
       for (int j = 0; j < nconv; ++j, ++nc) {
-        const float* bias = a.b[j];
         const bool second = (j & 1) != 0;
+        const uint32_t bias_j = s_bias + (uint32_t)(j * C) * 4u;     // conv j's bias vector (shared memory, filled at kernel start)
         const uint32_t dst = second ? sX : sY;
         mbar_wait(bar_acc, nc & 1);
         tc_fence_after();
@@ -192,7 +199,8 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
                   if (second) asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const float2 bq = __ldg(reinterpret_cast<const float2*>(bias + cc + q2 * 8 + k * 2));
+                    float2 bq;
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(bq.x), "=f"(bq.y) : "r"(bias_j + 4u * (uint32_t)(cc + q2 * 8 + k * 2)));
                     float f0 = __uint_as_float(v[hh][q2 * 8 + k * 2]) + bq.x, f1 = __uint_as_float(v[hh][q2 * 8 + k * 2 + 1]) + bq.y;
                     if (second) {
                       const float2 rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
@@ -289,7 +297,7 @@ bool chain_plan(const ChainArgs& a, ChainParams* p, size_t* smem) {
   // the taps of the last tile read up to 128*MT + 2*Wp + 2 rows into a plane; what lies behind the last Y plane must still
   // be inside the allocation (it only feeds accumulator rows that are never stored)
   const int overrun = std::max(0, (128 * p->MT + p->margin + p->Wp + 1) * 128 - p->plane_bytes);
-  const size_t tail = 256;
+  const size_t tail = 256 + (size_t)8 * a.C * 4;             // barriers + the bias vectors of up to eight convs
   int S = force_s ? force_s : CH_MAX_STAGES;
   S = std::min(S, CH_MAX_STAGES);
   while (S >= 2 && 1024 + (size_t)p->w_off + (size_t)S * p->kb_bytes + tail > (size_t)CH_SMEM_LIMIT) --S;

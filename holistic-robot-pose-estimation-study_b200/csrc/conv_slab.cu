@@ -71,6 +71,13 @@ conv_slab_kernel(const __grid_constant__ SlabParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane < 3) asm volatile("prefetch.tensormap [%0];" ::"l"(p.tmap[lane]) : "memory");
+  // the bias vector goes to shared memory once per CTA: a global load per four columns inside the drain loop keeps the
+  // in-order epilogue warps on the long scoreboard
+  const uint32_t s_bias = sBar + 256u;
+  if (tid >= 64 && tid - 64 < C / 4) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + (tid - 64));
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_bias + 16u * (uint32_t)(tid - 64)), "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w) : "memory");
+  }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -207,7 +214,8 @@ conv_slab_kernel(const __grid_constant__ SlabParams p) {
             float f[16], r[16];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-              const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + q4);
+              float4 bq;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w) : "r"(s_bias + 4u * (uint32_t)c0 + 16u * (uint32_t)q4));
               f[q4 * 4 + 0] = __uint_as_float(v[q4 * 4 + 0]) + bq.x;
               f[q4 * 4 + 1] = __uint_as_float(v[q4 * 4 + 1]) + bq.y;
               f[q4 * 4 + 2] = __uint_as_float(v[q4 * 4 + 2]) + bq.z;
@@ -337,7 +345,7 @@ bool slab_plan(const ConvArgs& a, int tf32, SlabParams* p, size_t* smem) {
   p->cpr_log = cl;
   const int sms = sm_count();
   static const int force_groups = slab_env("HRP_SLAB_GROUPS", 0);
-  const size_t warp_stg = (size_t)32 * (a.Cout * esz + 16), tail = 256;
+  const size_t warp_stg = (size_t)32 * (a.Cout * esz + 16), tail = 1024;   // barriers (256 B) + the bias vector (<= 128 floats)
   const size_t wres = (size_t)((p->w_bytes + 1023) / 1024 * 1024);
   // Plan: epilogue groups G (each four warps with a private staging tile and two TMEM accumulators) and unit size n
   // (128-position blocks per slab). The epilogue is the long pole (residual fetch + store latency per block), so take

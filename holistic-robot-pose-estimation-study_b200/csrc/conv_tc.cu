@@ -71,6 +71,7 @@ struct TcParams {
   int tiles_n, total_tiles;
   int stg_off;       // byte offset of the epilogue staging tile (after the operand stages)
   int bar_off;       // byte offset of the barrier block
+  int bias_off;      // byte offset of the layer's bias vector in shared memory (Cout floats, filled once per CTA)
   int cpr_log;       // log2 of 16-byte chunks per staged tile row (block_n * elem / 16)
   int round_tf32;    // round fp32 NHWC outputs to TF32 (nearest, ties away) so the next MMA sees exact operands
   int x3;            // TF32 only: 3xTF32 -- operands split into hi + lo TF32 halves, D += Ahi Whi + Alo Whi + Ahi Wlo (fp32-grade products)
@@ -108,6 +109,12 @@ __device__ __forceinline__ void split_chunk(uint32_t addr, uint32_t lo_off) {
 __device__ __forceinline__ void split_own_chunks(uint32_t row0, uint32_t sw_even, uint32_t sw_odd, uint32_t lo_off) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) split_chunk(row0 + ((i & 1) ? sw_odd : sw_even) + (uint32_t)i * (4 * TC_ROW_BYTES), lo_off);
+}
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 
 // Persistent, warp-specialised: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (N tile fastest, so
@@ -339,6 +346,14 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     const uint32_t cpr = 1u << cpr_log;
     const uint32_t my = stg + (uint32_t)et * pitch;
     const bool has_res = a.res != nullptr;
+    // the layer's bias vector in shared memory, once per CTA: a global load per four columns inside the drain loop keeps
+    // an in-order epilogue warp on the long scoreboard (measured on conv_roll.cu: the epilogue, not the MMAs, set the pace)
+    const uint32_t s_bias = smem_base + (uint32_t)p.bias_off;
+    for (int i = eid; i < a.Cout / 4; i += EPI_T) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + i);
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_bias + 16u * (uint32_t)i), "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w) : "memory");
+    }
+    epi_barrier<EPI>();
     int li = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
       const int buf = li & 1;
@@ -366,7 +381,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
+            const float4 bq = lds_f4(s_bias + 4u * (uint32_t)(n0 + c0) + 16u * (uint32_t)q);
             vals[c0 + q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + bq.x; vals[c0 + q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + bq.y;
             vals[c0 + q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + bq.z; vals[c0 + q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + bq.w;
           }
@@ -420,7 +435,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           if (!row_ok) continue;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
+            const float4 bq = lds_f4(s_bias + 4u * (uint32_t)(n0 + c0) + 16u * (uint32_t)q);
             float f0 = __uint_as_float(v[q * 4 + 0]) + bq.x, f1 = __uint_as_float(v[q * 4 + 1]) + bq.y;
             float f2 = __uint_as_float(v[q * 4 + 2]) + bq.z, f3 = __uint_as_float(v[q * 4 + 3]) + bq.w;
             if (a.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
@@ -465,7 +480,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           float f[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
+            const float4 bq = lds_f4(s_bias + 4u * (uint32_t)(n0 + c0) + 16u * (uint32_t)q);
             f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + bq.x;
             f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + bq.y;
             f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + bq.z;
@@ -518,6 +533,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             }
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
           }
+        
         }
         fence_proxy_async();                                   // generic-proxy writes -> visible to the TMA store
         tc_fence_before();
@@ -568,7 +584,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         float f[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
+          const float4 bq = lds_f4(s_bias + 4u * (uint32_t)(n0 + c0) + 16u * (uint32_t)q);
           f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + bq.x;
           f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + bq.y;
           f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + bq.z;
@@ -821,12 +837,12 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     // the store of tile li drain under tile li+1 (64->256 @64x64: 78 -> 70.5 us with residual, 46.8 -> 39.1 us without).
     static const int no_short_stg = env_int("HRP_TC_NO_SHORT_STG2", 0);
     const int min_stages = (short_k && !no_short_stg) ? 1 : 3;
-    p.n_stg = (2048 + 2 * one + tc_tail_bytes() + min_stages * opnd * tc_stage_bytes(bn, p.row_bytes) <= budget) ? 2 : 1;
+    p.n_stg = (2048 + 2 * one + tc_tail_bytes() + (size_t)a.Cout * 4 + min_stages * opnd * tc_stage_bytes(bn, p.row_bytes) <= budget) ? 2 : 1;
     staging = (p.n_stg * one + 1023) / 1024 * 1024;
     static const int no_prefetch = env_int("HRP_TC_NO_RES_PREFETCH", 0);
     p.res_prefetch = (p.n_stg == 2 && a.res != nullptr && !no_prefetch) ? 1 : 0;
   }
-  const size_t fixed = 2048 + staging + tc_tail_bytes();
+  const size_t fixed = 2048 + staging + tc_tail_bytes() + (size_t)a.Cout * 4;
   int smax = (int)((budget - fixed) / (opnd * tc_stage_bytes(bn, p.row_bytes)));
   smax = std::max(1, std::min(smax, TC_MAX_STAGES));
   if (force_stages) smax = std::max(1, std::min(force_stages, smax));
@@ -840,7 +856,8 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   int cl = 0;
   while ((16 << cl) < bn * esz) ++cl;
   p.cpr_log = cl;
-  const size_t smem = 1024 + (size_t)p.bar_off + tc_tail_bytes();
+  p.bias_off = p.bar_off + (int)tc_tail_bytes();
+  const size_t smem = 1024 + (size_t)p.bias_off + (size_t)a.Cout * 4;
   if (p.epi_tma) {
     const cuuint64_t gdim[2] = {(cuuint64_t)a.ld_out, (cuuint64_t)p.M};
     const cuuint64_t gstr[1] = {(cuuint64_t)a.ld_out * esz};

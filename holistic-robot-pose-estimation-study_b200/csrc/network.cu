@@ -117,7 +117,7 @@ struct hrp_handle {
   std::vector<TensorInfo> tensors;
   std::vector<OpDesc> ops;
   std::map<int, std::unique_ptr<Plan>> plans;      // key = batch * 8 + slot
-  int slots = 3;                   // graph path: up to this many plans (workspace + graph) per batch size; a forward that
+  int slots = 4;                   // graph path: up to this many plans (workspace + graph) per batch size; a forward that
   int next_slot = 0;               //   arrives on a DIFFERENT stream than its predecessor takes the next one (so the two
   cudaStream_t last_stream = nullptr; int last_B = 0, last_slot_used = 0;   //   overlap); one stream only ever allocates one
   int max_batches = 4;             // distinct batch sizes kept in the plan cache (least recently used is dropped)
@@ -1316,7 +1316,7 @@ extern "C" int hrp_finalize_weights(hrp_handle* h) {
   if (h->n_lanes > kMaxLanes) return fail(HRP_ERR_INVALID, "internal: %d lanes", h->n_lanes);
   for (int l = 1; l < h->n_lanes; ++l) HRP_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
   if (const char* e = getenv("HRP_NO_LANES")) h->use_lanes = atoi(e) == 0;
-  if (const char* e = getenv("HRP_SLOTS")) h->slots = std::max(1, std::min(4, atoi(e)));
+  if (const char* e = getenv("HRP_SLOTS")) h->slots = std::max(1, std::min(8, atoi(e)));
   if (getenv("HRP_TIMELINE")) {
     HRP_CUDA(cudaMalloc(&h->timeline, h->ops.size() * 16));
     HRP_CUDA(cudaMemset(h->timeline, 0, h->ops.size() * 16));
@@ -1351,8 +1351,8 @@ extern "C" size_t hrp_workspace_bytes(hrp_handle* h, int B) {
 extern "C" int hrp_set_option(hrp_handle* h, const char* name, int64_t value) {
   if (!h || !name) return fail(HRP_ERR_INVALID, "hrp_set_option: null argument");
   if (std::strcmp(name, "cuda_graph") == 0) { h->use_graph = value != 0; return HRP_OK; }
-  if (std::strcmp(name, "slots") == 0) {         // plans per batch size, 1..4 (default 3)
-    if (value < 1 || value > 4) return fail(HRP_ERR_INVALID, "hrp_set_option: slots must be 1..4");
+  if (std::strcmp(name, "slots") == 0) {         // plans per batch size, 1..8 (default 4)
+    if (value < 1 || value > 8) return fail(HRP_ERR_INVALID, "hrp_set_option: slots must be 1..8");
     h->slots = (int)value; h->next_slot = 0;
     return HRP_OK;
   }

@@ -432,7 +432,7 @@ class HoliRobPoseB200(torch.nn.Module):
 class HostPipeline:
     """Streaming inference from HOST batches: `submit()` enqueues the host->device copy of one batch on a copy stream
     (double-buffered device staging), the forward on the compute stream behind it and the device->host copy of the packed
-    output record; `result()` blocks on that batch only. With `depth` slots (default 3, the library's number of plans
+    output record; `result()` blocks on that batch only. With `depth` slots (default 4, the library's number of plans
     per batch size) uploads overlap forwards and the low-parallelism tail of batch i overlaps the head of batch i+1
     (50 MB of fp32 images per 64 frames is ~0.9 ms over PCIe 5, 15 % of the forward at batch 64). Inputs should be
     pinned (`torch.Tensor.pin_memory()`), otherwise the copies serialise with the host.
@@ -442,7 +442,7 @@ class HostPipeline:
         out = pipe.result(t)                         # dict of pinned-host views, valid until the slot is reused
     """
 
-    def __init__(self, model, batch, depth=3, post=None):
+    def __init__(self, model, batch, depth=4, post=None):
         self.model, self.B, self.depth, self.post = model, int(batch), int(depth), post
         dev = model.device
         self.copy_stream = torch.cuda.Stream(dev)

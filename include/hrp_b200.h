@@ -211,7 +211,7 @@ int hrp_crop_resize_u8(const uint8_t* frames, int B, int Hf, int Wf, const int32
 int hrp_release_plans(hrp_handle* h);
 
 /* Options: "cuda_graph" (0/1, default 1: replay one graph per batch size), "lanes" (0/1, default 1: capture the graph
- * over several streams so independent sub-networks overlap), "slots" (1..4, default 3: plans = workspace + graph kept per
+ * over several streams so independent sub-networks overlap), "slots" (1..8, default 4: plans = workspace + graph kept per
  * batch size and used round-robin, so consecutive forwards enqueued on different streams overlap), "lane_share_pct"
  * (5..100: share of the CTA slots one conv launch may take; default 25 for batches of 32 frames and more -- it maximises
  * the throughput of overlapping forwards -- and 50 below, where the latency of a single forward matters). Graph-shaping options take effect for graphs not yet captured.
