@@ -29,6 +29,11 @@ namespace {
 using namespace tc;
 
 constexpr int BK_MAX_GROUPS = 3;
+// MMA issuer warps: one elected thread needs ~70 clk of issue slots per tcgen05.mma (descriptor arithmetic in uniform
+// registers, R2UR moves), more than the ~44 clk an M128 N32 K16 MMA takes (conv_roll.cu / conv_chain.cu measured the same
+// effect). Blocks have separate accumulators, so issuer w takes blocks w, w + 2, ... of the unit's phase-1 / phase-2 sequence.
+constexpr int BK_ISSUERS = 2;
+constexpr int BK_FIRST_EPI = 1 + BK_ISSUERS;
 constexpr int BK_MAX_N1 = 12;
 constexpr int BK_SMEM_LIMIT = 227 * 1024;
 
@@ -44,7 +49,7 @@ struct BlockParams {
 
 // barrier block (8-byte slots): w | x_full | x_empty | y_empty | y_full[12] | acc_full[6] | acc_empty[6] | tmem slot
 template <int ROWB>
-__global__ void __launch_bounds__(64 + 128 * BK_MAX_GROUPS, 1)
+__global__ void __launch_bounds__(32 * BK_FIRST_EPI + 128 * BK_MAX_GROUPS, 1)
 conv_block_kernel(const __grid_constant__ BlockParams p) {
   constexpr int ESZ = 2;
   constexpr int KSTEPS = ROWB / 32;
@@ -60,7 +65,7 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
   const int C = p.C, Wp = p.Wp, G = p.groups, NACC = p.nacc, n = p.n, n1 = p.n1;
 
   if (tid == 0) {
-    mbar_init(bar_w, 1); mbar_init(bar_xf, 1); mbar_init(bar_xe, 1); mbar_init(bar_ye, 1);
+    mbar_init(bar_w, 1); mbar_init(bar_xf, 1); mbar_init(bar_xe, BK_ISSUERS); mbar_init(bar_ye, BK_ISSUERS);
     for (int i = 0; i < n1; ++i) mbar_init(bar_yf + 8u * i, 4);
     for (int i = 0; i < NACC; ++i) { mbar_init(bar_af + 8u * i, 1); mbar_init(bar_ae + 8u * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -121,9 +126,11 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
         R += seg;
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (all lanes walk the loops, one elected lane issues; tc_ptx.h) =======================================
+  } else if (warp < BK_FIRST_EPI) {
+    // ===== MMA issuers (all lanes walk the loops, one elected lane issues; tc_ptx.h); issuer iw owns every BK_ISSUERS-th block ==
     const bool leader = elect_one();
+    const int iw = warp - 1;
+    int seq = 0;                                                  // running block number (phase 1 and phase 2 blocks of all units)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t dhi = umma_desc_hi(ROWB);
     const uint32_t wt16 = (uint32_t)(C * ROWB) >> 4, w1_16 = (sW >> 4) | (1u << 16), w2_16 = ((sW + (uint32_t)p.w_bytes) >> 4) | (1u << 16);
@@ -138,7 +145,14 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
       // phase 1: Y block i, tap (0,0) reads slab X row (Y0 + 128 i - Wp - 1) - ra*Wp
       const long long y0 = (long long)u * unit_pos - Wp - 1;
       uint32_t a16 = ((sX >> 4) + (uint32_t)(y0 - Wp - 1 - (long long)slab_row0(u) * Wp) * (ROWB / 16)) | (1u << 16);
-      for (int i = 0; i < n1; ++i, a16 += 128u * (ROWB / 16)) {
+      for (int i = 0; i < n1; ++i, a16 += 128u * (ROWB / 16), ++seq) {
+        const bool mine = seq % BK_ISSUERS == iw;
+        if (!mine) {                                              // the other issuer's block: only its X-slab release is shared
+          if (i == n1 - 1 && leader) umma_commit(bar_xe);         // (this issuer's phase-1 MMAs of the unit have been issued)
+          __syncwarp();
+          if (++ab == NACC) { ab = 0; ++use; }
+          continue;
+        }
         if (use >= 1) mbar_wait(bar_ae + 8u * ab, (use - 1) & 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(ab * C);
@@ -157,7 +171,13 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
       // phase 2: output block j, tap (r,s) reads slab Y row 128 j + r*Wp + s; needs Y blocks j .. j + kmax
       uint32_t y16 = (sY >> 4) | (1u << 16);
       int ready = -1;                                           // Y blocks 0..ready are known to be written
-      for (int j = 0; j < n; ++j, y16 += 128u * (ROWB / 16)) {
+      for (int j = 0; j < n; ++j, y16 += 128u * (ROWB / 16), ++seq) {
+        if (seq % BK_ISSUERS != iw) {
+          if (j == n - 1 && leader) umma_commit(bar_ye);
+          __syncwarp();
+          if (++ab == NACC) { ab = 0; ++use; }
+          continue;
+        }
         const int need = min(j + p.kmax, n1 - 1);
         for (; ready < need; ++ready) mbar_wait(bar_yf + 8u * (ready + 1), li & 1);
         if (use >= 1) mbar_wait(bar_ae + 8u * ab, (use - 1) & 1);
@@ -176,9 +196,9 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
         if (++ab == NACC) { ab = 0; ++use; }
       }
     }
-  } else if (warp < 2 + 4 * G) {
+  } else if (warp < BK_FIRST_EPI + 4 * G) {
     // ===== epilogue warps: each its own pipeline over the 32 rows of its TMEM lane quarter; group g takes every G-th block =
-    const int e = warp - 2, g = e >> 2, quarter = warp & 3;
+    const int e = warp - BK_FIRST_EPI, g = e >> 2, quarter = warp & 3;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t pitch = (uint32_t)C * ESZ + 16u;
     const uint32_t cpr_log = (uint32_t)p.cpr_log, cpr = 1u << cpr_log;
@@ -418,7 +438,7 @@ int conv_block_launch(const BlockArgs& a, cudaStream_t st) {
     attr_done = true;
   }
   const int grid = std::min(p.units, std::max(1, sm_count() * (a.grid_pct > 0 ? a.grid_pct : 100) / 100));
-  conv_block_kernel<64><<<grid, 64 + 128 * p.groups, smem, st>>>(p);
+  conv_block_kernel<64><<<grid, 32 * BK_FIRST_EPI + 128 * p.groups, smem, st>>>(p);
   HRP_CHECK_LAUNCH("conv_block_kernel");
   return HRP_OK;
 }
