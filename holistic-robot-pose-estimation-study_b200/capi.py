@@ -11,7 +11,7 @@ NUM_CLASSES = 7
 FIELD_NAMES = ("joint_angles", "rot6d", "trans", "root_uv", "root_depth", "uvd", "kp3d_int", "kp3d_fk", "kp2d_int",
                "kp2d_fk")
 CLASS_NAMES = ("conv_tensor", "conv_fp32", "stem", "elementwise", "heads", "softargmax", "fk")
-PREC = {"fp32": 0, "tf32": 1, "bf16": 2, "tf32x3": 3}
+PREC = {"fp32": 0, "tf32": 1, "bf16": 2, "tf32x3": 3, "f16": 4}
 BACKBONE = {"resnet": 0, "resnet50": 0, "hrnet": 1, "hrnet32": 1}
 
 EXPORTS = (

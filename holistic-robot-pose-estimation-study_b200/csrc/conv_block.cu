@@ -48,7 +48,7 @@ struct BlockParams {
 };
 
 // barrier block (8-byte slots): w | x_full | x_empty | y_empty | y_full[12] | acc_full[6] | acc_empty[6] | tmem slot
-template <int ROWB>
+template <int ROWB, bool F16>
 __global__ void __launch_bounds__(32 * BK_FIRST_EPI + 128 * BK_MAX_GROUPS, 1)
 conv_block_kernel(const __grid_constant__ BlockParams p) {
   constexpr int ESZ = 2;
@@ -131,7 +131,8 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
     const bool leader = elect_one();
     const int iw = warp - 1;
     int seq = 0;                                                  // running block number (phase 1 and phase 2 blocks of all units)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t FMT = F16 ? 0u : 1u;                     // operand format: IEEE half / bf16
+    const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t dhi = umma_desc_hi(ROWB);
     const uint32_t wt16 = (uint32_t)(C * ROWB) >> 4, w1_16 = (sW >> 4) | (1u << 16), w2_16 = ((sW + (uint32_t)p.w_bytes) >> 4) | (1u << 16);
     uint32_t tap16[9];
@@ -244,8 +245,7 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
                   asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(bq.x), "=f"(bq.y) : "r"(s_bias + 4u * (uint32_t)(c0 + q2 * 8 + k * 2)));
                   const float f0 = ok ? fmaxf(__uint_as_float(v[q2 * 8 + k * 2]) + bq.x, 0.f) : 0.f;
                   const float f1 = ok ? fmaxf(__uint_as_float(v[q2 * 8 + k * 2 + 1]) + bq.y, 0.f) : 0.f;
-                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-                  w[k] = *reinterpret_cast<const uint32_t*>(&h2);
+                  w[k] = pack2<F16>(f0, f1);
                 }
                 const uint32_t un = (uint32_t)(c0 * ESZ) / 16u + (uint32_t)q2;
                 asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(yrow + ((un ^ swz) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
@@ -282,11 +282,10 @@ conv_block_kernel(const __grid_constant__ BlockParams p) {
                 for (int k = 0; k < 4; ++k) {
                   float2 bq;
                   asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(bq.x), "=f"(bq.y) : "r"(s_bias + 4u * (uint32_t)(C + c0 + q2 * 8 + k * 2)));
-                  const float2 rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+                  const float2 rr = unpack2<F16>(w[k]);
                   const float f0 = fmaxf(__uint_as_float(v[q2 * 8 + k * 2]) + bq.x + rr.x, 0.f);
                   const float f1 = fmaxf(__uint_as_float(v[q2 * 8 + k * 2 + 1]) + bq.y + rr.y, 0.f);
-                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-                  w[k] = *reinterpret_cast<const uint32_t*>(&h2);
+                  w[k] = pack2<F16>(f0, f1);
                 }
                 asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + (uint32_t)c0 * 2u + 16u * q2), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
               }
@@ -426,7 +425,7 @@ int conv_block_launch(const BlockArgs& a, cudaStream_t st) {
   for (int m = 0; m < 3; ++m) {
     CUtensorMap tm;
     const cuuint32_t box[4] = {(cuuint32_t)(ROWB / ESZ), (cuuint32_t)p.Wp, (cuuint32_t)box_rows[m], 1};
-    const CUresult r = block_encode_tiled()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.x), gdim, gstr, box, estr,
+    const CUresult r = block_encode_tiled()(&tm, a.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.x), gdim, gstr, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HRP_ERR_CUDA, "conv_block: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -434,11 +433,13 @@ int conv_block_launch(const BlockArgs& a, cudaStream_t st) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    HRP_CUDA(cudaFuncSetAttribute(conv_block_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_block_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_block_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = std::min(p.units, std::max(1, sm_count() * (a.grid_pct > 0 ? a.grid_pct : 100) / 100));
-  conv_block_kernel<64><<<grid, 32 * BK_FIRST_EPI + 128 * p.groups, smem, st>>>(p);
+  if (a.f16) conv_block_kernel<64, true><<<grid, 32 * BK_FIRST_EPI + 128 * p.groups, smem, st>>>(p);
+  else conv_block_kernel<64, false><<<grid, 32 * BK_FIRST_EPI + 128 * p.groups, smem, st>>>(p);
   HRP_CHECK_LAUNCH("conv_block_kernel");
   return HRP_OK;
 }

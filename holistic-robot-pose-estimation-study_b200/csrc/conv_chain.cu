@@ -52,7 +52,7 @@ struct ChainParams {
 };
 
 // barrier block (8-byte slots): x_full | x_free | acc_full | epi_done | w_full[6] | w_empty[6] | tmem slot
-template <int PLANES>
+template <int PLANES, bool F16>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 conv_chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr int C = 64 * PLANES;
@@ -126,7 +126,8 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
     // ===== MMA issuers (all lanes walk the loops, one elected lane issues; tc_ptx.h): issuer iw owns tiles iw, iw + 3, ... =====
     const bool leader = elect_one();
     const int iw = warp - 1;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t FMT = F16 ? 0u : 1u;                     // operand format: IEEE half / bf16
+    const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t dhi = umma_desc_hi(128);
     int s = 0, use = 0, li = 0, nc = 0;
     for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++li) {
@@ -203,11 +204,10 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
                     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(bq.x), "=f"(bq.y) : "r"(bias_j + 4u * (uint32_t)(cc + q2 * 8 + k * 2)));
                     float f0 = __uint_as_float(v[hh][q2 * 8 + k * 2]) + bq.x, f1 = __uint_as_float(v[hh][q2 * 8 + k * 2 + 1]) + bq.y;
                     if (second) {
-                      const float2 rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+                      const float2 rr = unpack2<F16>(w[k]);
                       f0 += rr.x; f1 += rr.y;
                     }
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
-                    w[k] = *reinterpret_cast<const uint32_t*>(&h2);
+                    w[k] = pack2<F16>(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
                   }
                   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
                 }
@@ -311,14 +311,14 @@ bool chain_plan(const ChainArgs& a, ChainParams* p, size_t* smem) {
   return *smem <= (size_t)CH_SMEM_LIMIT;
 }
 
-template <int PLANES>
+template <int PLANES, bool F16>
 int chain_launch_t(const ChainParams& p, int grid, size_t smem, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    HRP_CUDA(cudaFuncSetAttribute(conv_chain_kernel<PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_chain_kernel<PLANES, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_LIMIT));
     attr_done = true;
   }
-  conv_chain_kernel<PLANES><<<grid, CH_THREADS, smem, st>>>(p);
+  conv_chain_kernel<PLANES, F16><<<grid, CH_THREADS, smem, st>>>(p);
   HRP_CHECK_LAUNCH("conv_chain_kernel");
   return HRP_OK;
 }
@@ -341,7 +341,7 @@ int conv_chain_launch(const ChainArgs& a, cudaStream_t st) {
   const cuuint32_t box[4] = {64, (cuuint32_t)p.Wp, (cuuint32_t)p.Hp, 1};
   {
     CUtensorMap tm;
-    const CUresult r = chain_encode_tiled()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.x), gdim, gstr, box, estr,
+    const CUresult r = chain_encode_tiled()(&tm, a.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.x), gdim, gstr, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HRP_ERR_CUDA, "conv_chain: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -349,7 +349,8 @@ int conv_chain_launch(const ChainArgs& a, cudaStream_t st) {
   }
   // one image per CTA and one CTA per SM (the buffers fill the shared memory): no lane cap, the images ARE the grid
   const int grid = std::min(a.B, sm_count());
-  return a.C == 128 ? chain_launch_t<2>(p, grid, smem, st) : chain_launch_t<4>(p, grid, smem, st);
+  if (a.f16) return a.C == 128 ? chain_launch_t<2, true>(p, grid, smem, st) : chain_launch_t<4, true>(p, grid, smem, st);
+  return a.C == 128 ? chain_launch_t<2, false>(p, grid, smem, st) : chain_launch_t<4, false>(p, grid, smem, st);
 }
 
 }  // namespace hrp

@@ -5,6 +5,8 @@
 // weights and the bias / residual-add / ReLU of Bottleneck.forward and BasicBlock.forward (HRnet.py:41-98) applied in
 // the epilogue. The tensor-core families (conv_tc.cu) share the ConvArgs descriptor.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <type_traits>
 
 #include <cmath>
 #include <cstdint>
@@ -342,7 +344,7 @@ int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, vo
 // NCHW fp32 image -> zero-padded NHWC4 operand image of the tensor-core stems (kernels.h). One thread per padded pixel;
 // the three plane reads are coalesced along x, the write is one 8- or 16-byte store. Borders are rewritten every
 // forward because the arena recycles this memory.
-template <int MODE>      // 0 bf16, 1 fp32 rounded to TF32, 2 fp32 as is
+template <int MODE>      // 0 bf16, 1 fp32 rounded to TF32, 2 fp32 as is, 3 IEEE half
 __global__ void stem_pack_kernel(const float* __restrict__ in, void* __restrict__ out, int B) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * STEM_HP * STEM_WP;
@@ -364,6 +366,12 @@ __global__ void stem_pack_kernel(const float* __restrict__ in, void* __restrict_
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v1));
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(v2));
     reinterpret_cast<uint4*>(out)[i] = make_uint4(r0, r1, r2, 0u);
+  } else if constexpr (MODE == 3) {
+    const __half2 a = __floats2half2_rn(v0, v1), c = __floats2half2_rn(v2, 0.f);       // inputs are in [0, 1]
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&a);
+    r.y = *reinterpret_cast<const uint32_t*>(&c);
+    reinterpret_cast<uint2*>(out)[i] = r;
   } else {
     const __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1), c = __floats2bfloat162_rn(v2, 0.f);
     uint2 r;
@@ -377,7 +385,8 @@ int stem_pack_launch(const float* in_nchw, void* out, int B, int tf32, cudaStrea
   const long long total = (long long)B * STEM_HP * STEM_WP;
   if (total <= 0) return HRP_OK;
   const unsigned blocks = (unsigned)ceil_div64(total, 256);
-  if (tf32 == 2) stem_pack_kernel<2><<<blocks, 256, 0, s>>>(in_nchw, out, B);
+  if (tf32 == 3) stem_pack_kernel<3><<<blocks, 256, 0, s>>>(in_nchw, out, B);
+  else if (tf32 == 2) stem_pack_kernel<2><<<blocks, 256, 0, s>>>(in_nchw, out, B);
   else if (tf32) stem_pack_kernel<1><<<blocks, 256, 0, s>>>(in_nchw, out, B);
   else stem_pack_kernel<0><<<blocks, 256, 0, s>>>(in_nchw, out, B);
   HRP_CHECK_LAUNCH("stem_pack_kernel");
@@ -422,8 +431,13 @@ maxpool3x3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int Hi
       m.z = __float_as_uint(fmaxf(__uint_as_float(m.z), __uint_as_float(v[k].z))); m.w = __float_as_uint(fmaxf(__uint_as_float(m.w), __uint_as_float(v[k].w)));
     } else {
       auto mx = [](uint32_t p, uint32_t q) {
-        const __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&p), *reinterpret_cast<const __nv_bfloat162*>(&q));
-        return *reinterpret_cast<const uint32_t*>(&h);
+        if constexpr (std::is_same<T, __half>::value) {
+          const __half2 h = __hmax2(*reinterpret_cast<const __half2*>(&p), *reinterpret_cast<const __half2*>(&q));
+          return *reinterpret_cast<const uint32_t*>(&h);
+        } else {
+          const __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&p), *reinterpret_cast<const __nv_bfloat162*>(&q));
+          return *reinterpret_cast<const uint32_t*>(&h);
+        }
       };
       m.x = mx(m.x, v[k].x); m.y = mx(m.y, v[k].y); m.z = mx(m.z, v[k].z); m.w = mx(m.w, v[k].w);
     }
@@ -438,7 +452,8 @@ int maxpool3x3s2_launch(const void* in, void* out, int B, int Hi, int Wi, int C,
   if (total <= 0) return HRP_OK;
   if (C % V || total > 0x7fffffffLL) return fail(HRP_ERR_INVALID, "maxpool: unsupported shape (C=%d, %lld vectors)", C, total);
   const unsigned blocks = (unsigned)ceil_div64(total, 256);
-  if (bf16) maxpool3x3s2_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), B, Hi, Wi, Ho, Wo, C);
+  if (bf16 == 2) maxpool3x3s2_kernel<__half><<<blocks, 256, 0, s>>>(static_cast<const __half*>(in), static_cast<__half*>(out), B, Hi, Wi, Ho, Wo, C);
+  else if (bf16) maxpool3x3s2_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), B, Hi, Wi, Ho, Wo, C);
   else maxpool3x3s2_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(in), static_cast<float*>(out), B, Hi, Wi, Ho, Wo, C);
   HRP_CHECK_LAUNCH("maxpool3x3s2_kernel");
   return HRP_OK;
@@ -484,7 +499,9 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
       const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+        float2 f;
+        if constexpr (std::is_same<T, __half>::value) f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+        else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
         acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
       }
     }
@@ -509,7 +526,14 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseArgs a) {
   } else {
     uint32_t w4[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]); w4[e] = *reinterpret_cast<const uint32_t*>(&h2); }
+    for (int e = 0; e < 4; ++e) {
+      if constexpr (std::is_same<T, __half>::value) {
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w4[e]) : "f"(acc[2 * e + 1]), "f"(acc[2 * e]));
+      } else {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+        w4[e] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+    }
     outv = make_uint4(w4[0], w4[1], w4[2], w4[3]);
   }
   *reinterpret_cast<uint4*>(static_cast<T*>(a.out) + o) = outv;
@@ -521,7 +545,8 @@ int fuse_sum_launch(const FuseArgs& a, int bf16, cudaStream_t s) {
   if (total <= 0) return HRP_OK;
   if (a.C % V || total > 0x7fffffffLL || a.n_same > 4 || a.n_low > 3) return fail(HRP_ERR_INVALID, "fuse_sum: unsupported shape (C=%d, %lld vectors)", a.C, total);
   const unsigned blocks = (unsigned)ceil_div64(total, 256);
-  if (bf16) fuse_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(a);
+  if (bf16 == 2) fuse_sum_kernel<__half><<<blocks, 256, 0, s>>>(a);
+  else if (bf16) fuse_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(a);
   else fuse_sum_kernel<float><<<blocks, 256, 0, s>>>(a);
   HRP_CHECK_LAUNCH("fuse_sum_kernel");
   return HRP_OK;
@@ -537,14 +562,17 @@ __global__ void avgpool_kernel(const T* __restrict__ in, float* __restrict__ out
   const T* p = in + (size_t)b * HW * C + c;
   float s = 0.f;
   for (int k = 0; k < HW; ++k) {
-    if constexpr (sizeof(T) == 4) s += __ldg(p + (size_t)k * C); else s += __bfloat162float(p[(size_t)k * C]);
+    if constexpr (sizeof(T) == 4) s += __ldg(p + (size_t)k * C);
+    else if constexpr (std::is_same<T, __half>::value) s += __half2float(p[(size_t)k * C]);
+    else s += __bfloat162float(p[(size_t)k * C]);
   }
   out[i] = s / (float)HW;
 }
 
 int avgpool_launch(const void* in, float* out, int B, int HW, int C, int bf16, cudaStream_t s) {
   if (B * C <= 0) return HRP_OK;
-  if (bf16) avgpool_kernel<__nv_bfloat16><<<ceil_div(B * C, 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in), out, B, HW, C);
+  if (bf16 == 2) avgpool_kernel<__half><<<ceil_div(B * C, 256), 256, 0, s>>>(static_cast<const __half*>(in), out, B, HW, C);
+  else if (bf16) avgpool_kernel<__nv_bfloat16><<<ceil_div(B * C, 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in), out, B, HW, C);
   else avgpool_kernel<float><<<ceil_div(B * C, 256), 256, 0, s>>>(static_cast<const float*>(in), out, B, HW, C);
   HRP_CHECK_LAUNCH("avgpool_kernel");
   return HRP_OK;

@@ -51,6 +51,7 @@ struct RollParams {
 };
 
 // barrier block (8-byte slots): x_full | x_free | acc_full[2] | acc_empty[2] | w_full[6] | w_empty[6] | tmem slot
+template <bool F16>
 __global__ void __launch_bounds__(RL_THREADS, 1)
 conv_roll_kernel(const __grid_constant__ RollParams p) {
   constexpr int C = RL_C;
@@ -107,7 +108,8 @@ conv_roll_kernel(const __grid_constant__ RollParams p) {
     // ===== MMA issuers (all lanes walk the loops, one elected lane issues; tc_ptx.h): issuer iw owns tiles m0 + iw, + 3, ... ===
     const bool leader = elect_one();
     const int iw = warp - 1;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t FMT = F16 ? 0u : 1u;                     // operand format: IEEE half / bf16
+    const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t dhi = umma_desc_hi(128);
     int s = 0, use = 0, li = 0;
     int g = 0, waited = -1;                                        // global pass counter; highest pass whose epilogue has been awaited
@@ -217,11 +219,10 @@ conv_roll_kernel(const __grid_constant__ RollParams p) {
                     float f0 = __uint_as_float(v[k * 8 + i * 2]) + bv[k * 8 + i * 2];
                     float f1 = __uint_as_float(v[k * 8 + i * 2 + 1]) + bv[k * 8 + i * 2 + 1];
                     if (second) {
-                      const float2 x2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[i]));
+                      const float2 x2 = unpack2<F16>(rr[i]);
                       f0 += x2.x; f1 += x2.y;
                     }
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
-                    w[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                    w[i] = pack2<F16>(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
                   }
                   if (second) *reinterpret_cast<uint4*>(out8 + pix + 16 * k) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
@@ -341,7 +342,7 @@ int conv_roll_launch(const ChainArgs& a, void* scratch0, void* scratch1, cudaStr
   const cuuint32_t box[4] = {64, (cuuint32_t)p.Wp, (cuuint32_t)p.Hp, 1};
   {
     CUtensorMap tm;
-    const CUresult r = roll_encode_tiled()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.x), gdim, gstr, box, estr,
+    const CUresult r = roll_encode_tiled()(&tm, a.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.x), gdim, gstr, box, estr,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HRP_ERR_CUDA, "conv_roll: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -349,12 +350,14 @@ int conv_roll_launch(const ChainArgs& a, void* scratch0, void* scratch1, cudaStr
   }
   static bool attr_done = false;
   if (!attr_done) {
-    HRP_CUDA(cudaFuncSetAttribute(conv_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
     attr_done = true;
   }
   // one image per CTA and one CTA per SM (the buffer fills the shared memory): the images ARE the grid
   const int grid = std::min(a.B, sm_count());
-  conv_roll_kernel<<<grid, RL_THREADS, smem, st>>>(p);
+  if (a.f16) conv_roll_kernel<true><<<grid, RL_THREADS, smem, st>>>(p);
+  else conv_roll_kernel<false><<<grid, RL_THREADS, smem, st>>>(p);
   HRP_CHECK_LAUNCH("conv_roll_kernel");
   return HRP_OK;
 }

@@ -51,7 +51,7 @@ struct SlabParams {
 };
 
 // barrier block layout (8-byte slots): w | slab_full[2] | slab_empty[2] | acc_full[6] | acc_empty[6] | tmem slot
-template <bool TF32, int ROWB, int PLANES>
+template <bool TF32, int ROWB, int PLANES, bool F16>
 __global__ void __launch_bounds__(64 + 128 * SL_MAX_GROUPS, 1)
 conv_slab_kernel(const __grid_constant__ SlabParams p) {
   constexpr int ESZ = TF32 ? 4 : 2;
@@ -132,7 +132,8 @@ conv_slab_kernel(const __grid_constant__ SlabParams p) {
     // 9 x PLANES x KSTEPS MMAs with compile-time trip counts; every operand is a 32-bit descriptor low word = base +
     // precomputed offset, so the issue stream stays a few instructions per MMA (a small-N MMA is only ~44 clk). ==========
     const bool leader = elect_one();
-    const uint32_t idesc = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t FMT = TF32 ? 2u : (F16 ? 0u : 1u);       // operand format: TF32 / IEEE half / bf16
+    const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t dhi = umma_desc_hi(ROWB);
     const uint32_t wt16 = (uint32_t)(C * ROWB) >> 4, plane16 = (uint32_t)p.plane_bytes >> 4, w16 = (sW >> 4) | (1u << 16);
     uint32_t tap16[9];
@@ -233,7 +234,7 @@ conv_slab_kernel(const __grid_constant__ SlabParams p) {
                   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(my + (uint32_t)c0 * 2u + 16u * q2));
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const float2 ff = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+                    const float2 ff = unpack2<F16>(w[k]);
                     r[q2 * 8 + k * 2] = ff.x; r[q2 * 8 + k * 2 + 1] = ff.y;
                   }
                 }
@@ -261,8 +262,7 @@ conv_slab_kernel(const __grid_constant__ SlabParams p) {
                 uint32_t w[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q2 * 8 + k * 2], f[q2 * 8 + k * 2 + 1]);
-                  w[k] = *reinterpret_cast<const uint32_t*>(&h2);
+                  w[k] = pack2<F16>(f[q2 * 8 + k * 2], f[q2 * 8 + k * 2 + 1]);
                 }
                 asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + (uint32_t)c0 * 2u + 16u * q2), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
               }
@@ -410,7 +410,7 @@ int conv_slab_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s
   for (int m = 0; m < 3; ++m) {
     CUtensorMap tm;
     const cuuint32_t box[4] = {(cuuint32_t)p.kb_elems, (cuuint32_t)p.Wp, (cuuint32_t)box_rows[m], 1};
-    const CUresult r = slab_encode_tiled()(&tm, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.in),
+    const CUresult r = slab_encode_tiled()(&tm, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (a.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4, const_cast<void*>(a.in),
                                            gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                            p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -419,11 +419,14 @@ int conv_slab_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s
   }
   static bool attr_done = false;
   if (!attr_done) {
-    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<true, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
-    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<true, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
-    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
-    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
-    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<true, 128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<true, 128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, 64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, 128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, 128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, 64, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, 128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_slab_kernel<false, 128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = std::min(p.units, std::max(1, sm_count() * (a.grid_pct > 0 ? a.grid_pct : 100) / 100));
@@ -431,11 +434,16 @@ int conv_slab_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s
   static const int pdl_early = slab_env("HRP_PDL_EARLY", 0);
   p.pdl_early = pdl_early;
   cudaError_t le;
-  if (tf32 && p.planes == 1) le = launch_pdl(conv_slab_kernel<true, 128, 1>, grid, threads, smem, st, p);
-  else if (tf32) le = launch_pdl(conv_slab_kernel<true, 128, 2>, grid, threads, smem, st, p);
-  else if (p.row_bytes == 64) le = launch_pdl(conv_slab_kernel<false, 64, 1>, grid, threads, smem, st, p);
-  else if (p.planes == 1) le = launch_pdl(conv_slab_kernel<false, 128, 1>, grid, threads, smem, st, p);
-  else le = launch_pdl(conv_slab_kernel<false, 128, 2>, grid, threads, smem, st, p);
+  if (tf32 && p.planes == 1) le = launch_pdl(conv_slab_kernel<true, 128, 1, false>, grid, threads, smem, st, p);
+  else if (tf32) le = launch_pdl(conv_slab_kernel<true, 128, 2, false>, grid, threads, smem, st, p);
+  else if (a.f16) {
+    if (p.row_bytes == 64) le = launch_pdl(conv_slab_kernel<false, 64, 1, true>, grid, threads, smem, st, p);
+    else if (p.planes == 1) le = launch_pdl(conv_slab_kernel<false, 128, 1, true>, grid, threads, smem, st, p);
+    else le = launch_pdl(conv_slab_kernel<false, 128, 2, true>, grid, threads, smem, st, p);
+  }
+  else if (p.row_bytes == 64) le = launch_pdl(conv_slab_kernel<false, 64, 1, false>, grid, threads, smem, st, p);
+  else if (p.planes == 1) le = launch_pdl(conv_slab_kernel<false, 128, 1, false>, grid, threads, smem, st, p);
+  else le = launch_pdl(conv_slab_kernel<false, 128, 2, false>, grid, threads, smem, st, p);
   if (le != cudaSuccess) return fail(HRP_ERR_CUDA, "conv_slab_kernel launch: %s", cudaGetErrorString(le));
   HRP_CHECK_LAUNCH("conv_slab_kernel");
   return HRP_OK;

@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -121,7 +122,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 // co-resident CTAs share the activation rows they gather). The operand ring and both pipelines run across tile
 // boundaries: producers are already gathering tile i+1 while the MMA warp finishes tile i and the epilogue warps drain
 // the other TMEM accumulator buffer.
-template <bool TF32, int EPI>
+template <bool TF32, int EPI, bool F16>
 __global__ void __launch_bounds__(tc_threads(EPI), EPI == 4 ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int ESZ = TF32 ? 4 : 2;
@@ -264,7 +265,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   } else if (warp == 4) {
     // ===== MMA issuer: all lanes walk the loops (uniform operands), one elected lane issues (tc_ptx.h: elect_one) ========
     const bool leader = elect_one();
-    const uint32_t idesc = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+    constexpr uint32_t FMT = TF32 ? 2u : (F16 ? 0u : 1u);       // operand format: TF32 / IEEE half / bf16
+    const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                            ((uint32_t)(TC_BLOCK_M >> 4) << 24);
     const uint32_t dhi = umma_desc_hi(p.row_bytes);
     const int kbe = p.row_bytes / ESZ;                          // K elements per k-block
@@ -504,7 +506,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                  const float2 t2 = unpack2<F16>(w[e]);
                   r[2 * e] = t2.x; r[2 * e + 1] = t2.y;
                 }
               }
@@ -527,8 +529,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(ff[2 * e], ff[2 * e + 1]);
-                o[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                o[e] = pack2<F16>(ff[2 * e], ff[2 * e + 1]);
               }
             }
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
@@ -603,7 +604,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(my + (uint32_t)c0 * 2u + 16u * q));
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 ff = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                const float2 ff = unpack2<F16>(w[e]);
                 r[q * 8 + e * 2] = ff.x; r[q * 8 + e * 2 + 1] = ff.y;
               }
             }
@@ -631,8 +632,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
-              w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              w[e] = pack2<F16>(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
             }
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + (uint32_t)c0 * 2u + 16u * q), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
           }
@@ -666,13 +666,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+template <typename T>
+__global__ void cast_f32_to_half_kernel(const float* __restrict__ in, T* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+  if (i >= n) return;
+  if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) out[i] = __float2half_rn(fminf(fmaxf(in[i], -65504.f), 65504.f));
+  else out[i] = __float2bfloat16_rn(in[i]);
 }
-__global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+template <typename T>
+__global__ void cast_half_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __bfloat162float(in[i]);
+  if (i >= n) return;
+  if constexpr (std::is_same<T, __half>::value) out[i] = __half2float(in[i]); else out[i] = __bfloat162float(in[i]);
 }
 __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -774,7 +779,7 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
       for (int i = 0; i < 4; ++i) { gdim[i] = a.tm_gdim[i]; box[i] = a.tm_box[i]; estr[i] = 1; }
       for (int i = 0; i < 3; ++i) gstr[i] = a.tm_gstr[i];
     }
-    const CUresult r = encode_tiled()(&tm, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.in),
+    const CUresult r = encode_tiled()(&tm, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (a.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4, const_cast<void*>(a.in),
                                       gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                       p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -863,7 +868,7 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     const cuuint64_t gstr[1] = {(cuuint64_t)a.ld_out * esz};
     const cuuint32_t box[2] = {(cuuint32_t)(p.chunk_bytes / esz), (cuuint32_t)TC_BLOCK_M};
     const cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (a.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
     const CUtensorMapSwizzle sw = p.chunk_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap tmo, tmr;
     CUresult r = encode_tiled()(&tmo, dt, 2, a.out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -878,18 +883,21 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   if (smem > (size_t)TC_SMEM_LIMIT) return fail(HRP_ERR_INVALID, "conv_tc: %zu bytes of shared memory needed (block_n %d)", smem, bn);
   static bool attr_done = false;
   if (!attr_done) {
-    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = std::min(p.total_tiles, std::max(1, sms * ctas * (a.grid_pct > 0 ? a.grid_pct : 100) / 100));
   static const int pdl_early = env_int("HRP_PDL_EARLY", 0);
   p.pdl_early = pdl_early;
   cudaError_t le;
-  if (tf32) le = epi == 8 ? launch_pdl(conv_tc_kernel<true, 8>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<true, 4>, grid, tc_threads(4), smem, st, p);
-  else le = epi == 8 ? launch_pdl(conv_tc_kernel<false, 8>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<false, 4>, grid, tc_threads(4), smem, st, p);
+  if (tf32) le = epi == 8 ? launch_pdl(conv_tc_kernel<true, 8, false>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<true, 4, false>, grid, tc_threads(4), smem, st, p);
+  else if (a.f16) le = epi == 8 ? launch_pdl(conv_tc_kernel<false, 8, true>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<false, 4, true>, grid, tc_threads(4), smem, st, p);
+  else le = epi == 8 ? launch_pdl(conv_tc_kernel<false, 8, false>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<false, 4, false>, grid, tc_threads(4), smem, st, p);
   if (le != cudaSuccess) return fail(HRP_ERR_CUDA, "conv_tc_kernel launch: %s", cudaGetErrorString(le));
   HRP_CHECK_LAUNCH("conv_tc_kernel");
   return HRP_OK;
@@ -899,15 +907,40 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
 // exactly as the SWIZZLE_128B (chunk ^ (row & 7)) / SWIZZLE_64B (chunk ^ ((row >> 1) & 3)) operand layouts expect; K
 // zero-padded to a whole k-block.
 // tf32 == 2: the 3xTF32 image [num_kb][hi | lo][Cout][row_bytes], hi = rna_tf32(w), lo = rna_tf32(w - hi).
+// tf32 == 3: 2-byte elements like 0, IEEE half (round to nearest even, saturating) instead of bf16.
 size_t pack_conv_tc_bytes(int K, int Cout, int tf32, int row_bytes) {
-  return (size_t)ceil_div(K, row_bytes / (tf32 ? 4 : 2)) * Cout * row_bytes * (tf32 == 2 ? 2 : 1);
+  const bool four = tf32 == 1 || tf32 == 2;
+  return (size_t)ceil_div(K, row_bytes / (four ? 4 : 2)) * Cout * row_bytes * (tf32 == 2 ? 2 : 1);
 }
 
+namespace {
+uint16_t f32_to_f16_bits(float v) {          // round to nearest even, saturate to +-65504, subnormals kept
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t absu = u & 0x7fffffffu;
+  if (absu >= 0x7f800000u) return (uint16_t)(sign | (absu > 0x7f800000u ? 0x7e00u : 0x7bffu));   // NaN / inf (saturated)
+  float av;
+  std::memcpy(&av, &absu, 4);
+  if (av >= 65520.f) return (uint16_t)(sign | 0x7bffu);
+  if (av < 6.103515625e-5f) {                                   // subnormal half: multiples of 2^-24
+    const float scaled = av * 16777216.f;                       // exact
+    const uint32_t m = (uint32_t)std::nearbyint(scaled);        // round to nearest even (default rounding mode)
+    return (uint16_t)(sign | m);
+  }
+  uint32_t r = absu + 0xfffu + ((absu >> 13) & 1u);             // round the 13 dropped bits to nearest even
+  r = ((r >> 13) - (112u << 10));                               // rebias 127 -> 15
+  return (uint16_t)(sign | r);
+}
+}  // namespace
+
 void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, void* out) {
+  const bool f16 = tf32 == 3;
+  if (f16) tf32 = 0;
   const int ce = tf32 ? 4 : 8, chunks = row_bytes / 16, kb_elems = chunks * ce;
   const int num_kb = ceil_div(K, kb_elems);
   uint8_t* o = static_cast<uint8_t*>(out);
-  std::memset(o, 0, pack_conv_tc_bytes(K, Cout, tf32, row_bytes));
+  std::memset(o, 0, pack_conv_tc_bytes(K, Cout, f16 ? 3 : tf32, row_bytes));
   const bool x3 = tf32 == 2;
   auto rna = [](float v) { uint32_t u; std::memcpy(&u, &v, 4); if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & ~0x1fffu; float r; std::memcpy(&r, &u, 4); return r; };
   for (int kb = 0; kb < num_kb; ++kb)
@@ -924,6 +957,9 @@ void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, v
             const float hi = rna(v);                                                  // cvt.rna.tf32
             std::memcpy(chunk + e * 4, &hi, 4);
             if (x3) { const float lo = rna(v - hi); std::memcpy(chunk + (size_t)Cout * row_bytes + e * 4, &lo, 4); }
+          } else if (f16) {
+            const uint16_t hbits = f32_to_f16_bits(v);
+            std::memcpy(chunk + e * 2, &hbits, 2);
           } else {
             uint32_t u;
             std::memcpy(&u, &v, 4);
@@ -936,16 +972,18 @@ void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, v
     }
 }
 
-int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t st) {
+int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t st, int f16) {
   if (n == 0) return HRP_OK;
-  cast_f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, static_cast<__nv_bfloat16*>(out), n);
-  HRP_CHECK_LAUNCH("cast_f32_to_bf16_kernel");
+  if (f16) cast_f32_to_half_kernel<__half><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, static_cast<__half*>(out), n);
+  else cast_f32_to_half_kernel<__nv_bfloat16><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, static_cast<__nv_bfloat16*>(out), n);
+  HRP_CHECK_LAUNCH("cast_f32_to_half_kernel");
   return HRP_OK;
 }
-int cast_bf16_to_f32_launch(const void* in, float* out, size_t n, cudaStream_t st) {
+int cast_bf16_to_f32_launch(const void* in, float* out, size_t n, cudaStream_t st, int f16) {
   if (n == 0) return HRP_OK;
-  cast_bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), out, n);
-  HRP_CHECK_LAUNCH("cast_bf16_to_f32_kernel");
+  if (f16) cast_half_to_f32_kernel<__half><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const __half*>(in), out, n);
+  else cast_half_to_f32_kernel<__nv_bfloat16><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), out, n);
+  HRP_CHECK_LAUNCH("cast_half_to_f32_kernel");
   return HRP_OK;
 }
 int round_tf32_launch(const float* in, float* out, size_t n, cudaStream_t st) {

@@ -36,6 +36,8 @@ struct ConvArgs {
   float* sa_partial;
   // TF32 family only: 3xTF32 (conv_tc.cu). `w` is the pack_conv_tc(tf32 = 2) image, `in` / `res` / `out` are full fp32.
   int x3;
+  // 2-byte families only: the operands are IEEE half (f16 family) instead of bf16; `w` is the pack_conv_tc(tf32 = 3) image.
+  int f16;
 };
 
 int conv_f32_launch(const ConvArgs& a, cudaStream_t s);
@@ -53,7 +55,7 @@ int conv_slab_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t s
 // whether its activations will arrive by TMA tensor copies or by the cp.async gather.
 int conv_tc_row_bytes(const ConvArgs& a, int tf32, int* use_tma);
 size_t pack_conv_tc_bytes(int K, int Cout, int tf32, int row_bytes);
-void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, void* out);   // from pack_conv_f32's [K][Cout]; tf32 = 2: 3xTF32 image
+void pack_conv_tc(const float* w_kn, int K, int Cout, int tf32, int row_bytes, void* out);   // from pack_conv_f32's [K][Cout]; tf32 = 2: 3xTF32 image, 3: IEEE half
 // One whole BasicBlock (two 3x3/s1/p1 convs, Cin == Cout == C, BN folded, ReLU, identity residual) in one launch
 // (conv_block.cu): bf16 NHWC in/out, w1/w2 = pack_conv_tc images (64-byte operand rows), b1/b2 folded biases.
 struct BlockArgs {
@@ -63,6 +65,7 @@ struct BlockArgs {
   void* out;
   int B, H, W, C;
   int grid_pct;          // as ConvArgs::grid_pct
+  int f16;               // operands are IEEE half instead of bf16
 };
 bool conv_block_supported(const BlockArgs& a);
 int conv_block_launch(const BlockArgs& a, cudaStream_t s);
@@ -76,6 +79,7 @@ struct ChainArgs {
   const float* b[8];
   int nconv;
   int B, H, W, C;
+  int f16;               // operands are IEEE half instead of bf16
 };
 bool conv_chain_supported(const ChainArgs& a);
 int conv_chain_launch(const ChainArgs& a, cudaStream_t s);
@@ -85,8 +89,8 @@ int conv_chain_launch(const ChainArgs& a, cudaStream_t s);
 bool conv_roll_supported(const ChainArgs& a);
 int conv_roll_launch(const ChainArgs& a, void* scratch0, void* scratch1, cudaStream_t s);
 
-int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t s);
-int cast_bf16_to_f32_launch(const void* in, float* out, size_t n, cudaStream_t s);
+int cast_f32_to_bf16_launch(const float* in, void* out, size_t n, cudaStream_t s, int f16 = 0);   // f16: IEEE half instead of bf16
+int cast_bf16_to_f32_launch(const void* in, float* out, size_t n, cudaStream_t s, int f16 = 0);
 int round_tf32_launch(const float* in, float* out, size_t n, cudaStream_t s);
 
 // Stem: NCHW fp32 [B,3,Hi,Wi] -> NHWC [B,Ho,Wo,64], KxK stride 2, BN folded, ReLU. w packed [(c*KH+r)*KW+s][64].
@@ -100,13 +104,14 @@ int stem_conv_launch(const float* in_nchw, const float* w, const float* bias, vo
 // 32 elements = one 64-byte (bf16) / 128-byte (TF32) operand row, fetched by TMA through a view whose "ox" dimension
 // has a 2-pixel byte stride (overlapping windows). Taps s >= K and channel 3 carry zero weights.
 constexpr int STEM_PAD = 3, STEM_HP = 256 + 2 * STEM_PAD, STEM_WP = 264;
-int stem_pack_launch(const float* in_nchw, void* out, int B, int tf32 /*0 bf16, 1 fp32 rounded to TF32, 2 fp32 as is (3xTF32)*/, cudaStream_t s);
+int stem_pack_launch(const float* in_nchw, void* out, int B, int tf32 /*0 bf16, 1 fp32 rounded to TF32, 2 fp32 as is (3xTF32), 3 IEEE half*/, cudaStream_t s);
 
 // Same from uint8 NCHW images with the `/ 255.` of scripts/test.py:93-96 folded in (preprocess.cu); u8 -> fp32 NCHW for the
 // fp32 family's direct stem.
 int stem_pack_u8_launch(const uint8_t* in_nchw, void* out, int B, int mode, cudaStream_t s);
 int u8_to_f32_launch(const uint8_t* in, float* out, size_t n, cudaStream_t s);
 
+// `bf16` below: element type of the activations, 0 fp32, 1 bf16, 2 IEEE half
 int maxpool3x3s2_launch(const void* in, void* out, int B, int Hi, int Wi, int C, int bf16, cudaStream_t s);
 
 // out = relu( sum_i same[i] + sum_j nearest_up(low[j], 2^shift[j]) ), NHWC, up to 4 + 3 terms (HRNet fusion).

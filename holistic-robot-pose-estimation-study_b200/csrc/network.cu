@@ -292,6 +292,7 @@ struct GraphBuilder {
   bool x3 = false;       // the sub-network being built runs its convs as 3xTF32 (set per backbone in build())
   void push(OpDesc op) { op.lane = cur_lane; op.x3 = x3 ? 1 : 0; h->ops.push_back(op); }
   bool tc() const { return prec != HRP_PREC_FP32; }
+  bool two_byte() const { return prec == HRP_PREC_BF16 || prec == HRP_PREC_F16; }   // bf16 / IEEE half activations
   bool tf32() const { return prec == HRP_PREC_TF32 || prec == HRP_PREC_TF32X3; }
 
   const float* W(const std::string& name) {
@@ -337,7 +338,7 @@ struct GraphBuilder {
     Layer L; L.Cout = Cout; L.Cin = Cin; L.KH = KH; L.KW = KW; L.bias = dbias;
     if (tc()) {
       const int rb = conv_tc_row_bytes(g, tf32(), nullptr);
-      const int mode = tf32() ? (x3 ? 2 : 1) : 0;
+      const int mode = tf32() ? (x3 ? 2 : 1) : (prec == HRP_PREC_F16 ? 3 : 0);
       std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, mode, rb));
       pack_conv_tc(wp.data(), KH * KW * Cin, Cout, mode, rb, img.data());
       L.w_tc = upload_bytes(img);
@@ -470,7 +471,7 @@ struct GraphBuilder {
   Tn basic(const Tn& x, const std::string& p) {
     BlockArgs probe{};
     probe.B = 1; probe.H = x.H; probe.W = x.W; probe.C = x.C;
-    if (prec == HRP_PREC_BF16 && conv_block_supported(probe)) {
+    if (two_byte() && conv_block_supported(probe)) {
       // both convs in one launch, the intermediate stays in shared memory (conv_block.cu)
       OpDesc op{};
       op.kind = OP_BLOCK; op.cls = CLS_CONV_TC;
@@ -495,7 +496,7 @@ struct GraphBuilder {
   bool branch_chain(Tn* x, const std::string& p) {
     ChainArgs probe{};
     probe.B = 1; probe.H = x->H; probe.W = x->W; probe.C = x->C; probe.nconv = 8;
-    if (prec != HRP_PREC_BF16 || !(conv_chain_supported(probe) || conv_roll_supported(probe))) return false;
+    if (!two_byte() || !(conv_chain_supported(probe) || conv_roll_supported(probe))) return false;
     OpDesc op{};
     op.kind = OP_CHAIN; op.cls = CLS_CONV_TC;
     op.Hi = op.Ho = op.Ho_full = x->H; op.Wi = op.Wo = op.Wo_full = x->W; op.Cin = op.Cout = x->C; op.KH = op.KW = 3; op.stride = 1; op.pad_h = op.pad_w = 1;
@@ -734,7 +735,7 @@ struct GraphBuilder {
   int build() {
     h->tensors.clear(); h->ops.clear();
     prec = h->cfg.precision;
-    act_esize = prec == HRP_PREC_BF16 ? 2 : 4;
+    act_esize = two_byte() ? 2 : 4;
     {
       const char* e = getenv("HRP_NO_SA_FUSION");
       h->sa_fused = prec != HRP_PREC_FP32 && !(e && atoi(e) != 0);
@@ -1032,7 +1033,9 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
   };
   auto reads_image = [&](const OpDesc& o) { return o.in == h->t_xreg || o.in == h->t_xroot; };
   int64_t launches = 0;
-  const int bf16 = h->cfg.precision == HRP_PREC_BF16 ? 1 : 0, tf32 = (h->cfg.precision == HRP_PREC_TF32 || h->cfg.precision == HRP_PREC_TF32X3) ? 1 : 0;
+  const int f16 = h->cfg.precision == HRP_PREC_F16 ? 1 : 0;
+  const int bf16 = h->cfg.precision == HRP_PREC_BF16 ? 1 : (f16 ? 2 : 0);       // activation element type: 0 fp32, 1 bf16, 2 IEEE half
+  const int tf32 = (h->cfg.precision == HRP_PREC_TF32 || h->cfg.precision == HRP_PREC_TF32X3) ? 1 : 0;
   std::vector<cudaEvent_t> op_event(h->ops.size(), nullptr);
   auto new_event = [&]() -> cudaEvent_t {
     cudaEvent_t e = nullptr;
@@ -1076,7 +1079,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         a.B = B; a.Hi = o.Hi; a.Wi = o.Wi; a.Cin = o.Cin; a.Ho = o.Ho; a.Wo = o.Wo; a.Cout = o.Cout;
         a.KH = o.KH; a.KW = o.KW; a.stride = o.stride; a.pad_h = o.pad_h; a.pad_w = o.pad_w;
         a.out_sy = o.out_sy; a.out_sx = o.out_sx; a.out_oy = o.out_oy; a.out_ox = o.out_ox; a.Ho_full = o.Ho_full; a.Wo_full = o.Wo_full;
-        a.relu = o.relu; a.out_nchw = o.out_nchw; a.ld_out = o.ld; a.out_coff = 0; a.res_after_act = o.res_after_act; a.x3 = o.x3;
+        a.relu = o.relu; a.out_nchw = o.out_nchw; a.ld_out = o.ld; a.out_coff = 0; a.res_after_act = o.res_after_act; a.x3 = o.x3; a.f16 = f16;
         if (o.stem_tc) {
           // view of the packed image: {window 32 el, ox (2-pixel stride), padded row, frame}; the window of output
           // column ox starts at padded x = 2*ox + STEM_PAD - pad (o.pad_w carries the real padding)
@@ -1098,7 +1101,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         const Layer &L1 = h->layers[o.layer], &L2 = h->layers[o.layer2];
         BlockArgs a{};
         a.x = ptr(o.in); a.w1 = L1.w_tc; a.w2 = L2.w_tc; a.b1 = L1.bias; a.b2 = L2.bias; a.out = ptr(o.out);
-        a.B = B; a.H = o.Hi; a.W = o.Wi; a.C = o.Cin;
+        a.B = B; a.H = o.Hi; a.W = o.Wi; a.C = o.Cin; a.f16 = f16;
         if (lanes) a.grid_pct = (h->lane_pct_auto && B < 32) ? 2 * h->lane_pct[o.lane] : h->lane_pct[o.lane];
         HRP_TRY(conv_block_launch(a, st_op));
         break;
@@ -1107,7 +1110,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         ChainArgs a{};
         a.x = ptr(o.in); a.out = ptr(o.out); a.nconv = o.n_chain;
         for (int k = 0; k < o.n_chain; ++k) { a.w[k] = h->layers[o.chain[k]].w_tc; a.b[k] = h->layers[o.chain[k]].bias; }
-        a.B = B; a.H = o.Hi; a.W = o.Wi; a.C = o.Cin;
+        a.B = B; a.H = o.Hi; a.W = o.Wi; a.C = o.Cin; a.f16 = f16;
         static const int min_b = [] { const char* v = getenv("HRP_CHAIN_MIN_B"); return v ? atoi(v) : 8; }();
         if (B >= min_b) {
           if (conv_chain_supported(a)) HRP_TRY(conv_chain_launch(a, st_op));
@@ -1122,7 +1125,7 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
           const bool second = (k & 1) != 0;
           c.in = second ? T : blk[k / 2]; c.w = a.w[k]; c.bias = a.b[k]; c.res = second ? blk[k / 2] : nullptr; c.out = second ? blk[k / 2 + 1] : T;
           c.B = B; c.Hi = c.Ho = c.Ho_full = o.Hi; c.Wi = c.Wo = c.Wo_full = o.Wi; c.Cin = c.Cout = c.ld_out = o.Cin;
-          c.KH = c.KW = 3; c.stride = 1; c.pad_h = c.pad_w = 1; c.out_sy = c.out_sx = 1; c.relu = 1;
+          c.KH = c.KW = 3; c.stride = 1; c.pad_h = c.pad_w = 1; c.out_sy = c.out_sx = 1; c.relu = 1; c.f16 = f16;
           if (lanes) c.grid_pct = (h->lane_pct_auto && B < 32) ? 2 * h->lane_pct[o.lane] : h->lane_pct[o.lane];
           HRP_TRY(conv_tc_launch(c, 0, 0, st_op));
         }
@@ -1130,8 +1133,8 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         break;
       }
       case OP_STEM_PACK:
-        if (io.x_reg_u8) HRP_TRY(stem_pack_u8_launch(o.in == h->t_xroot ? io.x_root_u8 : io.x_reg_u8, ptr(o.out), B, tf32 ? (o.x3 ? 2 : 1) : 0, st_op));
-        else HRP_TRY(stem_pack_launch(static_cast<const float*>(ptr(o.in)), ptr(o.out), B, tf32 ? (o.x3 ? 2 : 1) : 0, st_op));
+        if (io.x_reg_u8) HRP_TRY(stem_pack_u8_launch(o.in == h->t_xroot ? io.x_root_u8 : io.x_reg_u8, ptr(o.out), B, tf32 ? (o.x3 ? 2 : 1) : (f16 ? 3 : 0), st_op));
+        else HRP_TRY(stem_pack_launch(static_cast<const float*>(ptr(o.in)), ptr(o.out), B, tf32 ? (o.x3 ? 2 : 1) : (f16 ? 3 : 0), st_op));
         break;
       case OP_MAXPOOL:
         HRP_TRY(maxpool3x3s2_launch(ptr(o.in), ptr(o.out), B, o.Hi, o.Wi, o.Cin, bf16, st_op));
@@ -1225,8 +1228,8 @@ extern "C" int hrp_create(const hrp_config* cfg, const hrp_fk_program* robot, in
   if (!cfg || !robot || !out) return fail(HRP_ERR_INVALID, "hrp_create: null argument");
   if (cfg->backbone != HRP_BACKBONE_RESNET50 && cfg->backbone != HRP_BACKBONE_HRNET32)
     return fail(HRP_ERR_INVALID, "hrp_create: unsupported backbone %d (resnet50 or hrnet32)", cfg->backbone);
-  if (cfg->precision != HRP_PREC_FP32 && cfg->precision != HRP_PREC_TF32 && cfg->precision != HRP_PREC_BF16 && cfg->precision != HRP_PREC_TF32X3)
-    return fail(HRP_ERR_INVALID, "hrp_create: unknown precision %d (0 fp32, 1 tf32, 2 bf16, 3 tf32x3)", cfg->precision);
+  if (cfg->precision < HRP_PREC_FP32 || cfg->precision > HRP_PREC_F16)
+    return fail(HRP_ERR_INVALID, "hrp_create: unknown precision %d (0 fp32, 1 tf32, 2 bf16, 3 tf32x3, 4 f16)", cfg->precision);
   if (cfg->n_iter < 1 || cfg->n_iter > 16) return fail(HRP_ERR_INVALID, "hrp_create: n_iter %d out of range", cfg->n_iter);
   if (cfg->image_size != 256.0f) return fail(HRP_ERR_INVALID, "hrp_create: only 256x256 inputs are supported (got %g)", cfg->image_size);
   std::unique_ptr<hrp_handle> h(new hrp_handle());
@@ -1537,7 +1540,7 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
                                int B, int Hi, int Wi, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu,
                                int precision, void* stream) {
   if (!in || !weight_oihw || !out) return fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: null argument");
-  if (precision != HRP_PREC_FP32 && precision != HRP_PREC_TF32 && precision != HRP_PREC_BF16 && precision != HRP_PREC_TF32X3)
+  if (precision < HRP_PREC_FP32 || precision > HRP_PREC_F16)
     return fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: unknown precision %d", precision);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nw = (size_t)Cout * Cin * KH * KW;
@@ -1573,11 +1576,12 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
     // tensor-core families: operands converted to the family's activation type exactly as a producing layer would
     const int x3 = precision == HRP_PREC_TF32X3;                // 3xTF32: full-fp32 operands, hi/lo split inside the kernel
     const int tf32 = precision == HRP_PREC_TF32 || x3;
-    a.x3 = x3;
+    const int f16 = precision == HRP_PREC_F16;
+    a.x3 = x3; a.f16 = f16;
     if (!conv_tc_supported(a, tf32)) rs = fail(HRP_ERR_INVALID, "hrp_conv2d_nhwc: shape not supported by the tensor-core family (Cin %% %d, Cout %% 16)", tf32 ? 16 : 32);
     const int rb = conv_tc_row_bytes(a, tf32, nullptr);
-    std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32 ? 1 + x3 : 0, rb));
-    pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32 ? 1 + x3 : 0, rb, img.data());
+    std::vector<uint8_t> img(pack_conv_tc_bytes(KH * KW * Cin, Cout, tf32 ? 1 + x3 : (f16 ? 3 : 0), rb));
+    pack_conv_tc(wp.data(), KH * KW * Cin, Cout, tf32 ? 1 + x3 : (f16 ? 3 : 0), rb, img.data());
     void* dw = dalloc(img.size());
     const size_t es = tf32 ? 4 : 2;
     void* din = dalloc(n_in * es);
@@ -1587,11 +1591,11 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
     if (rs == HRP_OK && cudaMemcpyAsync(dw, img.data(), img.size(), cudaMemcpyHostToDevice, st) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: copy failed");
     if (rs == HRP_OK && x3 && cudaMemcpyAsync(din, in, n_in * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: copy failed");
     if (rs == HRP_OK && x3 && residual && cudaMemcpyAsync(dres, residual, n_out * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: copy failed");
-    if (rs == HRP_OK && !x3) rs = tf32 ? round_tf32_launch(in, static_cast<float*>(din), n_in, st) : cast_f32_to_bf16_launch(in, din, n_in, st);
-    if (rs == HRP_OK && !x3 && residual) rs = tf32 ? round_tf32_launch(residual, static_cast<float*>(dres), n_out, st) : cast_f32_to_bf16_launch(residual, dres, n_out, st);
+    if (rs == HRP_OK && !x3) rs = tf32 ? round_tf32_launch(in, static_cast<float*>(din), n_in, st) : cast_f32_to_bf16_launch(in, din, n_in, st, f16);
+    if (rs == HRP_OK && !x3 && residual) rs = tf32 ? round_tf32_launch(residual, static_cast<float*>(dres), n_out, st) : cast_f32_to_bf16_launch(residual, dres, n_out, st, f16);
     a.in = din; a.w = dw; a.res = dres; a.out = dout;
     if (rs == HRP_OK) rs = conv_tc_launch(a, tf32, tf32, st);
-    if (rs == HRP_OK && !tf32) rs = cast_bf16_to_f32_launch(dout, out, n_out, st);
+    if (rs == HRP_OK && !tf32) rs = cast_bf16_to_f32_launch(dout, out, n_out, st, f16);
   }
   if (cudaStreamSynchronize(st) != cudaSuccess && rs == HRP_OK) rs = fail(HRP_ERR_CUDA, "hrp_conv2d_nhwc: %s", cudaGetErrorString(cudaGetLastError()));
   for (void* d : tmp) cudaFree(d);
@@ -1602,7 +1606,8 @@ extern "C" int hrp_conv2d_nhwc(const float* in, const float* weight_oihw, const 
 // image is packed once; `iters` back-to-back launches timed with CUDA events on `stream`). Tuning aid for the kernels.
 extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int Cout, int k, int stride, int with_residual,
                               int iters, float* ms_per_launch, void* stream) {
-  if (precision != HRP_PREC_TF32 && precision != HRP_PREC_BF16) return fail(HRP_ERR_INVALID, "hrp_conv_bench: tensor-core families only");
+  if (precision != HRP_PREC_TF32 && precision != HRP_PREC_BF16 && precision != HRP_PREC_F16) return fail(HRP_ERR_INVALID, "hrp_conv_bench: tensor-core families only");
+  const int f16 = precision == HRP_PREC_F16;
   if (!ms_per_launch || iters <= 0) return fail(HRP_ERR_INVALID, "hrp_conv_bench: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int tf32 = precision == HRP_PREC_TF32;
@@ -1610,15 +1615,15 @@ extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int C
   ConvArgs a{};
   a.B = B; a.Hi = H; a.Wi = W; a.Cin = Cin; a.Cout = Cout; a.KH = a.KW = k; a.stride = stride; a.pad_h = a.pad_w = k / 2;
   a.Ho = (H + 2 * a.pad_h - k) / stride + 1; a.Wo = (W + 2 * a.pad_w - k) / stride + 1;
-  a.out_sy = a.out_sx = 1; a.Ho_full = a.Ho; a.Wo_full = a.Wo; a.relu = 1; a.ld_out = Cout;
+  a.out_sy = a.out_sx = 1; a.Ho_full = a.Ho; a.Wo_full = a.Wo; a.relu = 1; a.ld_out = Cout; a.f16 = f16;
   if (!conv_tc_supported(a, tf32)) return fail(HRP_ERR_INVALID, "hrp_conv_bench: shape not supported");
   const size_t n_in = (size_t)B * H * W * Cin, n_out = (size_t)B * a.Ho * a.Wo * Cout, K = (size_t)k * k * Cin;
   std::vector<float> wp(K * Cout), bp(Cout, 0.1f);
   uint32_t lcg = 12345u;
   for (auto& v : wp) { lcg = lcg * 1664525u + 1013904223u; v = ((lcg >> 8) * (1.0f / 16777216.0f) - 0.5f) / std::sqrt((float)K); }
   const int rb = conv_tc_row_bytes(a, tf32, nullptr);
-  std::vector<uint8_t> img(pack_conv_tc_bytes((int)K, Cout, tf32, rb));
-  pack_conv_tc(wp.data(), (int)K, Cout, tf32, rb, img.data());
+  std::vector<uint8_t> img(pack_conv_tc_bytes((int)K, Cout, tf32 ? 1 : (f16 ? 3 : 0), rb));
+  pack_conv_tc(wp.data(), (int)K, Cout, tf32 ? 1 : (f16 ? 3 : 0), rb, img.data());
   void *dw = nullptr, *din = nullptr, *dout = nullptr, *dres = nullptr, *db = nullptr;
   float* tmp = nullptr;
   int rs = HRP_OK;
@@ -1631,8 +1636,8 @@ extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int C
     cudaMemcpyAsync(dw, img.data(), img.size(), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(db, bp.data(), (size_t)Cout * 4, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(tmp, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st);
-    rs = tf32 ? round_tf32_launch(tmp, static_cast<float*>(din), n_in, st) : cast_f32_to_bf16_launch(tmp, din, n_in, st);
-    if (rs == HRP_OK && with_residual) rs = tf32 ? round_tf32_launch(tmp, static_cast<float*>(dres), n_out, st) : cast_f32_to_bf16_launch(tmp, dres, n_out, st);
+    rs = tf32 ? round_tf32_launch(tmp, static_cast<float*>(din), n_in, st) : cast_f32_to_bf16_launch(tmp, din, n_in, st, f16);
+    if (rs == HRP_OK && with_residual) rs = tf32 ? round_tf32_launch(tmp, static_cast<float*>(dres), n_out, st) : cast_f32_to_bf16_launch(tmp, dres, n_out, st, f16);
     cudaStreamSynchronize(st);
   }
   a.in = din; a.w = dw; a.bias = static_cast<const float*>(db); a.res = dres; a.out = dout;
@@ -1643,7 +1648,7 @@ extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int C
     ChainArgs ch{};
     const bool chain = with_residual == 8;
     if (chain) {
-      ch.x = din; ch.out = dout; ch.nconv = 8; ch.B = B; ch.H = H; ch.W = W; ch.C = Cin;
+      ch.x = din; ch.out = dout; ch.nconv = 8; ch.B = B; ch.H = H; ch.W = W; ch.C = Cin; ch.f16 = f16;
       for (int j = 0; j < 8; ++j) { ch.w[j] = dw; ch.b[j] = static_cast<const float*>(db); }
       if (k != 3 || stride != 1 || Cin != Cout || tf32 || !(conv_chain_supported(ch) || conv_roll_supported(ch))) rs = fail(HRP_ERR_INVALID, "hrp_conv_bench: shape not taken by the chain kernels");
     }

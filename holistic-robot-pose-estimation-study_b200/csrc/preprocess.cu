@@ -11,6 +11,7 @@
 //    stem image straight from uint8 (conv_f32.cu stem_pack_kernel's layout), so a forward fed with uint8 crops uploads a
 //    quarter of the bytes and never materialises fp32 images.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "kernels.h"
 
@@ -127,7 +128,7 @@ __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restri
 }
 
 // uint8 NCHW image -> zero-padded NHWC4 operand image of the tensor-core stems (the layout of conv_f32.cu's
-// stem_pack_kernel, kernels.h), with the `/ 255.` folded in. MODE: 0 bf16, 1 fp32 rounded to TF32, 2 fp32 as is.
+// stem_pack_kernel, kernels.h), with the `/ 255.` folded in. MODE: 0 bf16, 1 fp32 rounded to TF32, 2 fp32 as is, 3 IEEE half.
 template <int MODE>
 __global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ in, void* __restrict__ out, int B) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -150,6 +151,12 @@ __global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ in, void* __rest
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v1));
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(v2));
     reinterpret_cast<uint4*>(out)[i] = make_uint4(r0, r1, r2, 0u);
+  } else if constexpr (MODE == 3) {
+    const __half2 a = __floats2half2_rn(v0, v1), c = __floats2half2_rn(v2, 0.f);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&a);
+    r.y = *reinterpret_cast<const uint32_t*>(&c);
+    reinterpret_cast<uint2*>(out)[i] = r;
   } else {
     const __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1), c = __floats2bfloat162_rn(v2, 0.f);
     uint2 r;
@@ -165,7 +172,8 @@ int stem_pack_u8_launch(const uint8_t* in_nchw, void* out, int B, int mode, cuda
   const long long total = (long long)B * STEM_HP * STEM_WP;
   if (total <= 0) return HRP_OK;
   const unsigned blocks = (unsigned)ceil_div64(total, 256);
-  if (mode == 2) stem_pack_u8_kernel<2><<<blocks, 256, 0, s>>>(in_nchw, out, B);
+  if (mode == 3) stem_pack_u8_kernel<3><<<blocks, 256, 0, s>>>(in_nchw, out, B);
+  else if (mode == 2) stem_pack_u8_kernel<2><<<blocks, 256, 0, s>>>(in_nchw, out, B);
   else if (mode == 1) stem_pack_u8_kernel<1><<<blocks, 256, 0, s>>>(in_nchw, out, B);
   else stem_pack_u8_kernel<0><<<blocks, 256, 0, s>>>(in_nchw, out, B);
   HRP_CHECK_LAUNCH("stem_pack_u8_kernel");

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdlib>
 
@@ -165,6 +166,25 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// The two 2-byte operand types of tcgen05.mma.kind::f16: bf16 (8-bit significand) and IEEE half (11-bit significand, the
+// same as TF32; conversions saturate instead of overflowing to infinity). F16 selects half.
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+  if constexpr (F16) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+    r = *reinterpret_cast<const uint32_t*>(&h2);
+  }
+  return r;
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack2(uint32_t w) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
 
 __device__ __forceinline__ float round_tf32_rna(float x) {
   uint32_t r;

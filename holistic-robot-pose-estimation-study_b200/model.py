@@ -453,7 +453,8 @@ class HostPipeline:
         self.K = [torch.empty(self.B, 3, 3, device=dev) for _ in range(depth)]
         self.kv = [torch.empty(self.B, device=dev) for _ in range(depth)]
         self.offs = model._record(self.B, dev)
-        self.host = [None] * depth
+        # pinned result buffers up front: a cudaHostAlloc inside the stream of submits synchronises the whole device
+        self.host = [torch.empty(self.offs[-1], dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
         self.ev_free = [None] * depth          # forward of the batch that last used this slot's inputs has finished
         self.ev_done = [None] * depth

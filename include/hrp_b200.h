@@ -41,6 +41,9 @@ typedef enum {
                                mode; single-pass on the ResNet-50 keypoint backbone and the DepthNet, 3xTF32 (below) on
                                the layers of an HRNet-W32 keypoint backbone */
   HRP_PREC_BF16 = 2,        /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+  HRP_PREC_F16 = 4,         /* tcgen05 kind::f16 with IEEE-half operands (11-bit significand, the same as TF32; conversions
+                               saturate at +-65504), fp32 accumulate in TMEM, fp16 NHWC activations: TF32-grade accuracy at
+                               the bf16 family's speed and memory traffic */
   HRP_PREC_TF32X3 = 3       /* 3xTF32 on every conv layer: operands split into hi + lo TF32 halves, three tcgen05 products
                                per k-step (Ahi Whi + Alo Whi + Ahi Wlo), fp32-grade results at a third of the TF32 rate.
                                HRP_PREC_TF32 itself uses it on the layers of an HRNet-W32 KEYPOINT backbone */
