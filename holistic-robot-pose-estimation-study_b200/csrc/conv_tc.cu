@@ -75,6 +75,9 @@ struct TcParams {
   int bias_off;      // byte offset of the layer's bias vector in shared memory (Cout floats, filled once per CTA)
   int cpr_log;       // log2 of 16-byte chunks per staged tile row (block_n * elem / 16)
   int round_tf32;    // round fp32 NHWC outputs to TF32 (nearest, ties away) so the next MMA sees exact operands
+  int cluster;       // CTAs per thread-block cluster (1, 2 or 4): they work on `cluster` consecutive M tiles of the SAME N tile in lockstep, and
+                     // every weight tile is fetched from L2 once per cluster (each CTA multicasts its 1/cluster of the rows to all)
+  int total_units;   // work units a cluster walks: ceil(M tiles / cluster) * tiles_n  (cluster == 1: the tiles themselves)
   int x3;            // TF32 only: 3xTF32 -- operands split into hi + lo TF32 halves, D += Ahi Whi + Alo Whi + Ahi Wlo (fp32-grade products)
 };
 
@@ -148,11 +151,19 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const ConvArgs& a = p.a;
+  // work units: unit u = (group of `cluster` consecutive M tiles, N tile), N tile fastest; CTA rank r of the cluster takes
+  // M tile group*cluster + r. Without clusters a unit is a tile and a "cluster" is one CTA.
+  const int CS = p.cluster;
+  const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = (int)blockIdx.x / CS, unit_step = (int)gridDim.x / CS;
+  const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
+#define HRP_TILE_M(u) (((u) / p.tiles_n) * CS + crank)
+#define HRP_TILE_N(u) ((u) % p.tiles_n)
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8u * s, p.tma ? 1 : TC_PRODUCERS + 1);
-      mbar_init(bar_empty + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, (uint32_t)p.cluster);     // one tcgen05.commit per CTA that received the stage's weight tile
       mbar_init(bar_split + 8u * s, TC_PRODUCERS);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8u * i, 1); mbar_init(bar_acce + 8u * i, 1); }
@@ -162,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   if (warp == 5 && lane == 0 && p.tma) asm volatile("prefetch.tensormap [%0];" ::"l"(p.tmap) : "memory");
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster > 1) cluster_sync_all(); else __syncthreads();   // peers multicast into this CTA's stages and arrive on its barriers
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -186,8 +197,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     int it = 0;
     int s = 0, as = 0;                                         // ring slot being filled / slot whose copies are awaited (lag behind)
     uint32_t ph = 1;                                           // parity to wait on for empty[s] (first pass: slots start free)
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * TC_BLOCK_M;
+    for (int u = unit0; u < p.total_units; u += unit_step) {
+      const int m0 = HRP_TILE_M(u) * TC_BLOCK_M;
       const int b0 = m0 / hw_o;                                // first image this tile touches
       const uint8_t* tile_base = in8 + (size_t)b0 * a.Hi * a.Wi * a.Cin * ESZ;
       {
@@ -252,7 +263,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const uint32_t n16 = (uint32_t)a_half >> 4;
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+      for (int u = unit0; u < p.total_units; u += unit_step)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(bar_full + 8u * s, ph);
           const uint32_t base = sA + (uint32_t)(s * a_stage);
@@ -273,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     int li = 0, s = 0;
     uint32_t ph = 0;
     const int num_kb = p.num_kb;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+    for (int u = unit0; u < p.total_units; u += unit_step, ++li) {
       const int buf = li & 1;
       if (li >= 2) mbar_wait(bar_acce + 8u * buf, ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
@@ -295,7 +306,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         for (int kk = 0; kk < nk; ++kk)
           if (leader) umma<TF32>(tmem_d, umma_desc_at(aa + 32u * kk, dhi), umma_desc_at(bb + 32u * kk, dhi), idesc, (kb | kk) != 0);
         if (leader) {
-          umma_commit(bar_empty + 8u * s);                       // frees the stage once these MMAs have read it
+          if (CS > 1) umma_commit_mc(bar_empty + 8u * s, cmask);    // ... in every CTA whose loader writes into this CTA's stage
+          else umma_commit(bar_empty + 8u * s);                  // frees the stage once these MMAs have read it
           if (kb == num_kb - 1) umma_commit(bar_accf + 8u * buf);   // accumulator complete
         }
         __syncwarp();
@@ -313,9 +325,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const uint32_t tx = (uint32_t)b_stage + (p.tma ? (uint32_t)a_half : 0u);
       int it = 0, s = 0;
       uint32_t ph = 1;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.tiles_n) * p.block_n;
-        const int m0 = (tile / p.tiles_n) * TC_BLOCK_M;
+      const uint32_t part = (uint32_t)b_half / (uint32_t)CS;     // this CTA's share of the rows of a multicast weight tile
+      for (int u = unit0; u < p.total_units; u += unit_step) {
+        const int n0 = HRP_TILE_N(u) * p.block_n;
+        const int m0 = HRP_TILE_M(u) * TC_BLOCK_M;
         const int x0 = (m0 % a.Wo) * a.stride - a.pad_w, t1 = m0 / a.Wo, y0 = (t1 % a.Ho) * a.stride - a.pad_h, b0 = t1 / a.Ho;
         const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)n0 * p.row_bytes;
         int c = 0, fr = 0, fs = 0;
@@ -325,7 +338,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           if (leader) {
             mbar_arrive_expect_tx(bar, tx);
             if (p.tma) tma_load_4d(sA + (uint32_t)(s * a_stage), p.tmap, c, x0 + fs, y0 + fr, b0, bar);
-            bulk_g2s(sB + (uint32_t)(s * b_stage), wsrc + kb * kb_stride, (uint32_t)b_half, bar);
+            if (CS > 1) bulk_g2s_mc(sB + (uint32_t)(s * b_stage) + (uint32_t)crank * part, wsrc + kb * kb_stride + (size_t)crank * part, part, bar, cmask);
+            else bulk_g2s(sB + (uint32_t)(s * b_stage), wsrc + kb * kb_stride, (uint32_t)b_half, bar);
             if (x3) bulk_g2s(sB + (uint32_t)(s * b_stage + b_half), wsrc + kb * kb_stride + (size_t)a.Cout * p.row_bytes, (uint32_t)b_half, bar);
           }
           if (p.tma) {
@@ -357,9 +371,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     }
     epi_barrier<EPI>();
     int li = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++li) {
+    for (int u = unit0; u < p.total_units; u += unit_step, ++li) {
       const int buf = li & 1;
-      const int m0 = (tile / p.tiles_n) * TC_BLOCK_M, n0 = (tile % p.tiles_n) * p.block_n;
+      const int m0 = HRP_TILE_M(u) * TC_BLOCK_M, n0 = HRP_TILE_N(u) * p.block_n;
       const int m = m0 + et;
       const bool row_ok = m < p.M;
       const int mm = row_ok ? m : 0;
@@ -460,18 +474,30 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const uint32_t bar_res = sBar + 16u * TC_MAX_STAGES + 48u + 16u * TC_BLOCK_M + 8u * (uint32_t)sb;
         const uint32_t cbytes = (uint32_t)p.chunk_bytes, chunk_sz = (uint32_t)TC_BLOCK_M * cbytes;
         const uint32_t swz = cbytes == 128 ? ((uint32_t)et & 7u) : (((uint32_t)et >> 1) & 3u);
+        // with two staging buffers the residual of tile li+1 is requested while tile li is drained, so that short-K tiles
+        // (1x1 expansions: four MMAs per tile) do not sit out a load latency each. res_prefetch == 2: requested at the START
+        // of tile li (after waiting for the store of tile li-1, issued a moment ago, to finish reading that buffer: a short
+        // stall that buys the load the whole drain as head start); == 1: at the end of tile li (below), no stall
+        const bool prefetch = has_res && p.res_prefetch != 0;
+        const bool early = prefetch && p.res_prefetch == 2;
         if (eid == 0) {                                        // the store that last read this buffer has finished reading
-          if (p.n_stg == 2) bulk_wait_read1(); else bulk_wait_read0();
+          if (p.n_stg == 2 && !early) bulk_wait_read1(); else bulk_wait_read0();
+          if (has_res && (!prefetch || li == 0)) {
+            mbar_arrive_expect_tx(bar_res, (uint32_t)p.n_chunks * chunk_sz);
+            for (int k = 0; k < p.n_chunks; ++k)
+              tma_load_2d(tile_stg + (uint32_t)k * chunk_sz, p.tmap_res, a.out_coff + n0 + k * (int)(cbytes / ESZ), m0, bar_res);
+          }
+          const int next = u + unit_step;
+          if (early && next < p.total_units) {
+            const int m1 = HRP_TILE_M(next) * TC_BLOCK_M, n1 = HRP_TILE_N(next) * p.block_n;
+            const uint32_t stg1 = stg + (uint32_t)(sb ^ 1) * (uint32_t)(p.n_chunks * TC_BLOCK_M * p.chunk_bytes);
+            const uint32_t bar1 = bar_res - 8u * (uint32_t)sb + 8u * (uint32_t)(sb ^ 1);
+            mbar_arrive_expect_tx(bar1, (uint32_t)p.n_chunks * chunk_sz);
+            for (int k = 0; k < p.n_chunks; ++k)
+              tma_load_2d(stg1 + (uint32_t)k * chunk_sz, p.tmap_res, a.out_coff + n1 + k * (int)(cbytes / ESZ), m1, bar1);
+          }
         }
         epi_barrier<EPI>();
-        // with two staging buffers the residual of tile li+1 is requested at the end of tile li (below), so that short-K
-        // tiles (1x1 expansions: four MMAs per tile) do not sit out a load latency each; only the first tile asks here
-        const bool prefetch = has_res && p.res_prefetch != 0;
-        if (has_res && eid == 0 && (!prefetch || li == 0)) {
-          mbar_arrive_expect_tx(bar_res, (uint32_t)p.n_chunks * chunk_sz);
-          for (int k = 0; k < p.n_chunks; ++k)
-            tma_load_2d(tile_stg + (uint32_t)k * chunk_sz, p.tmap_res, a.out_coff + n0 + k * (int)(cbytes / ESZ), m0, bar_res);
-        }
         mbar_wait(bar_accf + 8u * buf, (li >> 1) & 1);
         tc_fence_after();
         if (has_res) mbar_wait(bar_res, p.n_stg == 2 ? ((li >> 1) & 1) : (li & 1));
@@ -544,10 +570,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           for (int k = 0; k < p.n_chunks; ++k)
             tma_store_2d(p.tmap_out, a.out_coff + n0 + k * (int)(cbytes / ESZ), m0, tile_stg + (uint32_t)k * chunk_sz);
           bulk_commit();
-          const int next = tile + (int)gridDim.x;
-          if (prefetch && next < p.total_tiles) {
+          const int next = u + unit_step;
+          if (prefetch && !early && next < p.total_units) {
             bulk_wait_read1();                                 // the store of tile li-1 has finished reading the other buffer
-            const int m1 = (next / p.tiles_n) * TC_BLOCK_M, n1 = (next % p.tiles_n) * p.block_n;
+            const int m1 = HRP_TILE_M(next) * TC_BLOCK_M, n1 = HRP_TILE_N(next) * p.block_n;
             const uint32_t stg1 = stg + (uint32_t)(sb ^ 1) * (uint32_t)(p.n_chunks * TC_BLOCK_M * p.chunk_bytes);
             const uint32_t bar1 = bar_res - 8u * (uint32_t)sb + 8u * (uint32_t)(sb ^ 1);
             mbar_arrive_expect_tx(bar1, (uint32_t)p.n_chunks * chunk_sz);
@@ -659,11 +685,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     if (p.epi_tma && eid == 0) bulk_wait_read0();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync_all(); else __syncthreads();     // a peer's last commits still arrive on this CTA's barriers
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+#undef HRP_TILE_M
+#undef HRP_TILE_N
 }
 
 template <typename T>
@@ -825,7 +853,7 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   if (a.sa_partial != nullptr) epi = 4;
   int ctas = (epi == 4 && p.total_tiles >= 2 * sms && tm <= 256) ? 2 : 1;
   if (force_ctas) ctas = (epi == 4 && force_ctas == 2 && tm <= 256) ? 2 : 1;
-  size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 1024 : 0);
+  size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 512 : 0);       // two CTAs: 113 KB each + 1 KB reserved = 228 KB
   if (budget_kb > 0 && a.grid_pct > 0) budget = std::min(budget, (size_t)budget_kb * 1024);   // experiment: leave room for a CTA of another lane's kernel
   // TMA epilogue: dense NHWC output whose tile rows are consecutive rows of the [M][Cout] matrix
   static const int no_epi_tma = env_int("HRP_TC_NO_EPI_TMA", 0);
@@ -845,7 +873,8 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     p.n_stg = (2048 + 2 * one + tc_tail_bytes() + (size_t)a.Cout * 4 + min_stages * opnd * tc_stage_bytes(bn, p.row_bytes) <= budget) ? 2 : 1;
     staging = (p.n_stg * one + 1023) / 1024 * 1024;
     static const int no_prefetch = env_int("HRP_TC_NO_RES_PREFETCH", 0);
-    p.res_prefetch = (p.n_stg == 2 && a.res != nullptr && !no_prefetch) ? 1 : 0;
+    static const int early = env_int("HRP_TC_RES_EARLY", 1);
+    p.res_prefetch = (p.n_stg == 2 && a.res != nullptr && !no_prefetch) ? (early ? 2 : 1) : 0;
   }
   const size_t fixed = 2048 + staging + tc_tail_bytes() + (size_t)a.Cout * 4;
   int smax = (int)((budget - fixed) / (opnd * tc_stage_bytes(bn, p.row_bytes)));
@@ -891,13 +920,37 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     HRP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr_done = true;
   }
-  const int grid = std::min(p.total_tiles, std::max(1, sms * ctas * (a.grid_pct > 0 ? a.grid_pct : 100) / 100));
+  // Thread-block clusters (HRP_TC_CLUSTER=2|4, off by default): `cs` CTAs take consecutive M tiles of one N tile and share
+  // every weight tile through one multicast fetch. Weights re-read by every M tile are 27 % of the network's L2 request
+  // bytes, but halving / quartering them left the whole-network rate where it was (13.40k / 13.41k / 13.43k frames/s for
+  // cluster 1 / 2 / 4 on the same box) and made single layers 2-5 % (cluster 2) to 50 % (cluster 4, short-K layers) slower
+  // because the CTAs of a cluster advance in lockstep: the multi-lane graph is bound by SM time, not by L2 requests
+  // (profiles/r02_throughput_experiments.txt). Kept as a measured switch. Needs a whole number of M-tile groups.
+  static const int cl_env = env_int("HRP_TC_CLUSTER", 1);
+  const int cap = std::max(1, sms * ctas * (a.grid_pct > 0 ? a.grid_pct : 100) / 100);
+  int cs = 1;
+  if (!x3)
+    for (int c = std::min(cl_env, 4); c >= 2; c >>= 1)
+      if ((c & (c - 1)) == 0 && mtiles % c == 0 && cap >= c && (bn / c) % 8 == 0) { cs = c; break; }
+  p.cluster = cs;
+  p.total_units = (mtiles / cs) * p.tiles_n;
+  if (cs == 1) p.total_units = p.total_tiles;
+  int grid = std::min(p.total_units * cs, cap);
+  grid -= grid % cs;
+  size_t smem_req = smem;
+  if (cs > 1) {
+    // A cluster CTA that holds TMEM may wait for a peer that is still waiting for TMEM on another SM, so cluster CTAs must
+    // never oversubscribe an SM's 512 columns among themselves: each asks for at least its TMEM share of the SM's shared
+    // memory (228 KB, 1 KB reserved per CTA), which makes the co-residency limit the stricter of the two.
+    const size_t share = ((size_t)228 * 1024 * tm + 511) / 512;
+    smem_req = std::min((size_t)TC_SMEM_LIMIT, std::max(smem, share > 1024 ? share - 1024 : 0));
+  }
   static const int pdl_early = env_int("HRP_PDL_EARLY", 0);
   p.pdl_early = pdl_early;
   cudaError_t le;
-  if (tf32) le = epi == 8 ? launch_pdl(conv_tc_kernel<true, 8, false>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<true, 4, false>, grid, tc_threads(4), smem, st, p);
-  else if (a.f16) le = epi == 8 ? launch_pdl(conv_tc_kernel<false, 8, true>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<false, 4, true>, grid, tc_threads(4), smem, st, p);
-  else le = epi == 8 ? launch_pdl(conv_tc_kernel<false, 8, false>, grid, tc_threads(8), smem, st, p) : launch_pdl(conv_tc_kernel<false, 4, false>, grid, tc_threads(4), smem, st, p);
+  if (tf32) le = epi == 8 ? launch_pdl(conv_tc_kernel<true, 8, false>, grid, tc_threads(8), smem_req, st, p, cs) : launch_pdl(conv_tc_kernel<true, 4, false>, grid, tc_threads(4), smem_req, st, p, cs);
+  else if (a.f16) le = epi == 8 ? launch_pdl(conv_tc_kernel<false, 8, true>, grid, tc_threads(8), smem_req, st, p, cs) : launch_pdl(conv_tc_kernel<false, 4, true>, grid, tc_threads(4), smem_req, st, p, cs);
+  else le = epi == 8 ? launch_pdl(conv_tc_kernel<false, 8, false>, grid, tc_threads(8), smem_req, st, p, cs) : launch_pdl(conv_tc_kernel<false, 4, false>, grid, tc_threads(4), smem_req, st, p, cs);
   if (le != cudaSuccess) return fail(HRP_ERR_CUDA, "conv_tc_kernel launch: %s", cudaGetErrorString(le));
   HRP_CHECK_LAUNCH("conv_tc_kernel");
   return HRP_OK;
