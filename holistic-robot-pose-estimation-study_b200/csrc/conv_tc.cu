@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cmath>
 #include <type_traits>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -817,16 +818,22 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   }
   const int mtiles = ceil_div(p.M, TC_BLOCK_M);
   const int sms = sm_count();
-  // N tile: every CTA re-reads its activation rows, so wide tiles cut that traffic; take the widest that still
-  // leaves about one tile per SM, else the narrowest. (TF32: <= 128 so the fp32 staging tile fits beside the stages.)
+  // N tile: every CTA re-reads its activation rows, so wide tiles cut that traffic and run the MMAs at their full rate; take
+  // the widest that still leaves about one tile per SM THIS LAUNCH MAY HOLD (inside the multi-lane graph a launch is capped
+  // at a quarter of the GPU and the SMs are fully subscribed by the other lanes and plans, so what a layer costs is its
+  // duration x the SMs it holds: at that cap the 2048->256 deconv phases @8x8 take 185 us on 37 SMs with 64-wide tiles and
+  // 53 us on 32 SMs with 256-wide ones; profiles/r02_tile_width_at_quarter_gpu.txt), else the narrowest.
+  // (TF32: <= 128 so the fp32 staging tile fits beside the stages.)
   static const int force_bn = env_int("HRP_TC_BN", 0), force_stages = env_int("HRP_TC_STAGES", 0), force_ctas = env_int("HRP_TC_CTAS", 0);
   static const int budget_kb = env_int("HRP_TC_BUDGET_KB", 0), bn_max = env_int("HRP_TC_BN_MAX", 256);
+  static const int bn_full = env_int("HRP_TC_BN_FULL_GPU", 0);        // 1: size tiles as if the launch had the whole GPU (the old rule)
+  const int sm_share = (a.grid_pct > 0 && !bn_full) ? std::max(1, sms * a.grid_pct / 100) : sms;
   const int cand[4] = {256, 128, 64, 32};
   int bn = 0;
   for (int i = tf32 ? 1 : 0; i < 4; ++i) {
     if (a.Cout % cand[i] || cand[i] > bn_max) continue;
     bn = cand[i];
-    if ((long long)mtiles * (a.Cout / cand[i]) >= (sms * 4) / 5) break;
+    if ((long long)mtiles * (a.Cout / cand[i]) >= (sm_share * 4) / 5) break;
   }
   if (bn == 0) return fail(HRP_ERR_INVALID, "conv_tc: Cout=%d must be a multiple of 32", a.Cout);
   // very short K (1x1 expansions out of 64 / 128 channels): the tile is all epilogue and the layer is bound by the bytes it
@@ -851,7 +858,8 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   int epi = (bn >= 128 && p.Ktot <= 256 && !short_k) ? 8 : 4;
   if (force_epi == 4 || force_epi == 8) epi = force_epi;
   if (a.sa_partial != nullptr) epi = 4;
-  int ctas = (epi == 4 && p.total_tiles >= 2 * sms && tm <= 256) ? 2 : 1;
+  static const int ctas_share = env_int("HRP_TC_CTAS_SHARE", 0);
+  int ctas = (epi == 4 && p.total_tiles >= 2 * (ctas_share ? sm_share : sms) && tm <= 256) ? 2 : 1;
   if (force_ctas) ctas = (epi == 4 && force_ctas == 2 && tm <= 256) ? 2 : 1;
   size_t budget = (size_t)TC_SMEM_LIMIT / ctas - (ctas > 1 ? 512 : 0);       // two CTAs: 113 KB each + 1 KB reserved = 228 KB
   if (budget_kb > 0 && a.grid_pct > 0) budget = std::min(budget, (size_t)budget_kb * 1024);   // experiment: leave room for a CTA of another lane's kernel
@@ -945,6 +953,9 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     const size_t share = ((size_t)228 * 1024 * tm + 511) / 512;
     smem_req = std::min((size_t)TC_SMEM_LIMIT, std::max(smem, share > 1024 ? share - 1024 : 0));
   }
+  static const int dbg = env_int("HRP_TC_DEBUG", 0);
+  if (dbg) fprintf(stderr, "conv_tc %dx%d %d->%d k%d s%d res%d: bn %d epi %d ctas %d grid %d stages %d n_stg %d smem %zu tiles %d\n", a.Hi, a.Wi, a.Cin, a.Cout, a.KH,
+                   a.stride, a.res != nullptr, bn, epi, ctas, grid, p.stages, p.n_stg, smem_req, p.total_tiles);
   static const int pdl_early = env_int("HRP_PDL_EARLY", 0);
   p.pdl_early = pdl_early;
   cudaError_t le;

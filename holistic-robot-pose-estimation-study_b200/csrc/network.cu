@@ -1616,6 +1616,7 @@ extern "C" int hrp_conv_bench(int precision, int B, int H, int W, int Cin, int C
   a.B = B; a.Hi = H; a.Wi = W; a.Cin = Cin; a.Cout = Cout; a.KH = a.KW = k; a.stride = stride; a.pad_h = a.pad_w = k / 2;
   a.Ho = (H + 2 * a.pad_h - k) / stride + 1; a.Wo = (W + 2 * a.pad_w - k) / stride + 1;
   a.out_sy = a.out_sx = 1; a.Ho_full = a.Ho; a.Wo_full = a.Wo; a.relu = 1; a.ld_out = Cout; a.f16 = f16;
+  if (const char* e = getenv("HRP_BENCH_PCT")) a.grid_pct = atoi(e);      // the share of the GPU a launch gets inside the multi-lane graph
   if (!conv_tc_supported(a, tf32)) return fail(HRP_ERR_INVALID, "hrp_conv_bench: shape not supported");
   const size_t n_in = (size_t)B * H * W * Cin, n_out = (size_t)B * a.Ho * a.Wo * Cout, K = (size_t)k * k * Cin;
   std::vector<float> wp(K * Cout), bp(Cout, 0.1f);
