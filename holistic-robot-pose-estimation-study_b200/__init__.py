@@ -13,7 +13,7 @@ __all__ = ["arch", "consts", "synth", "urdf"]
 def __getattr__(name):
     # native-backed modules are imported lazily so that pure-Python users (weight generation, URDF compilation)
     # do not need the CUDA library
-    if name in ("capi", "model"):
+    if name in ("capi", "model", "metrics"):
         import importlib
         return importlib.import_module("." + name, __name__)
     if name == "HoliRobPoseB200":

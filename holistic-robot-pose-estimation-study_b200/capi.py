@@ -19,6 +19,7 @@ EXPORTS = (
     "hrp_conv2d_nhwc", "hrp_basic_block_nhwc", "hrp_basic_chain_nhwc", "hrp_create", "hrp_destroy", "hrp_num_weights", "hrp_weight_name", "hrp_weight_shape",
     "hrp_set_weight", "hrp_finalize_weights", "hrp_output_offsets", "hrp_workspace_bytes", "hrp_forward", "hrp_forward_ex",
     "hrp_forward_timed", "hrp_release_plans", "hrp_forward_u8", "hrp_crop_resize_u8",
+    "hrp_metrics_batch", "hrp_summary_workspace", "hrp_summary_add_pck",
     "hrp_set_option", "hrp_launch_count", "hrp_debug_tensor", "hrp_forward_profile", "hrp_conv_bench", "hrp_last_error",
     "hrp_version",
 )
@@ -80,6 +81,10 @@ def lib():
         L.hrp_release_plans.argtypes = [vp]
         L.hrp_forward_u8.argtypes = [vp, f32p, f32p, f32p, f32p, i32, f32p, vp]
         L.hrp_crop_resize_u8.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.hrp_metrics_batch.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+        L.hrp_summary_workspace.argtypes = [i64]
+        L.hrp_summary_workspace.restype = C.c_size_t
+        L.hrp_summary_add_pck.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
         L.hrp_set_option.argtypes = [vp, C.c_char_p, i64]
         L.hrp_launch_count.argtypes = [vp]
         L.hrp_launch_count.restype = i64

@@ -201,6 +201,22 @@ def make_fk_inputs(robot, n, seed):
     return q, rot6d, trans, K
 
 
+def make_metrics_inputs(robot, n, seed):
+    """Evaluation-tail inputs: a ground-truth pose sweep and a prediction = ground truth + noise (a few
+    centimetres / hundredths of a radian, growing along the batch so the ADD curve has a shape), the ORIGINAL camera (640x480).
+    Returns dict of float32 arrays: gt_q, gt_rot, gt_trans, q, rot, trans, K."""
+    gq, grot, gtr, _ = make_fk_inputs(robot, n, seed)
+    g = np.random.Generator(np.random.PCG64([int(seed), 11]))
+    amp = np.linspace(0.05, 1.5, n)[:, None]
+    q = (gq + 0.04 * amp * g.standard_normal(gq.shape)).astype(np.float32)
+    rot = (grot + 0.02 * amp * g.standard_normal(grot.shape)).astype(np.float32)
+    trans = (gtr + 0.03 * amp * g.standard_normal(gtr.shape)).astype(np.float32)
+    K = np.zeros((n, 3, 3), np.float32)
+    K[:, 0, 0] = g.uniform(500.0, 650.0, n); K[:, 1, 1] = K[:, 0, 0] * g.uniform(0.98, 1.02, n)
+    K[:, 0, 2] = g.uniform(300.0, 340.0, n); K[:, 1, 2] = g.uniform(220.0, 260.0, n); K[:, 2, 2] = 1.0
+    return dict(gt_q=gq, gt_rot=grot, gt_trans=gtr, q=q, rot=rot, trans=trans, K=K)
+
+
 def make_heatmaps(batch, nkpt, seed, mode="blobs"):
     """Adversarial heatmap logits [B, nkpt*64, 64, 64] fp32 for kernel-level soft-argmax tests."""
     g = np.random.Generator(np.random.PCG64([int(seed), 4]))

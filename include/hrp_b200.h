@@ -207,6 +207,25 @@ int hrp_forward_u8(hrp_handle* h, const uint8_t* x_reg, const uint8_t* x_root, c
 int hrp_crop_resize_u8(const uint8_t* frames, int B, int Hf, int Wf, const int32_t* crop_box, const float* k_box,
                        const float* K_in, uint8_t* crops, float* K_out, float* k_value, void* stream);
 
+/* Evaluation tail on the device, replacing compute_metrics_batch (lib/utils/metrics.py:8-118; callers
+ * lib/core/function.py:158-172, scripts/test.py:167-181). pred_xyz [B,nkpt,3] / pred_uv [B,nkpt,2]: the predicted pose through
+ * hrp_fk_project with the ORIGINAL camera matrix (metrics.py:29-42); pred_joint [B,dof] or NULL (metrics.py:90-92: zeros);
+ * gt_xyz, gt_uv, gt_joint: ground truth of the batch. joint_cols: columns averaged per frame (dof, Panda dof-1:
+ * metrics.py:87-88). Outputs (device): per_frame [B,6] = error3d, error2d (mean over keypoints with gt inside the 640x480 frame;
+ * NaN when none is), mean_jointerror, error_depth, batch_error_relative, error3d_relative; dis3d [nkpt], dis2d [nkpt],
+ * l1_joint [dof] = the batch means per keypoint / joint. */
+int hrp_metrics_batch(const float* pred_xyz, const float* pred_uv, const float* pred_joint, const float* gt_xyz,
+                      const float* gt_uv, const float* gt_joint, int B, int nkpt, int dof, int root_kp, int joint_cols,
+                      float* per_frame, float* dis3d, float* dis2d, float* l1_joint, void* stream);
+
+/* summary_add_pck (lib/utils/metrics.py:121-162; scripts/test.py:232-233) over the per-frame error lists of a whole run, kept on
+ * the device: dis3d [N] metres, dis2d [N] pixels -> out22 (device, fp64): for dis3d then dis2d, {mean, median, AUC (trapezoid of
+ * the fraction under np.arange(0, 0.1, 1e-5) metres / np.arange(0, 20, 0.01) pixels, over the range), fraction <= each of the
+ * eight table thresholds (1,5,10,20,40,60,80,100 mm / 2.5,...,20 px)}. workspace: hrp_summary_workspace(N) bytes. */
+size_t hrp_summary_workspace(int64_t N);
+int hrp_summary_add_pck(const float* dis3d, const float* dis2d, int64_t N, double* out22, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* Plans (workspace + CUDA graph) are cached per batch size: at most "max_cached_batches" distinct sizes (default 4, least
  * recently used dropped first), and a second / third plan of a size only when forwards of that size arrive on different
  * streams. hrp_release_plans frees every cached plan now (waits for the forwards that use them); the next forward

@@ -35,6 +35,7 @@ FULLNET = [("panda", "resnet50", 2, 2024), ("kuka", "resnet50", 2, 2025), ("baxt
 UNDAMPED = [("panda", "resnet50", 2, 2031), ("panda", "hrnet32", 1, 2032)]
 LOGIT_STRIDES = (37, 5, 7)
 FK_N, FK_SEED = 512, 99
+METRICS_N, METRICS_SEED = 400, 2718
 SA_CASES = [("resnet50", 7, "blobs", 2, 11), ("resnet50", 7, "extreme", 2, 12), ("resnet50", 17, "noise", 1, 13),
             ("hrnet32", 8, "blobs", 2, 14), ("hrnet32", 17, "extreme", 1, 15)]
 
@@ -187,10 +188,47 @@ def preprocess():
     print("preprocess", np.stack(crops).shape, "k_value", kvs)
 
 
+def metrics():
+    """compute_metrics_batch + summary_add_pck of the reference itself (lib/utils/metrics.py) on synth.make_metrics_inputs."""
+    ns = harness.setup()
+    import warnings
+    from utils import metrics as ref_metrics
+    for robot in ("panda", "kuka", "baxter"):
+        r = ns.urdf_robot.URDFRobot(robot)
+        root = consts.ROBOTS[robot]["ref_kp"]
+        d = synth.make_metrics_inputs(robot, METRICS_N, METRICS_SEED)
+        with torch.no_grad():
+            kp = (lambda q, ro, tr: r.get_keypoints(q, ro, tr)) if root == 0 else (lambda q, ro, tr: r.get_keypoints_root(q, ro, tr, root=root))
+            gt_xyz = kp(t(d["gt_q"]), t(d["gt_rot"]), t(d["gt_trans"]))
+            gt_uv = ns.transforms.point_projection_from_3d_tensor(t(d["K"]), gt_xyz)
+            gt_uv[3] = -50.0                                  # one frame with no keypoint inside the image: error2d = 0/0
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = ref_metrics.compute_metrics_batch(r, gt_xyz, gt_uv, t(d["K"]), t(d["gt_q"]), pred_joint=t(d["q"]), pred_rot=t(d["rot"]),
+                                                        pred_trans=t(d["trans"]), pred_depth=None, pred_xy=None, pred_xyz_integral=None,
+                                                        reference_keypoint_id=root)
+                pred_xyz = kp(t(d["q"]), t(d["rot"]), t(d["trans"]))
+                res_nojoint = ref_metrics.compute_metrics_batch(r, gt_xyz, gt_uv, t(d["K"]), t(d["gt_q"]), pred_joint=None, pred_rot=None, pred_trans=None,
+                                                                pred_xyz_integral=pred_xyz, reference_keypoint_id=root)
+                ok = ~np.isnan(np.asarray(res[1]))
+                alldis = {"dis3d": list(np.asarray(res[0])[ok]), "dis2d": list(np.asarray(res[1])[ok])}
+                summ = ref_metrics.summary_add_pck(alldis)
+        names = ["error3d", "error2d", "dis3d", "dis2d", "l1_jointerror", "mean_jointerror", "error_depth", "batch_error_relative", "error3d_relative"]
+        out = {n_: np.asarray(v) for n_, v in zip(names, res)}
+        out.update({"nojoint_" + n_: np.asarray(v) for n_, v in zip(names, res_nojoint)})
+        out["summary_keys"] = np.asarray(list(summ.keys()))
+        out["summary_values"] = np.asarray([float(v) for v in summ.values()], np.float64)
+        out["summary_dtypes"] = np.asarray([type(v).__name__ for v in summ.values()])
+        out["gt_xyz"] = gt_xyz.numpy(); out["gt_uv"] = gt_uv.numpy(); out["pred_xyz"] = pred_xyz.numpy()
+        out["meta"] = np.asarray([METRICS_SEED, METRICS_N, root])
+        np.savez_compressed(os.path.join(OUT, "metrics_%s.npz" % robot), **out)
+        print("metrics", robot, {k: (round(float(v), 5)) for k, v in list(summ.items())[:6]}, "error2d NaN frames:", int((~ok).sum()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    what = sys.argv[1:] or ["fk", "softargmax", "fullnet", "undamped", "checkpoint", "preprocess"]
+    what = sys.argv[1:] or ["fk", "softargmax", "fullnet", "undamped", "checkpoint", "preprocess", "metrics"]
     if "fk" in what:
         fk()
     if "softargmax" in what:
@@ -205,3 +243,5 @@ if __name__ == "__main__":
         checkpoint()
     if "preprocess" in what:
         preprocess()
+    if "metrics" in what:
+        metrics()

@@ -802,3 +802,58 @@ def test_fullnet_tensor_core_families_against_reference_golden(prec, robot, back
         rel = float(np.linalg.norm(a - g[key]) / np.linalg.norm(g[key]))
         assert rel < t["rel"], (name, rel)
     assert m.launch_count() > 300
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot", ["panda", "kuka", "baxter"])
+def test_metrics_tail_against_reference_golden(robot, dev):
+    """compute_metrics_batch / summary_add_pck on the device (8f N4) against the reference's own outputs and the oracle port."""
+    from hrp_b200 import metrics as hm
+    from hrp_b200.model import FkRobot
+    from oracle import metrics as ometrics
+    g = helpers.load_golden("metrics_%s.npz" % robot)
+    seed, n, root = (int(v) for v in g["meta"])
+    d = synth.make_metrics_inputs(robot, n, seed)
+    fk = FkRobot(robot)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    names = ["error3d", "error2d", "dis3d", "dis2d", "l1_jointerror", "mean_jointerror", "error_depth", "batch_error_relative", "error3d_relative"]
+    # the reference's call (scripts/test.py:167-181): poses in, FK + projection with the original camera inside
+    res = hm.compute_metrics_batch(fk, T(g["gt_xyz"]), T(g["gt_uv"]), T(d["K"]), T(d["gt_q"]), pred_joint=T(d["q"]), pred_rot=T(d["rot"]),
+                                   pred_trans=T(d["trans"]), pred_depth=None, pred_xy=None, pred_xyz_integral=None, reference_keypoint_id=root)
+    assert len(res) == 9
+    # FK runs in fp32 on both sides with different operation orders: 2e-6 m on the keypoints, amplified by the projection (f/z ~ 1e3)
+    tol = dict(error3d=5e-6, error2d=5e-3, dis3d=5e-6, dis2d=5e-3, l1_jointerror=1e-6, mean_jointerror=1e-6, error_depth=5e-6,
+               batch_error_relative=5e-6, error3d_relative=5e-6)
+    for k, v in zip(names, res):
+        np.testing.assert_allclose(np.asarray(v, np.float32), g[k], rtol=2e-5, atol=tol[k], equal_nan=True, err_msg=k)
+    assert np.isnan(res[1][3])                                                       # no keypoint inside the frame: 0/0 like numpy
+    # given 3-D points instead of a pose (metrics.py:22-26): no FK, joint errors reported as zeros
+    res2 = hm.compute_metrics_batch(fk, T(g["gt_xyz"]), T(g["gt_uv"]), T(d["K"]), T(d["gt_q"]), pred_joint=None, pred_rot=None, pred_trans=None,
+                                    pred_xyz_integral=T(g["pred_xyz"]), reference_keypoint_id=root)
+    want = ometrics.batch_errors(g["pred_xyz"], g["gt_xyz"], g["gt_uv"], d["K"], d["gt_q"], None, root, robot)
+    for k, v, w in zip(names, res2, want):
+        np.testing.assert_allclose(np.asarray(v, np.float32), g["nojoint_" + k], rtol=2e-5, atol=tol[k] if "2d" in k else 2e-6, equal_nan=True, err_msg=k)
+        np.testing.assert_allclose(np.asarray(v, np.float32), np.asarray(w, np.float32), rtol=2e-5, atol=tol[k] if "2d" in k else 2e-6, equal_nan=True, err_msg=k)
+    # the run summary from the SAME per-frame lists the reference summarised (exact inputs -> tight tolerance)
+    ok = ~np.isnan(g["error2d"])
+    s = hm.summary_add_pck({"dis3d": list(g["error3d"][ok]), "dis2d": list(g["error2d"][ok])})
+    assert list(s.keys()) == [str(k) for k in g["summary_keys"]]
+    for k, v in zip(g["summary_keys"], g["summary_values"]):
+        np.testing.assert_allclose(float(s[str(k)]), v, rtol=1e-6, atol=1e-9, err_msg=str(k))
+    # device-resident accumulation over batches (ErrorLog) gives the same summary; odd and even list lengths for the median
+    log = hm.ErrorLog(dev, capacity=64)
+    pf, _, _, _ = hm.metrics_batch_device(fk, T(g["gt_xyz"]), T(g["gt_uv"]), T(d["K"]), T(d["gt_q"]), pred_xyz_integral=T(g["pred_xyz"]))
+    keep = torch.from_numpy(ok).to(dev)
+    for lo in range(0, n, 96):
+        sel = pf[lo:lo + 96][keep[lo:lo + 96]]
+        log.extend(sel)
+    assert log.n == int(ok.sum())
+    s2 = log.summary()
+    for k in s:
+        np.testing.assert_allclose(float(s2[k]), float(s[k]), rtol=1e-5, atol=1e-7, err_msg=k)
+    for m in (log.n - 1, 7):
+        e3, e2 = g["error3d"][ok][:m], g["error2d"][ok][:m]
+        s3 = hm.summary_add_pck({"dis3d": T(e3), "dis2d": T(e2)})
+        w3 = ometrics.summary(e3, e2)
+        for k in w3:
+            np.testing.assert_allclose(float(s3[k]), float(w3[k]), rtol=1e-6, atol=1e-9, err_msg=k)

@@ -129,3 +129,26 @@ def test_preprocess_matches_reference():
         np.testing.assert_allclose(Kn, g["K"][i], rtol=0, atol=1e-4)
         np.testing.assert_allclose(kv, g["k_value"][i], rtol=1e-6)
     assert crop[0][2] - crop[0][0] == 256          # the no-resize branch is part of the fixture
+
+
+@pytest.mark.parametrize("robot", ["panda", "kuka", "baxter"])
+def test_metrics_match_reference(robot):
+    """Evaluation tail (8f N4): the port of compute_metrics_batch / summary_add_pck against what the reference's own functions
+    returned (metrics.py:8-162), including a frame with no keypoint inside the image (error2d = NaN) and the no-joint branch."""
+    from oracle import metrics as ometrics
+    g = helpers.load_golden("metrics_%s.npz" % robot)
+    seed, n, root = (int(v) for v in g["meta"])
+    d = synth.make_metrics_inputs(robot, n, seed)
+    names = ["error3d", "error2d", "dis3d", "dis2d", "l1_jointerror", "mean_jointerror", "error_depth", "batch_error_relative", "error3d_relative"]
+    res = ometrics.batch_errors(g["pred_xyz"], g["gt_xyz"], g["gt_uv"], d["K"], d["gt_q"], d["q"], root, robot)
+    for k, v in zip(names, res):
+        np.testing.assert_allclose(np.asarray(v), g[k], rtol=2e-5, atol=2e-6, equal_nan=True, err_msg=k)
+    res = ometrics.batch_errors(g["pred_xyz"], g["gt_xyz"], g["gt_uv"], d["K"], d["gt_q"], None, root, robot)
+    for k, v in zip(names, res):
+        np.testing.assert_allclose(np.asarray(v), g["nojoint_" + k], rtol=2e-5, atol=2e-6, equal_nan=True, err_msg=k)
+    assert np.isnan(g["error2d"]).sum() >= 1 and np.isnan(g["error2d"][3])
+    ok = ~np.isnan(g["error2d"])
+    s = ometrics.summary(g["error3d"][ok], g["error2d"][ok])
+    assert list(s.keys()) == [str(k) for k in g["summary_keys"]]
+    for k, v in zip(g["summary_keys"], g["summary_values"]):
+        np.testing.assert_allclose(float(s[str(k)]), v, rtol=1e-6, atol=1e-9, err_msg=str(k))
