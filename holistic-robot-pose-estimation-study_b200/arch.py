@@ -104,8 +104,16 @@ def _linear(p, cin, cout):
     yield p + ".bias", (cout,), "lin_b"
 
 
-def full_net(robot, backbone="resnet50"):
-    """Ordered tensor list of RootNetwithRegInt(robot, backbone_name=backbone, rootnet_backbone_name='hrnet32')."""
+VARIANT_DEFAULTS = dict(direct_reg_rot=False, rot_iterative_matmul=False, add_fc=False, depth_num=1)
+
+
+def full_net(robot, backbone="resnet50", variant=None):
+    """Ordered tensor list of RootNetwithRegInt(robot, backbone_name=backbone, rootnet_backbone_name='hrnet32').
+
+    variant: the constructor switches that change the tensor list (full_net.py:107-131, 149-176): direct_reg_rot (a seven-layer
+    rotation regressor instead of the refinement loop), add_fc (the DepthNet's bottleneck MLP), depth_num (multi_kp: one depth
+    output per entry of kps_need_depth). rot_iterative_matmul changes arithmetic only."""
+    v = dict(VARIANT_DEFAULTS, **(variant or {}))
     spec = consts.ROBOTS[robot]
     dof, nkpt = spec["dof"], spec["nkpt"]
     hm = nkpt * consts.DEPTH_DIM
@@ -124,11 +132,22 @@ def full_net(robot, backbone="resnet50"):
     yield from _linear("fc_pose_1", consts.FEATURE_DIM + dof, 1024)
     yield from _linear("fc_pose_2", 1024, 1024)
     yield from _linear("decpose", 1024, dof)
-    yield from _linear("fc_rot_1", consts.FEATURE_DIM + consts.ROT_DIM, 1024)
-    yield from _linear("fc_rot_2", 1024, 1024)
+    if v["direct_reg_rot"]:                                     # full_net.py:110-117
+        yield from _linear("fc_rot_1", consts.FEATURE_DIM, 1024)
+        for i in range(2, 7):
+            yield from _linear("fc_rot_%d" % i, 1024, 1024)
+    else:
+        yield from _linear("fc_rot_1", consts.FEATURE_DIM + consts.ROT_DIM, 1024)
+        yield from _linear("fc_rot_2", 1024, 1024)
     yield from _linear("decrot", 1024, consts.ROT_DIM)
     yield from hrnet_w32("rootnet_backbone.", 0)
-    yield from _conv("depth_layer", consts.FEATURE_DIM, 1, 1, bias=True)
+    if v["add_fc"]:                                             # full_net.py:156-163
+        yield from _linear("depth_fc_d1", consts.FEATURE_DIM, 1024)
+        yield from _linear("depth_fc_d2", 1024, 512)
+        yield from _bn("depth_bn", 512)
+        yield from _linear("depth_fc_u2", 512, 1024)
+        yield from _linear("depth_fc_u1", 1024, consts.FEATURE_DIM)
+    yield from _conv("depth_layer", consts.FEATURE_DIM, int(v["depth_num"]), 1, bias=True)
     yield "init_pose", (1, dof), "buf"
     yield "init_rot", (1, consts.ROT_DIM), "buf"
 

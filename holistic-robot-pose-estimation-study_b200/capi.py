@@ -6,7 +6,7 @@ import numpy as np
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhrp_b200.so")
 
-NUM_FIELDS = 10
+NUM_FIELDS = 11          # the ten named fields + HRP_F_DEPTHS (multi_kp: every regressed depth; width 0 otherwise)
 NUM_CLASSES = 7
 FIELD_NAMES = ("joint_angles", "rot6d", "trans", "root_uv", "root_depth", "uvd", "kp3d_int", "kp3d_fk", "kp2d_int",
                "kp2d_fk")
@@ -38,7 +38,9 @@ class FkProgram(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("backbone", C.c_int32), ("precision", C.c_int32), ("n_iter", C.c_int32), ("fix_root", C.c_int32),
-                ("image_size", C.c_float), ("depth_factor", C.c_float)]
+                ("image_size", C.c_float), ("depth_factor", C.c_float),
+                ("direct_reg_rot", C.c_int32), ("rot_iterative_matmul", C.c_int32), ("add_fc", C.c_int32),
+                ("depth_num", C.c_int32), ("depth_root", C.c_int32)]
 
 
 _lib = None

@@ -606,6 +606,62 @@ int depth_head_launch(const float* feat, const float* w, const float* bias, cons
   return HRP_OK;
 }
 
+// DepthNet head of the constructor variants (full_net.py:293-330): add_fc -- the bottleneck MLP 2048 -> 1024 -> 512 ->
+// BatchNorm1d -> LeakyReLU -> 1024 -> 2048 with two averaged skips -- and multi_kp -- `dn` depth outputs per frame. Everything
+// around the LeakyReLU is linear, so (composed in fp64 at hrp_finalize_weights, network.cu)
+//   z = lrelu(Wz f + bz)  [Z = 512],   gamma_d = Af_d . f + Bz_d . z + c_d,   depth_d = gamma_d * k / 1000.
+// Z == 0: no MLP (multi_kp alone), gamma_d = Af_d . f + c_d. One CTA per frame.
+__global__ void __launch_bounds__(256)
+depth_head_ex_kernel(const float* __restrict__ feat, const float* __restrict__ Af, const float* __restrict__ Bz,
+                     const float* __restrict__ Wz, const float* __restrict__ bz, const float* __restrict__ c,
+                     const float* __restrict__ k_value, float* __restrict__ depth, float* __restrict__ depths, int C, int Z, int dn,
+                     int root_index) {
+  extern __shared__ float dsm[];                      // f [C], z [Z]
+  float* f = dsm;
+  float* z = dsm + C;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x * 4; i < C; i += 256 * 4)
+    *reinterpret_cast<float4*>(f + i) = __ldg(reinterpret_cast<const float4*>(feat + (size_t)b * C + i));
+  __syncthreads();
+  for (int r = warp; r < Z; r += 8) {
+    const float4* wr = reinterpret_cast<const float4*>(Wz + (size_t)r * C);
+    float acc = 0.f;
+    for (int i = lane; i < C / 4; i += 32) {
+      const float4 w = __ldg(wr + i);
+      const float4 x = *reinterpret_cast<const float4*>(f + 4 * i);
+      acc = fmaf(w.x, x.x, acc); acc = fmaf(w.y, x.y, acc); acc = fmaf(w.z, x.z, acc); acc = fmaf(w.w, x.w, acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      const float v = acc + bz[r];
+      z[r] = v > 0.f ? v : 0.01f * v;                 // nn.LeakyReLU() default slope
+    }
+  }
+  __syncthreads();
+  for (int d = warp; d < dn; d += 8) {
+    float acc = 0.f;
+    for (int i = lane; i < C; i += 32) acc = fmaf(__ldg(Af + (size_t)d * C + i), f[i], acc);
+    for (int i = lane; i < Z; i += 32) acc = fmaf(__ldg(Bz + (size_t)d * Z + i), z[i], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      const float v = (acc + c[d]) * k_value[b] / 1000.0f;       // full_net.py:326-327 / 334-336
+      if (depths != nullptr) depths[(size_t)b * dn + d] = v;
+      if (d == root_index) depth[b] = v;
+    }
+  }
+}
+
+int depth_head_ex_launch(const float* feat, const float* Af, const float* Bz, const float* Wz, const float* bz, const float* c,
+                         const float* k_value, float* depth, float* depths, int B, int C, int Z, int dn, int root_index, cudaStream_t s) {
+  if (B <= 0) return HRP_OK;
+  if (C % 4 || dn < 1 || root_index < 0 || root_index >= dn) return fail(HRP_ERR_INVALID, "depth_head_ex: bad sizes (C=%d dn=%d root=%d)", C, dn, root_index);
+  depth_head_ex_kernel<<<B, 256, (size_t)(C + Z) * sizeof(float), s>>>(feat, Af, Bz, Wz, bz, c, k_value, depth, depths, C, Z, dn, root_index);
+  HRP_CHECK_LAUNCH("depth_head_ex_kernel");
+  return HRP_OK;
+}
+
 // The pose / rotation refinement loops (full_net.py:376-394, 430-444) have no nonlinearity (dropout is the identity in eval
 // mode), so n iterations of  s <- s + dec(fc2(fc1([xf, s])))  are the affine map  s_n = G_n xf + P_n s_0 + g_n  with
 // G_n, P_n, g_n composed once in fp64 at hrp_finalize_weights (network.cu, compose_heads). One launch evaluates every
@@ -616,8 +672,8 @@ __global__ void __launch_bounds__(256)
 heads_affine_kernel(const float* __restrict__ xf, const float* __restrict__ G, const float* __restrict__ P,
                     const float* __restrict__ g, const float* __restrict__ s0_default, const float* ovr_pose,
                     const float* ovr_rot, const int* flags, float* __restrict__ iters, float* __restrict__ pose,
-                    float* __restrict__ rot, int F, int dof, int n_iter) {
-  extern __shared__ float hx[];                       // xf row, then the two initial states
+                    float* __restrict__ rot, int F, int dof, int n_iter, int rot_matmul) {
+  extern __shared__ float hx[];                       // xf row, then the two initial states, then u (rot_matmul)
   const int b = blockIdx.x, R1 = dof + 6, R = n_iter * R1;
   for (int c = threadIdx.x * 4; c < F; c += 256 * 4)
     *reinterpret_cast<float4*>(hx + c) = __ldg(reinterpret_cast<const float4*>(xf + (size_t)b * F + c));
@@ -632,7 +688,9 @@ heads_affine_kernel(const float* __restrict__ xf, const float* __restrict__ G, c
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pblk = dof * dof + 36;
+  float* u = s0 + R1;                                 // rot_matmul: A xf + c, the state-independent part of decrot's output
   for (int r = warp; r < R; r += 8) {
+    if (rot_matmul && r >= R1 && (r % R1) >= dof) continue;      // composed rows of later rotation iterates do not exist
     const float4* gr = reinterpret_cast<const float4*>(G + (size_t)r * F);
     float acc = 0.f;
     for (int c = lane; c < F / 4; c += 32) {
@@ -649,6 +707,7 @@ heads_affine_kernel(const float* __restrict__ xf, const float* __restrict__ G, c
       const float* pr = P + (size_t)n * pblk + (is_rot ? dof * dof : 0) + jj * w;
       const float* st = s0 + (is_rot ? dof : 0);
       float v = acc + g[r];
+      if (rot_matmul && is_rot) { u[jj] = v; continue; }
       for (int q = 0; q < w; ++q) v = fmaf(pr[q], st[q], v);
       iters[(size_t)b * R + r] = v;
       if (n == n_iter - 1) {
@@ -656,15 +715,48 @@ heads_affine_kernel(const float* __restrict__ xf, const float* __restrict__ G, c
       }
     }
   }
+  if (rot_matmul) {
+    // rot_iterative_matmul (full_net.py:413-429): d = decrot(...) = u + M s is itself a 6-D rotation, COMPOSED with the
+    // current one: s <- first two rows of R(d) R(s) (geometries.py:100-132). M = rotation block of P's first iterate.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float* M = P + dof * dof;
+      float s[6];
+      for (int q = 0; q < 6; ++q) s[q] = s0[dof + q];
+      auto rotmat = [](const float* v, float* Rm) {       // rows x, y, z: x = a1/|a1|, z = (x X a2)/|.|, y = z X x
+        const float nx = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        const float x0 = v[0] / nx, x1 = v[1] / nx, x2 = v[2] / nx;
+        float z0 = x1 * v[5] - x2 * v[4], z1 = x2 * v[3] - x0 * v[5], z2 = x0 * v[4] - x1 * v[3];
+        const float nz = sqrtf(z0 * z0 + z1 * z1 + z2 * z2);
+        z0 /= nz; z1 /= nz; z2 /= nz;
+        Rm[0] = x0; Rm[1] = x1; Rm[2] = x2;
+        Rm[3] = z1 * x2 - z2 * x1; Rm[4] = z2 * x0 - z0 * x2; Rm[5] = z0 * x1 - z1 * x0;
+        Rm[6] = z0; Rm[7] = z1; Rm[8] = z2;
+      };
+      for (int n = 0; n < n_iter; ++n) {
+        float d[6], Rd[9], Rs[9];
+        for (int j = 0; j < 6; ++j) {
+          float v = u[j];
+          for (int q = 0; q < 6; ++q) v = fmaf(M[j * 6 + q], s[q], v);
+          d[j] = v;
+        }
+        rotmat(d, Rd); rotmat(s, Rs);
+        for (int i = 0; i < 2; ++i)
+          for (int j = 0; j < 3; ++j) s[i * 3 + j] = Rd[i * 3] * Rs[j] + Rd[i * 3 + 1] * Rs[3 + j] + Rd[i * 3 + 2] * Rs[6 + j];
+        for (int j = 0; j < 6; ++j) iters[(size_t)b * R + (size_t)n * R1 + dof + j] = s[j];
+      }
+      for (int j = 0; j < 6; ++j) rot[(size_t)b * 6 + j] = s[j];
+    }
+  }
 }
 
 int heads_affine_launch(const float* xf, const float* G, const float* P, const float* g, const float* s0_default,
                         const float* ovr_pose, const float* ovr_rot, const int* flags, float* iters, float* pose, float* rot,
-                        int B, int F, int dof, int n_iter, cudaStream_t s) {
+                        int B, int F, int dof, int n_iter, int rot_matmul, cudaStream_t s) {
   if (B <= 0) return HRP_OK;
   if (F % 4) return fail(HRP_ERR_INVALID, "heads_affine: feature width %d is not a multiple of 4", F);
-  heads_affine_kernel<<<B, 256, (size_t)(F + dof + 6) * sizeof(float), s>>>(xf, G, P, g, s0_default, ovr_pose, ovr_rot, flags, iters, pose,
-                                                                            rot, F, dof, n_iter);
+  heads_affine_kernel<<<B, 256, (size_t)(F + dof + 6 + 6) * sizeof(float), s>>>(xf, G, P, g, s0_default, ovr_pose, ovr_rot, flags, iters, pose,
+                                                                                rot, F, dof, n_iter, rot_matmul);
   HRP_CHECK_LAUNCH("heads_affine_kernel");
   return HRP_OK;
 }

@@ -137,9 +137,11 @@ int depth_head_launch(const float* feat, const float* w, const float* bias, cons
 // Every iterate of both refinement heads as one affine map per iterate (conv_f32.cu, heads_affine_kernel):
 // iters [B, n_iter, dof+6]; pose [B,dof] / rot [B,6] receive the last iterate. G [n_iter*(dof+6), F], P per iterate
 // {dof x dof, 6 x 6}, g [n_iter*(dof+6)], s0_default [dof+6]; ovr_* optional per-frame initial states.
+int depth_head_ex_launch(const float* feat, const float* Af, const float* Bz, const float* Wz, const float* bz, const float* c,
+                         const float* k_value, float* depth, float* depths, int B, int C, int Z, int dn, int root_index, cudaStream_t s);
 int heads_affine_launch(const float* xf, const float* G, const float* P, const float* g, const float* s0_default,
                         const float* ovr_pose, const float* ovr_rot, const int* flags, float* iters, float* pose, float* rot,
-                        int B, int F, int dof, int n_iter, cudaStream_t s);
+                        int B, int F, int dof, int n_iter, int rot_matmul, cudaStream_t s);
 
 // ---- integral layer / kinematics (softargmax.cu, fk_project.cu) ----------------------------------------------------------
 size_t softargmax_workspace(int B, int K, int D, int H, int W);

@@ -267,11 +267,23 @@ void build_specs(hrp_handle* h) {
   sb.linear("fc_pose_1", 2048 + h->dof, 1024);
   sb.linear("fc_pose_2", 1024, 1024);
   sb.linear("decpose", 1024, h->dof);
-  sb.linear("fc_rot_1", 2048 + 6, 1024);
-  sb.linear("fc_rot_2", 1024, 1024);
+  if (h->cfg.direct_reg_rot) {                       // full_net.py:110-117
+    sb.linear("fc_rot_1", 2048, 1024);
+    for (int i = 2; i <= 6; ++i) sb.linear(S("fc_rot_%d", i), 1024, 1024);
+  } else {
+    sb.linear("fc_rot_1", 2048 + 6, 1024);
+    sb.linear("fc_rot_2", 1024, 1024);
+  }
   sb.linear("decrot", 1024, 6);
   spec_hrnet(sb, "rootnet_backbone.", 0);
-  sb.conv("depth_layer", 2048, 1, 1, true);
+  if (h->cfg.add_fc) {                               // full_net.py:156-163
+    sb.linear("depth_fc_d1", 2048, 1024);
+    sb.linear("depth_fc_d2", 1024, 512);
+    sb.bn("depth_bn", 512);
+    sb.linear("depth_fc_u2", 512, 1024);
+    sb.linear("depth_fc_u1", 1024, 2048);
+  }
+  sb.conv("depth_layer", 2048, std::max(1, h->cfg.depth_num), 1, true);
   sb.add("init_pose", {1, h->dof});
   sb.add("init_rot", {1, 6});
   for (size_t i = 0; i < h->specs.size(); ++i) h->spec_index[h->specs[i].name] = (int)i;
@@ -664,7 +676,9 @@ struct GraphBuilder {
     const char* init[2] = {"init_pose", "init_rot"};
     const int sd[2] = {dof, 6}, row0[2] = {0, dof};
     std::vector<float> G((size_t)nit * R1 * F), P((size_t)nit * (dof * dof + 36)), gv((size_t)nit * R1), s0(R1);
+    const bool direct = h->cfg.direct_reg_rot != 0, matmul = !direct && h->cfg.rot_iterative_matmul != 0;
     for (int k = 0; k < 2; ++k) {
+      if (k == 1 && direct) { direct_rot(G, P, gv, s0); continue; }
       const int n = sd[k], in1 = F + n;
       const float* w1 = W(std::string(fc1[k]) + ".weight"); const float* b1 = W(std::string(fc1[k]) + ".bias");
       const float* w2 = W(std::string(fc2[k]) + ".weight"); const float* b2 = W(std::string(fc2[k]) + ".bias");
@@ -695,6 +709,17 @@ struct GraphBuilder {
       }
       std::vector<double> E(M), Pn((size_t)n * n, 0.0), Sn((size_t)n * n, 0.0), tmp((size_t)n * n);
       for (int j = 0; j < n; ++j) { E[(size_t)j * n + j] += 1.0; Pn[(size_t)j * n + j] = 1.0; }
+      if (k == 1 && matmul) {
+        // rot_iterative_matmul: the update is not additive, so nothing composes across iterations. Iterate 0 carries
+        // A, c and M (rows of later iterates stay zero); heads_affine_kernel runs the loop itself (rot_matmul mode)
+        for (int j = 0; j < n; ++j) {
+          const size_t r = (size_t)row0[k] + j;
+          for (int q = 0; q < F; ++q) G[r * F + q] = (float)A[(size_t)j * F + q];
+          gv[r] = (float)c[j];
+          for (int q = 0; q < n; ++q) P[(size_t)dof * dof + (size_t)j * n + q] = (float)M[(size_t)j * n + q];
+        }
+        continue;
+      }
       for (int it = 0; it < nit; ++it) {
         for (size_t q = 0; q < Sn.size(); ++q) Sn[q] += Pn[q];          // S_{it+1} = S_it + P_it
         for (int j = 0; j < n; ++j)                                     // P_{it+1} = E P_it
@@ -727,9 +752,122 @@ struct GraphBuilder {
     op.kind = OP_HEADS; op.cls = CLS_HEADS; op.in = xf.id; op.in2 = h->t_initp; op.in3 = h->t_initr; op.in4 = h->t_flags;
     op.out = h->t_field[HRP_F_POSE]; op.out2 = h->t_field[HRP_F_ROT]; op.out3 = iters.id;
     op.same[0] = constant(upload(G)); op.same[1] = constant(upload(P)); op.same[2] = constant(upload(gv)); op.same[3] = constant(upload(s0));
-    op.n_same = 4; op.Cin = F; op.dof = dof; op.N = nit;
+    op.n_same = 4; op.Cin = F; op.dof = dof; op.N = nit; op.relu = matmul ? 1 : 0;     // relu: the kernel's rot_matmul mode
     op.flops = 2.0 * nit * R1 * F;
     push(op);
+  }
+
+  // direct_reg_rot (full_net.py:395-409): rot = decrot(fc6(fc5(fc4(fc3(fc2(x1))))) + x1), x1 = fc1(xf): seven linear layers and a
+  // skip, no activation -> one affine map of xf, the same for every "iterate" and independent of init_rot. Row vectors of
+  // decrot are pulled back through the layers in fp64.
+  void direct_rot(std::vector<float>& G, std::vector<float>& P, std::vector<float>& gv, std::vector<float>& s0) {
+    const int dof = h->dof, F = 2048, Hd = 1024, nit = h->cfg.n_iter, R1 = dof + 6;
+    const float* wd = W("decrot.weight"); const float* bd = W("decrot.bias");
+    const float* w1 = W("fc_rot_1.weight"); const float* b1 = W("fc_rot_1.bias");
+    const float* i0 = W("init_rot");
+    if (status != HRP_OK) return;
+    for (int j = 0; j < 6; ++j) s0[dof + j] = i0[j];
+    std::vector<double> T((size_t)6 * Hd), acc((size_t)6 * Hd), cst(6);
+    for (int j = 0; j < 6; ++j) { cst[j] = bd[j]; for (int m = 0; m < Hd; ++m) T[(size_t)j * Hd + m] = wd[(size_t)j * Hd + m]; }
+    for (int l = 6; l >= 2; --l) {                                 // T <- T W_l, constants pick up T b_l on the way
+      const float* wl = W(S("fc_rot_%d.weight", l)); const float* bl = W(S("fc_rot_%d.bias", l));
+      if (status != HRP_OK) return;
+      std::fill(acc.begin(), acc.end(), 0.0);
+      for (int j = 0; j < 6; ++j)
+        for (int m = 0; m < Hd; ++m) {
+          const double t = T[(size_t)j * Hd + m];
+          cst[j] += t * (double)bl[m];
+          const float* row = wl + (size_t)m * Hd;
+          double* a = &acc[(size_t)j * Hd];
+          for (int q = 0; q < Hd; ++q) a[q] += t * (double)row[q];
+        }
+      T = acc;
+    }
+    for (int j = 0; j < 6; ++j)
+      for (int m = 0; m < Hd; ++m) T[(size_t)j * Hd + m] += (double)wd[(size_t)j * Hd + m];      // the skip: x6 + x1
+    for (int j = 0; j < 6; ++j) {
+      std::vector<double> row(F, 0.0);
+      double cj = cst[j];
+      for (int m = 0; m < Hd; ++m) {
+        const double t = T[(size_t)j * Hd + m];
+        cj += t * (double)b1[m];
+        const float* r1 = w1 + (size_t)m * F;
+        for (int q = 0; q < F; ++q) row[q] += t * (double)r1[q];
+      }
+      for (int it = 0; it < nit; ++it) {
+        const size_t r = (size_t)it * R1 + dof + j;
+        for (int q = 0; q < F; ++q) G[r * F + q] = (float)row[q];
+        gv[r] = (float)cj;
+        for (int q = 0; q < 6; ++q) P[(size_t)it * (dof * dof + 36) + (size_t)dof * dof + (size_t)j * 6 + q] = 0.f;
+      }
+    }
+  }
+
+  // DepthNet head of the add_fc / multi_kp variants (full_net.py:293-330), composed in fp64 around the one nonlinearity:
+  //   d1 = W1 f + b1;  z = lrelu(s (W2 d1 + b2 - mu) + beta), s = gamma / sqrt(var + eps);
+  //   f3 = (Wu2 z + bu2 + d1) / 2;  f4 = (Wu1 f3 + bu1 + f) / 2;  gamma_d = wd_d . f4 + bd_d
+  //   => z = lrelu(Wz f + bz),  gamma_d = Af_d . f + Bz_d . z + c_d   (conv_f32.cu: depth_head_ex_kernel)
+  int depth_head_variant(const Tn& img_feat) {
+    const int F = 2048, H1 = 1024, Z = h->cfg.add_fc ? 512 : 0, dn = std::max(1, h->cfg.depth_num);
+    const float* wd = W("depth_layer.weight"); const float* bd = W("depth_layer.bias");
+    if (status != HRP_OK) return status;
+    std::vector<float> Af((size_t)dn * F), Bz((size_t)dn * std::max(Z, 1), 0.f), Wz((size_t)std::max(Z, 1) * F, 0.f), bz(std::max(Z, 1), 0.f), cc(dn);
+    if (!Z) {
+      for (int d = 0; d < dn; ++d) { for (int q = 0; q < F; ++q) Af[(size_t)d * F + q] = wd[(size_t)d * F + q]; cc[d] = bd[d]; }
+    } else {
+      const float* w1 = W("depth_fc_d1.weight"); const float* b1 = W("depth_fc_d1.bias");
+      const float* w2 = W("depth_fc_d2.weight"); const float* b2 = W("depth_fc_d2.bias");
+      const float* u2 = W("depth_fc_u2.weight"); const float* c2 = W("depth_fc_u2.bias");
+      const float* u1 = W("depth_fc_u1.weight"); const float* c1 = W("depth_fc_u1.bias");
+      const float* bw = W("depth_bn.weight"); const float* bb = W("depth_bn.bias");
+      const float* bm = W("depth_bn.running_mean"); const float* bv = W("depth_bn.running_var");
+      if (status != HRP_OK) return status;
+      // Wz = diag(s) W2 W1, bz = s (W2 b1 + b2 - mu) + beta
+      for (int r = 0; r < Z; ++r) {
+        const double sc = (double)bw[r] / std::sqrt((double)bv[r] + 1e-5);        // nn.BatchNorm1d default eps
+        std::vector<double> row(F, 0.0);
+        double cst = b2[r];
+        for (int m = 0; m < H1; ++m) {
+          const double t = w2[(size_t)r * H1 + m];
+          cst += t * (double)b1[m];
+          const float* r1 = w1 + (size_t)m * F;
+          for (int q = 0; q < F; ++q) row[q] += t * (double)r1[q];
+        }
+        for (int q = 0; q < F; ++q) Wz[(size_t)r * F + q] = (float)(sc * row[q]);
+        bz[r] = (float)(sc * (cst - (double)bm[r]) + (double)bb[r]);
+      }
+      for (int d = 0; d < dn; ++d) {
+        const float* wdr = wd + (size_t)d * F;
+        std::vector<double> t1(H1, 0.0);                                           // wd_d Wu1  [1024]
+        double cst = bd[d];
+        for (int q = 0; q < F; ++q) {
+          const double t = wdr[q];
+          cst += 0.5 * t * (double)c1[q];
+          const float* r = u1 + (size_t)q * H1;
+          for (int m = 0; m < H1; ++m) t1[m] += t * (double)r[m];
+        }
+        std::vector<double> af(F, 0.0), bzr(Z, 0.0);
+        for (int m = 0; m < H1; ++m) {
+          const double t = 0.25 * t1[m];
+          cst += t * ((double)c2[m] + (double)b1[m]);
+          const float* r2 = u2 + (size_t)m * Z;
+          for (int q = 0; q < Z; ++q) bzr[q] += t * (double)r2[q];
+          const float* r1 = w1 + (size_t)m * F;
+          for (int q = 0; q < F; ++q) af[q] += t * (double)r1[q];
+        }
+        for (int q = 0; q < F; ++q) Af[(size_t)d * F + q] = (float)(af[q] + 0.5 * (double)wdr[q]);
+        for (int q = 0; q < Z; ++q) Bz[(size_t)d * Z + q] = (float)bzr[q];
+        cc[d] = (float)cst;
+      }
+    }
+    OpDesc op{};
+    op.kind = OP_DEPTH; op.cls = CLS_HEADS; op.in = img_feat.id; op.in2 = h->t_kval; op.out = h->t_field[HRP_F_DEPTH];
+    op.out2 = h->cfg.depth_num > 0 ? h->t_field[HRP_F_DEPTHS] : -1;
+    op.same[0] = constant(upload(Af)); op.same[1] = constant(upload(Bz)); op.same[2] = constant(upload(Wz)); op.same[3] = constant(upload(bz));
+    op.n_same = 4; op.bptr = upload(cc); op.Cin = F; op.Cout = Z; op.N = dn; op.dof = h->cfg.depth_root; op.relu = 1;   // relu: variant kernel
+    op.flops = 2.0 * ((double)Z * F + (double)dn * (F + Z));
+    push(op);
+    return status;
   }
 
   int build() {
@@ -741,7 +879,7 @@ struct GraphBuilder {
       h->sa_fused = prec != HRP_PREC_FP32 && !(e && atoi(e) != 0);
     }
     const int nk = h->nkpt, dof = h->dof;
-    const int fw[HRP_NUM_FIELDS] = {dof, 6, 3, 2, 1, nk * 3, nk * 3, nk * 3, nk * 2, nk * 2};
+    const int fw[HRP_NUM_FIELDS] = {dof, 6, 3, 2, 1, nk * 3, nk * 3, nk * 3, nk * 2, nk * 2, h->cfg.depth_num};
     h->t_xreg = special(T_XREG, 3LL * 256 * 256);
     h->t_xroot = special(T_XROOT, 3LL * 256 * 256);
     h->t_kval = special(T_KVAL, 1);
@@ -761,7 +899,7 @@ struct GraphBuilder {
     // DepthNet: lanes 0-3 (one per HRNet branch); its head ends on lane 3
     Tn img_feat = hrnet(h->t_xroot, "rootnet_backbone.", 0, nullptr, 0);
     h->tensors[img_feat.id].keep = true; h->debug["img_feat"] = img_feat.id;
-    {
+    if (!h->cfg.add_fc && h->cfg.depth_num == 0) {
       const float* w = W("depth_layer.weight"); const float* b = W("depth_layer.bias");
       if (status != HRP_OK) return status;
       OpDesc op{};
@@ -769,6 +907,8 @@ struct GraphBuilder {
       op.wptr = upload(std::vector<float>(w, w + 2048)); op.bptr = upload(std::vector<float>(b, b + 1)); op.Cin = 2048;
       op.flops = 2.0 * 2048;
       push(op);
+    } else {
+      if (depth_head_variant(img_feat) != HRP_OK) return status;
     }
     // keypoint branch: lane 4 (ResNet-50 trunk, deconv head, logits, soft-argmax) or lanes 4-7 (HRNet-W32); the
     // regression heads and FK run on their own lane beside the deconv head
@@ -1151,13 +1291,19 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
         HRP_TRY(avgpool_launch(ptr(o.in), static_cast<float*>(ptr(o.out)), B, o.Hi * o.Wi, o.Cin, bf16, st_op));
         break;
       case OP_DEPTH:
-        HRP_TRY(depth_head_launch(static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, static_cast<const float*>(ptr(o.in2)), static_cast<float*>(ptr(o.out)), B, o.Cin, st_op));
+        if (o.relu)          // add_fc / multi_kp variants
+          HRP_TRY(depth_head_ex_launch(static_cast<const float*>(ptr(o.in)), static_cast<const float*>(ptr(o.same[0])), static_cast<const float*>(ptr(o.same[1])),
+                                       static_cast<const float*>(ptr(o.same[2])), static_cast<const float*>(ptr(o.same[3])), o.bptr,
+                                       static_cast<const float*>(ptr(o.in2)), static_cast<float*>(ptr(o.out)), o.out2 >= 0 ? static_cast<float*>(ptr(o.out2)) : nullptr,
+                                       B, o.Cin, o.Cout, o.N, o.dof, st_op));
+        else
+          HRP_TRY(depth_head_launch(static_cast<const float*>(ptr(o.in)), o.wptr, o.bptr, static_cast<const float*>(ptr(o.in2)), static_cast<float*>(ptr(o.out)), B, o.Cin, st_op));
         break;
       case OP_HEADS:
         HRP_TRY(heads_affine_launch(static_cast<const float*>(ptr(o.in)), static_cast<const float*>(ptr(o.same[0])), static_cast<const float*>(ptr(o.same[1])),
                                     static_cast<const float*>(ptr(o.same[2])), static_cast<const float*>(ptr(o.same[3])), static_cast<const float*>(ptr(o.in2)),
                                     static_cast<const float*>(ptr(o.in3)), static_cast<const int*>(ptr(o.in4)), static_cast<float*>(ptr(o.out3)),
-                                    static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)), B, o.Cin, o.dof, o.N, st_op));
+                                    static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)), B, o.Cin, o.dof, o.N, o.relu, st_op));
         break;
       case OP_RESERVED:
         break;
@@ -1232,12 +1378,14 @@ extern "C" int hrp_create(const hrp_config* cfg, const hrp_fk_program* robot, in
     return fail(HRP_ERR_INVALID, "hrp_create: unknown precision %d (0 fp32, 1 tf32, 2 bf16, 3 tf32x3, 4 f16)", cfg->precision);
   if (cfg->n_iter < 1 || cfg->n_iter > 16) return fail(HRP_ERR_INVALID, "hrp_create: n_iter %d out of range", cfg->n_iter);
   if (cfg->image_size != 256.0f) return fail(HRP_ERR_INVALID, "hrp_create: only 256x256 inputs are supported (got %g)", cfg->image_size);
+  if (cfg->depth_num < 0 || cfg->depth_num > HRP_FK_MAX_KP || cfg->depth_root < 0 || cfg->depth_root >= std::max(1, cfg->depth_num))
+    return fail(HRP_ERR_INVALID, "hrp_create: depth_num %d / depth_root %d out of range", cfg->depth_num, cfg->depth_root);
   std::unique_ptr<hrp_handle> h(new hrp_handle());
   h->cfg = *cfg;
   h->device = device;
   HRP_TRY(hrp_fk_create(robot, &h->fk));
   h->dof = robot->dof; h->nkpt = robot->nkpt; h->ref_kp = robot->root_kp;
-  const int fw[HRP_NUM_FIELDS] = {h->dof, 6, 3, 2, 1, h->nkpt * 3, h->nkpt * 3, h->nkpt * 3, h->nkpt * 2, h->nkpt * 2};
+  const int fw[HRP_NUM_FIELDS] = {h->dof, 6, 3, 2, 1, h->nkpt * 3, h->nkpt * 3, h->nkpt * 3, h->nkpt * 2, h->nkpt * 2, cfg->depth_num};
   for (int f = 0; f < HRP_NUM_FIELDS; ++f) h->field_width[f] = fw[f];
   build_specs(h.get());
   *out = h.release();

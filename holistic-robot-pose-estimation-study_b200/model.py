@@ -14,9 +14,8 @@ import torch
 
 from . import arch, capi, consts, urdf
 
-UNSUPPORTED = {  # ctor variants of the reference that no shipped config enables -> explicit error
-    "reg_joint_map": False, "direct_reg_rot": False, "rot_iterative_matmul": False, "add_fc": False,
-    "multi_kp": False, "use_rpmg": False,
+UNSUPPORTED = {  # ctor variants of the reference that no shipped config enables and this path does not build -> explicit error
+    "reg_joint_map": False, "use_rpmg": False,
 }
 
 
@@ -189,6 +188,15 @@ class HoliRobPoseB200(torch.nn.Module):
         self.bbox_3d_shape = tuple(cfg.get("bbox_3d_shape", spec["bbox_3d"]))
         self.reference_keypoint_id = int(cfg.get("reference_keypoint_id", spec["ref_kp"]))
         self.fix_root = bool(cfg.get("fix_root", True))
+        # constructor variants outside the shipped configuration (full_net.py:107-131, 149-164)
+        self.direct_reg_rot = bool(cfg.get("direct_reg_rot", False))
+        self.rot_iterative_matmul = bool(cfg.get("rot_iterative_matmul", False))
+        self.add_fc = bool(cfg.get("add_fc", False))
+        self.multi_kp = bool(cfg.get("multi_kp", False))
+        self.kps_need_depth = list(cfg.get("kps_need_depth") or []) if self.multi_kp else [self.reference_keypoint_id]   # full_net.py:150-151
+        if self.multi_kp and self.reference_keypoint_id not in self.kps_need_depth:
+            raise ValueError("%d is not in list" % self.reference_keypoint_id)      # what kps_need_depth.index raises, full_net.py:328
+        self.depth_num = len(self.kps_need_depth)
         self.dof, self.nkpt = spec["dof"], spec["nkpt"]
         self.num_joints = self.nkpt
         if device is None:
@@ -204,7 +212,9 @@ class HoliRobPoseB200(torch.nn.Module):
         self._prog_struct, self._prog_keep = capi.fk_program_struct(self.program)
         depth_factor = float(np.float32(self.bbox_3d_shape[2]) * np.float32(1e-3))       # integral.py:96-97
         self._cfg = capi.Config(capi.BACKBONE[self.backbone_name], capi.PREC[precision], self.n_iter, int(self.fix_root),
-                                self.image_size, depth_factor)
+                                self.image_size, depth_factor, int(self.direct_reg_rot), int(self.rot_iterative_matmul),
+                                int(self.add_fc), self.depth_num if self.multi_kp else 0,
+                                self.kps_need_depth.index(self.reference_keypoint_id) if self.multi_kp else 0)
         h = C.c_void_p()
         capi.check(capi.lib().hrp_create(C.byref(self._cfg), C.byref(self._prog_struct), self.device.index, C.byref(h)))
         self._h = h
@@ -360,7 +370,8 @@ class HoliRobPoseB200(torch.nn.Module):
         return rec, offs
 
     def _fields(self, rec, offs, B):
-        w = (self.dof, 6, 3, 2, 1, self.nkpt * 3, self.nkpt * 3, self.nkpt * 3, self.nkpt * 2, self.nkpt * 2)
+        w = (self.dof, 6, 3, 2, 1, self.nkpt * 3, self.nkpt * 3, self.nkpt * 3, self.nkpt * 2, self.nkpt * 2,
+             self.depth_num if self.multi_kp else 0)
         out = []
         for f in range(capi.NUM_FIELDS):
             t = rec[offs[f]:offs[f] + B * w[f]].view(B, w[f])
@@ -384,6 +395,8 @@ class HoliRobPoseB200(torch.nn.Module):
         times = [] if test_fps else None
         rec, offs = self.forward_record(x_reg_input, x_root_input, k_value, K, init_pose, init_rot, times)
         f = self._fields(rec, offs, B)
+        if self.multi_kp and not test_fps:                                   # full_net.py:462-464: pred_depths rides along
+            return tuple(f[:5]) + (f[10],) + tuple(f[5:8])
         return tuple(f[:8]) + ((times[0],) if test_fps else ())
 
     def forward_dict(self, images, K, k_value=None):
@@ -393,7 +406,11 @@ class HoliRobPoseB200(torch.nn.Module):
         if k_value is None:                                                  # scripts/real_test.py:285-289, full-frame bbox
             k_value = torch.sqrt(K[:, 0, 0] * K[:, 1, 1] * 1000.0 * 1000.0 / (self.image_size * self.image_size))
         rec, offs = self.forward_record(images, images, k_value, K)
-        return dict(zip(capi.FIELD_NAMES, self._fields(rec, offs, B)))
+        f = self._fields(rec, offs, B)
+        out = dict(zip(capi.FIELD_NAMES, f))
+        if self.multi_kp:
+            out["depths"] = f[10]
+        return out
 
     def launch_count(self):
         return int(capi.lib().hrp_launch_count(self._h))
@@ -501,6 +518,6 @@ def get_rootNetwithRegInt_model(init_param_dict, args, device=None, precision="f
     """Factory with the reference's name and arguments (full_net.py:470-505); weights are loaded by the caller."""
     cfg = dict(args) if isinstance(args, dict) else {k: getattr(args, k) for k in dir(args) if not k.startswith("_")}
     keys = ("backbone_name", "rootnet_backbone_name", "n_iter", "rotation_dim", "reg_joint_map", "direct_reg_rot",
-            "rot_iterative_matmul", "add_fc", "multi_kp", "use_rpmg", "fix_root", "bbox_3d_shape",
+            "rot_iterative_matmul", "add_fc", "multi_kp", "kps_need_depth", "use_rpmg", "fix_root", "bbox_3d_shape",
             "reference_keypoint_id", "other_image_size")
     return HoliRobPoseB200(init_param_dict["robot_type"], {k: cfg[k] for k in keys if k in cfg}, device, precision)

@@ -89,7 +89,7 @@ def _calib(recipe):
     return _calib_cache[recipe]
 
 
-def make_state_dict(robot, backbone="resnet50", seed=1234, calibrated=True, recipe="damped"):
+def make_state_dict(robot, backbone="resnet50", seed=1234, calibrated=True, recipe="damped", ctor=None):
     """Ordered dict name -> numpy array in the reference's state-dict format.
 
     recipe "damped" (default, module docstring) or "undamped": every BatchNorm gain U(0.6, 1.4), i.e. SURVEY.md 8d's
@@ -102,9 +102,12 @@ def make_state_dict(robot, backbone="resnet50", seed=1234, calibrated=True, reci
     if calibrated and z is None:
         raise FileNotFoundError("BN calibration file for recipe %r missing: run scripts/make_bn_calib.py" % recipe)
     sd = {}
-    for name, shape, kind in arch.full_net(robot, backbone):
+    for name, shape, kind in arch.full_net(robot, backbone, ctor):
         t = _draw(name, shape, kind, seed, robot, damped=recipe == "damped")
-        if z is not None and kind in ("bn_mean", "bn_var"):
+        if name.startswith("depth_bn.") and kind in ("bn_mean", "bn_var"):   # BatchNorm1d of the add_fc variant: drawn, not calibrated
+            g = _rng(seed, name)
+            t = (g.standard_normal(shape) * 0.1 if kind == "bn_mean" else g.uniform(0.5, 1.5, shape)).astype(np.float32)
+        elif z is not None and kind in ("bn_mean", "bn_var"):
             key = "%d/%s/%s" % (seed, variant if name.startswith(("reg_backbone", "deconv")) else "rootnet", name)
             t = z[key].astype(np.float32)
             assert t.shape == tuple(shape), (name, t.shape, shape)

@@ -133,6 +133,12 @@ typedef struct {
   int32_t fix_root;          /* zero the root keypoint's d before back-projection (shipped: 1) */
   float image_size;          /* 256 */
   float depth_factor;        /* bbox_3d_shape[2] * 1e-3 (shipped: 1.3) */
+  /* constructor variants outside the shipped configuration; all 0 = the shipped network */
+  int32_t direct_reg_rot;        /* rotation from a seven-layer regressor instead of the refinement loop (full_net.py:107-117, 395-409) */
+  int32_t rot_iterative_matmul;  /* each refinement step COMPOSES the regressed rotation with the current one (full_net.py:413-429) */
+  int32_t add_fc;                /* DepthNet bottleneck MLP in front of depth_layer (full_net.py:156-163, 296-313) */
+  int32_t depth_num;             /* multi_kp: len(kps_need_depth) depth outputs (>= 1), all returned in HRP_F_DEPTHS; 0 = single root depth */
+  int32_t depth_root;            /* multi_kp: kps_need_depth.index(reference_keypoint_id) (full_net.py:328-329) */
 } hrp_config;
 
 typedef struct hrp_handle hrp_handle;
@@ -164,7 +170,8 @@ enum {
   HRP_F_XYZ_FK = 7,    /* [B,nkpt,3] forward-kinematics keypoints      full_net.py:447-450 */
   HRP_F_KP2D_INT = 8,  /* [B,nkpt,2] projection of XYZ_INT             transforms.py:17-21 */
   HRP_F_KP2D_FK = 9,   /* [B,nkpt,2] projection of XYZ_FK */
-  HRP_NUM_FIELDS = 10
+  HRP_F_DEPTHS = 10,   /* [B,depth_num] every regressed depth (m), multi_kp only (width 0 otherwise)   full_net.py:319-327, 462-464 */
+  HRP_NUM_FIELDS = 11
 };
 int hrp_output_offsets(const hrp_handle* h, int B, int64_t* offsets /*[HRP_NUM_FIELDS+1]*/);
 

@@ -1,7 +1,7 @@
 """Oracle: the full inference forward `model(x_reg, x_root, k_value, K)` + caller-side projections.
 
-Follows lib/models/full_net.py:262-466 (shipped configuration: n_iter=4, rotation_dim=6, fix_root=True, no
-reg_joint_map / direct_reg_rot / rot_iterative_matmul / add_fc / multi_kp) and lib/core/function.py:133-141.
+Follows lib/models/full_net.py:262-466 (shipped configuration: n_iter=4, rotation_dim=6, fix_root=True; the
+constructor variants direct_reg_rot / rot_iterative_matmul / add_fc / multi_kp through `ctor`; no reg_joint_map) and lib/core/function.py:133-141.
 """
 import numpy as np
 import torch
@@ -24,7 +24,11 @@ BAXTER_KP_JOINTS = ["torso_t0", "right_s0", "left_s0", "right_s1", "left_s1", "r
 
 class OracleModel:
     def __init__(self, robot, state_dict, urdf_text, backbone="resnet50", image_size=256.0, depth_mm=1300.0,
-                 fix_root=True, n_iter=4):
+                 fix_root=True, n_iter=4, ctor=None):
+        # constructor switches outside the shipped configuration (full_net.py:107-131, 149-164, 293-330, 395-444):
+        # direct_reg_rot, rot_iterative_matmul, add_fc, depth_num (= len(kps_need_depth)) + depth_root (index of the root keypoint in it)
+        self.ctor = dict(direct_reg_rot=False, rot_iterative_matmul=False, add_fc=False, depth_num=1, depth_root=0)
+        self.ctor.update(ctor or {})
         self.robot = robot
         self.dof, self.nkpt, self.ref, _ = ROBOTS[robot]
         self.backbone = "resnet50" if backbone in ("resnet", "resnet50") else "hrnet32"
@@ -53,8 +57,15 @@ class OracleModel:
         x_reg, x_root = x_reg.float(), x_root.float()
         B = x_reg.shape[0]
         _, img_feat = network.hrnet_w32(x_root, sd, "rootnet_backbone.", False, calib)
-        gamma = torch.nn.functional.conv2d(img_feat[:, :, None, None], sd["depth_layer.weight"], sd["depth_layer.bias"])
-        depth = (gamma.view(-1, 1) * k_value.view(-1, 1)).reshape(B, 1) / 1000.0          # full_net.py:334-336
+        feat = network.depth_add_fc(img_feat, sd) if self.ctor["add_fc"] else img_feat
+        gamma = torch.nn.functional.conv2d(feat[:, :, None, None], sd["depth_layer.weight"], sd["depth_layer.bias"])
+        if self.ctor["depth_num"] > 1:                                                      # multi_kp, full_net.py:319-329
+            depths = gamma.view(-1, self.ctor["depth_num"]) * k_value.view(-1, 1).expand(-1, self.ctor["depth_num"]) / 1000.0
+            depth = depths[:, self.ctor["depth_root"]].reshape(-1, 1)
+            if trace is not None:
+                trace["depths"] = depths
+        else:
+            depth = (gamma.view(-1, 1) * k_value.view(-1, 1)).reshape(B, 1) / 1000.0      # full_net.py:334-336
         if self.backbone == "resnet50":
             x_out = network.resnet50(x_reg, sd, "reg_backbone.", calib)
             xf = torch.nn.functional.avg_pool2d(x_out, 8, 1).view(B, -1)
@@ -70,7 +81,12 @@ class OracleModel:
         p0 = sd["init_pose"].expand(B, -1) if init_pose is None else init_pose        # full_net.py:268-272
         r0 = sd["init_rot"].expand(B, -1) if init_rot is None else init_rot
         pose = network.iterative_head(xf, p0, sd, "fc_pose_1", "fc_pose_2", "decpose", self.n_iter, tp)
-        rot = network.iterative_head(xf, r0, sd, "fc_rot_1", "fc_rot_2", "decrot", self.n_iter, tr)
+        if self.ctor["direct_reg_rot"]:
+            rot = network.direct_rot_head(xf, sd)
+        elif self.ctor["rot_iterative_matmul"]:
+            rot = network.matmul_rot_head(xf, r0, sd, self.n_iter, tr)
+        else:
+            rot = network.iterative_head(xf, r0, sd, "fc_rot_1", "fc_rot_2", "decrot", self.n_iter, tr)
         xyz_fk = torch.from_numpy(self.fk(pose.numpy(), rot.numpy(), trans.numpy()))
         if trace is not None:
             trace.update(logits=logits, xf=xf, img_feat=img_feat, pose_iters=tp, rot_iters=tr)

@@ -134,3 +134,45 @@ def iterative_head(xf, state, sd, fc1, fc2, dec, n_iter=4, trace=None):
         if trace is not None:
             trace.append(state.clone())
     return state
+
+
+def rot6d_to_rotmat(r):
+    # lib/utils/geometries.py:100-115: rows (x, y, z) with x = a1/|a1|, z = (x X a2)/|.|, y = z X x
+    x = r[..., 0:3] / torch.norm(r[..., 0:3], p=2, dim=-1, keepdim=True)
+    z = torch.cross(x, r[..., 3:6], dim=-1)
+    z = z / torch.norm(z, p=2, dim=-1, keepdim=True)
+    y = torch.cross(z, x, dim=-1)
+    return torch.stack((x, y, z), -2)
+
+
+def matmul_rot_head(xf, state, sd, n_iter=4, trace=None):
+    # full_net.py:413-429 (rot_iterative_matmul): the regressed 6-vector is a rotation COMPOSED with the current one,
+    # and the state is the first two rows of the product (geometries.py:117-132)
+    for _ in range(n_iter):
+        xc = torch.cat([xf, state], 1)
+        xc = F.linear(xc, sd["fc_rot_1.weight"], sd["fc_rot_1.bias"])
+        xc = F.linear(xc, sd["fc_rot_2.weight"], sd["fc_rot_2.bias"])
+        d = F.linear(xc, sd["decrot.weight"], sd["decrot.bias"])
+        state = (rot6d_to_rotmat(d) @ rot6d_to_rotmat(state))[..., :2, :].reshape(-1, 6)
+        if trace is not None:
+            trace.append(state.clone())
+    return state
+
+
+def direct_rot_head(xf, sd):
+    # full_net.py:395-409 (direct_reg_rot): seven linear layers, fc_rot_1's output added back before the decoder
+    x1 = F.linear(xf, sd["fc_rot_1.weight"], sd["fc_rot_1.bias"])
+    x = x1
+    for i in range(2, 7):
+        x = F.linear(x, sd["fc_rot_%d.weight" % i], sd["fc_rot_%d.bias" % i])
+    return F.linear(x + x1, sd["decrot.weight"], sd["decrot.bias"])
+
+
+def depth_add_fc(feat, sd):
+    # full_net.py:296-313 (add_fc): 2048 -> 1024 -> 512 -> BatchNorm1d -> LeakyReLU -> 1024 (+skip)/2 -> 2048 (+skip)/2
+    f1 = F.linear(feat, sd["depth_fc_d1.weight"], sd["depth_fc_d1.bias"])
+    f2 = F.linear(f1, sd["depth_fc_d2.weight"], sd["depth_fc_d2.bias"])
+    mid = F.batch_norm(f2, sd["depth_bn.running_mean"], sd["depth_bn.running_var"], sd["depth_bn.weight"], sd["depth_bn.bias"], False, 0.0, 1e-5)
+    mid = F.leaky_relu(mid, 0.01)
+    f3 = 0.5 * (F.linear(mid, sd["depth_fc_u2.weight"], sd["depth_fc_u2.bias"]) + f1)
+    return 0.5 * (F.linear(f3, sd["depth_fc_u1.weight"], sd["depth_fc_u1.bias"]) + feat)

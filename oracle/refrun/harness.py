@@ -95,20 +95,23 @@ def setup():
     return ns
 
 
-def make_cfg(robot, backbone_name=None):
-    """args object the reference ctor reads (full_net.py:58-75), from the shipped YAML (configs/<robot>/full.yaml)."""
+def make_cfg(robot, backbone_name=None, **overrides):
+    """args object the reference ctor reads (full_net.py:58-75), from the shipped YAML (configs/<robot>/full.yaml);
+    `overrides` set constructor switches the shipped files leave at their defaults (direct_reg_rot, add_fc, multi_kp, ...)."""
     ns = setup()
     cfg = ns.core_config.make_cfg(argparse.Namespace(config=f"configs/{robot}/full.yaml", resume=False))
     cfg.pretrained_rootnet = None
     if backbone_name is not None:
         cfg.backbone_name = backbone_name
+    for k, v in overrides.items():
+        setattr(cfg, k, v)
     return cfg
 
 
-def build_model(robot, backbone_name=None):
+def build_model(robot, backbone_name=None, **overrides):
     """Construct RootNetwithRegInt directly (the factory's init_weights call raises for hrnet32)."""
     ns = setup()
-    cfg = make_cfg(robot, backbone_name)
+    cfg = make_cfg(robot, backbone_name, **overrides)
     init = {"robot_type": robot, "pose_params": ns.const.INITIAL_JOINT_ANGLE,
             "cam_params": np.eye(4, dtype=float), "init_pose_from_mean": True}
     model = ns.full_net.RootNetwithRegInt(init, cfg)
@@ -122,12 +125,14 @@ def build_model(robot, backbone_name=None):
 def forward(model, x_reg, x_root, k_value, K):
     """The boundary call (function.py:133-141): 8-tuple + caller-side projections of both 3-D keypoint sets."""
     ns = setup()
+    names = ["joint_angles", "rot6d", "trans", "root_uv", "root_depth", "uvd", "kp3d_int", "kp3d_fk"]
     with torch.no_grad():
         out = model(x_reg, x_root, k_value, K)
-        kp2d_int = ns.transforms.point_projection_from_3d_tensor(K, out[6])
-        kp2d_fk = ns.transforms.point_projection_from_3d_tensor(K, out[7])
-    names = ["joint_angles", "rot6d", "trans", "root_uv", "root_depth", "uvd", "kp3d_int", "kp3d_fk"]
-    res = {n: o for n, o in zip(names, out)}
+        if len(out) == 9:                     # multi_kp: every regressed depth rides along after the root depth (full_net.py:462-464)
+            names = names[:5] + ["depths"] + names[5:]
+        res = {n: o for n, o in zip(names, out)}
+        kp2d_int = ns.transforms.point_projection_from_3d_tensor(K, res["kp3d_int"])
+        kp2d_fk = ns.transforms.point_projection_from_3d_tensor(K, res["kp3d_fk"])
     res["kp2d_int"] = kp2d_int
     res["kp2d_fk"] = kp2d_fk
     return res

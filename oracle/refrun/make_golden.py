@@ -188,6 +188,35 @@ def preprocess():
     print("preprocess", np.stack(crops).shape, "k_value", kvs)
 
 
+# constructor variants outside the shipped configuration (full_net.py:107-131, 149-164): name -> reference cfg overrides
+VARIANTS = {
+    "direct_addfc_multikp": dict(direct_reg_rot=True, add_fc=True, multi_kp=True, kps_need_depth=[0, 3, 6]),
+    "rotmatmul": dict(rot_iterative_matmul=True),
+}
+
+
+def variant_ctor(over, ref_kp):
+    """The same switches in the form synth / the oracle / the CUDA path take."""
+    kps = over.get("kps_need_depth") if over.get("multi_kp") else None
+    return dict(direct_reg_rot=bool(over.get("direct_reg_rot", False)), rot_iterative_matmul=bool(over.get("rot_iterative_matmul", False)),
+                add_fc=bool(over.get("add_fc", False)), depth_num=len(kps) if kps else 1, depth_root=kps.index(ref_kp) if kps else 0)
+
+
+def variants():
+    robot, bb, B, seed = "panda", "resnet50", 3, 31
+    for name, over in VARIANTS.items():
+        ctor = variant_ctor(over, consts.ROBOTS[robot]["ref_kp"])
+        sd = synth.make_state_dict(robot, bb, WEIGHT_SEED, ctor={k: v for k, v in ctor.items() if k != "depth_root"})
+        model, _ = harness.build_model(robot, bb, **over)
+        model.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+        img, K, kv = synth.make_inputs(B, seed)
+        res = harness.forward(model, t(img), t(img), t(kv), t(K))
+        out = {k: v.numpy() for k, v in res.items()}
+        out["meta"] = np.asarray([WEIGHT_SEED, seed, B], np.int64)
+        np.savez_compressed(os.path.join(OUT, "variant_%s.npz" % name), **out)
+        print("variant", name, ctor, "rot6d[0]", out["rot6d"][0].round(3), "depth", out["root_depth"].ravel().round(3))
+
+
 def metrics():
     """compute_metrics_batch + summary_add_pck of the reference itself (lib/utils/metrics.py) on synth.make_metrics_inputs."""
     ns = harness.setup()
@@ -228,7 +257,7 @@ def metrics():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    what = sys.argv[1:] or ["fk", "softargmax", "fullnet", "undamped", "checkpoint", "preprocess", "metrics"]
+    what = sys.argv[1:] or ["fk", "softargmax", "fullnet", "undamped", "checkpoint", "preprocess", "metrics", "variants"]
     if "fk" in what:
         fk()
     if "softargmax" in what:
@@ -245,3 +274,5 @@ if __name__ == "__main__":
         preprocess()
     if "metrics" in what:
         metrics()
+    if "variants" in what:
+        variants()

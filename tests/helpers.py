@@ -25,6 +25,21 @@ def oracle_for(robot, backbone, seed=1234, recipe="damped"):
     return _oracles[key]
 
 
+# constructor variants outside the shipped configuration (tests/golden/variant_<name>.npz, made by the reference built with
+# these switches: oracle/refrun/make_golden.py variants): name -> (config keys as the reference spells them, ctor dict of the port)
+VARIANT_CASES = {
+    "direct_addfc_multikp": (dict(direct_reg_rot=True, add_fc=True, multi_kp=True, kps_need_depth=[0, 3, 6]),
+                             dict(direct_reg_rot=True, rot_iterative_matmul=False, add_fc=True, depth_num=3, depth_root=1)),
+    "rotmatmul": (dict(rot_iterative_matmul=True),
+                  dict(direct_reg_rot=False, rot_iterative_matmul=True, add_fc=False, depth_num=1, depth_root=0)),
+}
+
+
+def variant_state_dict(name, seed=1234):
+    ctor = VARIANT_CASES[name][1]
+    return synth.make_state_dict("panda", "resnet50", seed, ctor={k: v for k, v in ctor.items() if k != "depth_root"})
+
+
 def checkpoint_case():
     """The weights of tests/golden/fullnet_panda_resnet50_ckpt.npz as the two reference-format checkpoints it was made
     from (oracle/refrun/make_golden.py checkpoint()): (main checkpoint dict with DataParallel-prefixed keys and no DepthNet

@@ -857,3 +857,51 @@ def test_metrics_tail_against_reference_golden(robot, dev):
         w3 = ometrics.summary(e3, e2)
         for k in w3:
             np.testing.assert_allclose(float(s3[k]), float(w3[k]), rtol=1e-6, atol=1e-9, err_msg=k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16"])
+@pytest.mark.parametrize("name", list(helpers.VARIANT_CASES))
+def test_constructor_variants_against_reference_golden(name, prec, dev):
+    """8f N4: direct_reg_rot + add_fc + multi_kp and rot_iterative_matmul on the device, against the reference built with those
+    switches (tests/golden/variant_*.npz) and, at a second batch size, against the oracle port."""
+    from hrp_b200.model import HoliRobPoseB200
+    from oracle import model as omodel
+    g = helpers.load_golden("variant_%s.npz" % name)
+    wseed, seed, B = (int(v) for v in g["meta"])
+    cfg, ctor = helpers.VARIANT_CASES[name]
+    sd = helpers.variant_state_dict(name, wseed)
+    model = HoliRobPoseB200("panda", dict(cfg), device=dev, precision=prec)
+    model.load_state_dict(sd)
+    img, K, kv = helpers.inputs(B, seed)
+    out = model(img.to(dev), img.to(dev), kv.to(dev), K.to(dev))
+    names = ["joint_angles", "rot6d", "trans", "root_uv", "root_depth", "uvd", "kp3d_int", "kp3d_fk"]
+    if cfg.get("multi_kp"):
+        assert len(out) == 9                                                   # full_net.py:462-464
+        names = names[:5] + ["depths"] + names[5:]
+        assert tuple(out[5].shape) == (B, len(cfg["kps_need_depth"]))
+    else:
+        assert len(out) == 8
+    res = dict(zip(names, out))
+    t_rad, t_m, t_px = (2e-5, 2e-5, 1e-2) if prec == "fp32" else (1e-3, 1e-3, 0.5)
+    tol = dict(joint_angles=t_rad, rot6d=t_rad, trans=t_m, root_depth=t_m, uvd=t_rad, kp3d_int=t_m, kp3d_fk=t_m, root_uv=t_px, depths=t_m)
+    for k, v in res.items():
+        assert helpers.maxdiff(v, g[k]) < tol[k], (k, helpers.maxdiff(v, g[k]))
+    # a batch the golden does not hold, with init_rot overridden (only the refinement variant reads it)
+    om = omodel.OracleModel("panda", sd, open(consts.urdf_path("panda")).read(), "resnet50", ctor=ctor)
+    img2, K2, kv2 = helpers.inputs(5, seed + 1)
+    r0 = torch.tensor([[0.9, 0.1, -0.2, 0.05, 1.1, 0.3]]).expand(5, 6).contiguous()
+    want = om.forward(img2, img2, kv2, K2, init_rot=r0)
+    got = model(img2.to(dev), img2.to(dev), kv2.to(dev), K2.to(dev), init_rot=r0.to(dev))
+    if cfg.get("multi_kp"):
+        got = got[:5] + got[6:]
+    for k, a, b in zip(["joint_angles", "rot6d", "trans", "root_uv", "root_depth"], got, want):
+        assert helpers.maxdiff(a, b) < tol[k], (k, helpers.maxdiff(a, b))
+    if name == "rotmatmul":
+        iters = model.debug_tensor("head_iters", 5).reshape(5, model.n_iter, model.dof + 6)
+        trace = {}
+        om.forward(img2, img2, kv2, K2, init_rot=r0, trace=trace)
+        for n in range(model.n_iter):                                          # every composed rotation, not just the last
+            assert helpers.maxdiff(iters[:, n, model.dof:], trace["rot_iters"][n]) < t_rad * 2
+            R = iters[:, n, model.dof:].reshape(5, 2, 3)
+            assert float((R.norm(dim=2) - 1).abs().max()) < 1e-5 and float((R[:, 0] * R[:, 1]).sum(1).abs().max()) < 1e-5

@@ -5,6 +5,8 @@ import socket
 
 import numpy as np
 import pytest
+
+import helpers
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -33,13 +35,26 @@ def test_cxx_graph_builder_wants_the_reference_state_dict(lib_built, robot, back
     assert sorted(m.expected_tensors()) == mine
 
 
+@pytest.mark.parametrize("name", list(helpers.VARIANT_CASES))
+def test_cxx_graph_builder_wants_the_variant_state_dicts(lib_built, name):
+    """Constructor variants (8f N4): same tensor list as the reference built with those switches (the goldens' generator
+    loads synth's state dict into it with strict=True)."""
+    from hrp_b200.model import HoliRobPoseB200
+    cfg, ctor = helpers.VARIANT_CASES[name]
+    m = HoliRobPoseB200("panda", dict(cfg))
+    mine = sorted((n, tuple(s)) for n, s, _ in arch.full_net("panda", "resnet50", {k: v for k, v in ctor.items() if k != "depth_root"}))
+    assert sorted(m.expected_tensors()) == mine
+
+
 def test_unsupported_configs_fail_loudly(lib_built):
     from hrp_b200.model import HoliRobPoseB200
     with pytest.raises(ValueError):
         HoliRobPoseB200("owi535")
-    for k in ("reg_joint_map", "direct_reg_rot", "rot_iterative_matmul", "add_fc", "multi_kp"):
+    for k in ("reg_joint_map", "use_rpmg"):
         with pytest.raises(NotImplementedError):
             HoliRobPoseB200("panda", {k: True})
+    with pytest.raises(ValueError, match="not in list"):                      # kps_need_depth.index(reference_keypoint_id), full_net.py:328
+        HoliRobPoseB200("panda", {"multi_kp": True, "kps_need_depth": [0, 1]})
     with pytest.raises(NotImplementedError):
         HoliRobPoseB200("panda", {"rotation_dim": 4})
     with pytest.raises(NotImplementedError):

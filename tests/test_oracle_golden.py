@@ -152,3 +152,26 @@ def test_metrics_match_reference(robot):
     assert list(s.keys()) == [str(k) for k in g["summary_keys"]]
     for k, v in zip(g["summary_keys"], g["summary_values"]):
         np.testing.assert_allclose(float(s[str(k)]), v, rtol=1e-6, atol=1e-9, err_msg=str(k))
+
+
+@pytest.mark.parametrize("name", list(helpers.VARIANT_CASES))
+def test_constructor_variants_match_reference(name):
+    """8f N4: direct_reg_rot + add_fc + multi_kp, and rot_iterative_matmul (full_net.py:107-131, 149-164, 293-330, 395-429),
+    against the reference constructed with those switches."""
+    g = helpers.load_golden("variant_%s.npz" % name)
+    wseed, seed, B = (int(v) for v in g["meta"])
+    from oracle import model as omodel
+    om = omodel.OracleModel("panda", helpers.variant_state_dict(name, wseed), open(consts.urdf_path("panda")).read(), "resnet50",
+                            ctor=helpers.VARIANT_CASES[name][1])
+    img, K, kv = helpers.inputs(B, seed)
+    res = om.forward_dict(img, img, kv, K)
+    for k, t in dict(joint_angles=2e-5, rot6d=2e-5, trans=2e-5, root_depth=2e-5, uvd=2e-5, kp3d_fk=2e-5, kp2d_int=1e-2, kp2d_fk=1e-2).items():
+        assert helpers.maxdiff(res[k], g[k]) < t, (k, helpers.maxdiff(res[k], g[k]))
+    if "depths" in g:                                                              # multi_kp: the 9-tuple's extra entry
+        trace = {}
+        om.forward(img, img, kv, K, trace=trace)
+        assert g["depths"].shape == (B, 3) and helpers.maxdiff(trace["depths"], g["depths"]) < 2e-5
+        assert helpers.maxdiff(g["depths"][:, 1:2], g["root_depth"]) == 0.0
+    shipped, _ = helpers.oracle_for("panda", "resnet50", wseed)
+    base = shipped.forward_dict(img, img, kv, K)
+    assert helpers.maxdiff(base["rot6d"], g["rot6d"]) > 1e-2                       # the switch matters
