@@ -104,7 +104,8 @@ def _linear(p, cin, cout):
     yield p + ".bias", (cout,), "lin_b"
 
 
-VARIANT_DEFAULTS = dict(direct_reg_rot=False, rot_iterative_matmul=False, add_fc=False, depth_num=1)
+VARIANT_DEFAULTS = dict(direct_reg_rot=False, rot_iterative_matmul=False, add_fc=False, depth_num=1, reg_joint_map=False,
+                        joint_conv_dim=())
 
 
 def full_net(robot, backbone="resnet50", variant=None):
@@ -112,7 +113,8 @@ def full_net(robot, backbone="resnet50", variant=None):
 
     variant: the constructor switches that change the tensor list (full_net.py:107-131, 149-176): direct_reg_rot (a seven-layer
     rotation regressor instead of the refinement loop), add_fc (the DepthNet's bottleneck MLP), depth_num (multi_kp: one depth
-    output per entry of kps_need_depth). rot_iterative_matmul changes arithmetic only."""
+    output per entry of kps_need_depth), reg_joint_map + joint_conv_dim (joint angles from per-joint maps instead of the
+    refinement MLP). rot_iterative_matmul changes arithmetic only."""
     v = dict(VARIANT_DEFAULTS, **(variant or {}))
     spec = consts.ROBOTS[robot]
     dof, nkpt = spec["dof"], spec["nkpt"]
@@ -129,9 +131,16 @@ def full_net(robot, backbone="resnet50", variant=None):
         yield from hrnet_w32("reg_backbone.", hm)
     else:
         raise ValueError("unsupported backbone_name %r (supported: resnet50, hrnet32)" % backbone)
-    yield from _linear("fc_pose_1", consts.FEATURE_DIM + dof, 1024)
-    yield from _linear("fc_pose_2", 1024, 1024)
-    yield from _linear("decpose", 1024, dof)
+    if v["reg_joint_map"]:                                      # full_net.py:92-101, 240-258 (nn.Sequential indices 0,1 / 3,4 / 6,7)
+        cin = consts.FEATURE_DIM
+        for i, c in enumerate(v["joint_conv_dim"]):
+            yield from _conv_bn("joint_conv_layers.%d" % (3 * i), "joint_conv_layers.%d" % (3 * i + 1), cin, c, 3, bias=True)
+            cin = c
+        yield from _conv("joint_final_layer", cin, dof, 1, bias=True)
+    else:
+        yield from _linear("fc_pose_1", consts.FEATURE_DIM + dof, 1024)
+        yield from _linear("fc_pose_2", 1024, 1024)
+        yield from _linear("decpose", 1024, dof)
     if v["direct_reg_rot"]:                                     # full_net.py:110-117
         yield from _linear("fc_rot_1", consts.FEATURE_DIM, 1024)
         for i in range(2, 7):

@@ -40,7 +40,8 @@ class Config(C.Structure):
     _fields_ = [("backbone", C.c_int32), ("precision", C.c_int32), ("n_iter", C.c_int32), ("fix_root", C.c_int32),
                 ("image_size", C.c_float), ("depth_factor", C.c_float),
                 ("direct_reg_rot", C.c_int32), ("rot_iterative_matmul", C.c_int32), ("add_fc", C.c_int32),
-                ("depth_num", C.c_int32), ("depth_root", C.c_int32)]
+                ("depth_num", C.c_int32), ("depth_root", C.c_int32), ("reg_joint_map", C.c_int32),
+                ("joint_conv_dim", C.c_int32 * 3), ("joint_bounds", C.c_float * 32)]
 
 
 _lib = None

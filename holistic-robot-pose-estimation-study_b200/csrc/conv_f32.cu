@@ -606,6 +606,61 @@ int depth_head_launch(const float* feat, const float* w, const float* bias, cons
   return HRP_OK;
 }
 
+// reg_joint_map head (full_net.py:92-101, 376-379): joint_final_layer (1x1 conv, d2 -> dof, bias) on the [B,HW,d2] NHWC map
+// that joint_conv_layers left, then HeatmapIntegralJoint (lib/utils/integral.py:211-251): softmax over the HW positions of
+// each joint's map, expected position index / HW in [0,1), scaled into the joint's bounds. One CTA per frame; the logits
+// (dof x HW floats) never leave shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256)
+joint_map_head_kernel(const T* __restrict__ y, const float* __restrict__ w, const float* __restrict__ bias,
+                      const float* __restrict__ bounds, float* __restrict__ pose, int HW, int C, int dof) {
+  extern __shared__ float jm[];                       // logits [dof][HW]
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* yb = y + (size_t)b * HW * C;
+  for (int o = warp; o < dof * HW; o += 8) {          // one warp per (joint, position): a C-long dot product
+    const int j = o / HW, p = o - j * HW;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float v;
+      if constexpr (sizeof(T) == 4) v = __ldg(reinterpret_cast<const float*>(yb) + (size_t)p * C + c);
+      else if constexpr (std::is_same<T, __half>::value) v = __half2float(yb[(size_t)p * C + c]);
+      else v = __bfloat162float(yb[(size_t)p * C + c]);
+      acc = fmaf(__ldg(w + (size_t)j * C + c), v, acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) jm[o] = acc + bias[j];
+  }
+  __syncthreads();
+  for (int j = warp; j < dof; j += 8) {
+    const float* l = jm + j * HW;
+    float mx = -INFINITY;
+    for (int p = lane; p < HW; p += 32) mx = fmaxf(mx, l[p]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float se = 0.f, sp = 0.f;
+    for (int p = lane; p < HW; p += 32) { const float e = expf(l[p] - mx); se += e; sp += e * (float)p; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, off); sp += __shfl_xor_sync(0xffffffffu, sp, off); }
+    if (lane == 0) {
+      const float coord = (sp / se) / (float)HW;                       // integral.py:239-243
+      const float lo = bounds[2 * j], hi = bounds[2 * j + 1];
+      pose[(size_t)b * dof + j] = coord * (hi - lo) + lo;               // integral.py:245-249
+    }
+  }
+}
+
+int joint_map_head_launch(const void* y, const float* w, const float* bias, const float* bounds, float* pose, int B, int HW, int C,
+                          int dof, int bf16, cudaStream_t s) {
+  if (B <= 0) return HRP_OK;
+  const size_t sm = (size_t)dof * HW * sizeof(float);
+  if (bf16 == 2) joint_map_head_kernel<__half><<<B, 256, sm, s>>>(static_cast<const __half*>(y), w, bias, bounds, pose, HW, C, dof);
+  else if (bf16) joint_map_head_kernel<__nv_bfloat16><<<B, 256, sm, s>>>(static_cast<const __nv_bfloat16*>(y), w, bias, bounds, pose, HW, C, dof);
+  else joint_map_head_kernel<float><<<B, 256, sm, s>>>(static_cast<const float*>(y), w, bias, bounds, pose, HW, C, dof);
+  HRP_CHECK_LAUNCH("joint_map_head_kernel");
+  return HRP_OK;
+}
+
 // DepthNet head of the constructor variants (full_net.py:293-330): add_fc -- the bottleneck MLP 2048 -> 1024 -> 512 ->
 // BatchNorm1d -> LeakyReLU -> 1024 -> 2048 with two averaged skips -- and multi_kp -- `dn` depth outputs per frame. Everything
 // around the LeakyReLU is linear, so (composed in fp64 at hrp_finalize_weights, network.cu)

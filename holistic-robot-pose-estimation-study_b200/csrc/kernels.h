@@ -137,6 +137,8 @@ int depth_head_launch(const float* feat, const float* w, const float* bias, cons
 // Every iterate of both refinement heads as one affine map per iterate (conv_f32.cu, heads_affine_kernel):
 // iters [B, n_iter, dof+6]; pose [B,dof] / rot [B,6] receive the last iterate. G [n_iter*(dof+6), F], P per iterate
 // {dof x dof, 6 x 6}, g [n_iter*(dof+6)], s0_default [dof+6]; ovr_* optional per-frame initial states.
+int joint_map_head_launch(const void* y, const float* w, const float* bias, const float* bounds, float* pose, int B, int HW, int C,
+                          int dof, int bf16, cudaStream_t s);
 int depth_head_ex_launch(const float* feat, const float* Af, const float* Bz, const float* Wz, const float* bz, const float* c,
                          const float* k_value, float* depth, float* depths, int B, int C, int Z, int dn, int root_index, cudaStream_t s);
 int heads_affine_launch(const float* xf, const float* G, const float* P, const float* g, const float* s0_default,

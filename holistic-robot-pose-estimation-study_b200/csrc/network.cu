@@ -23,7 +23,7 @@ struct hrp_fk;  // fk_project.cu
 
 namespace hrp {
 
-enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_HEADS, OP_RESERVED, OP_SOFTARGMAX, OP_FK, OP_STEM_PACK, OP_BLOCK, OP_CHAIN };
+enum OpKind { OP_STEM, OP_CONV, OP_MAXPOOL, OP_FUSE, OP_AVGPOOL, OP_DEPTH, OP_HEADS, OP_JOINTMAP, OP_SOFTARGMAX, OP_FK, OP_STEM_PACK, OP_BLOCK, OP_CHAIN };
 enum { CLS_CONV_TC = 0, CLS_CONV_F32 = 1, CLS_STEM = 2, CLS_ELEM = 3, CLS_HEADS = 4, CLS_SOFTARGMAX = 5, CLS_FK = 6 };
 enum TKind { T_WS = 0, T_XREG, T_XROOT, T_KVAL, T_KMAT, T_FIELD, T_CONST, T_INITP, T_INITR, T_FLAGS };
 
@@ -264,9 +264,17 @@ void build_specs(hrp_handle* h) {
   } else {
     spec_hrnet(sb, "reg_backbone.", hm);
   }
-  sb.linear("fc_pose_1", 2048 + h->dof, 1024);
-  sb.linear("fc_pose_2", 1024, 1024);
-  sb.linear("decpose", 1024, h->dof);
+  if (h->cfg.reg_joint_map) {                        // full_net.py:92-101, 240-258
+    const int* jd = h->cfg.joint_conv_dim;
+    sb.conv_bn("joint_conv_layers.0", "joint_conv_layers.1", 2048, jd[0], 3, true);
+    sb.conv_bn("joint_conv_layers.3", "joint_conv_layers.4", jd[0], jd[1], 3, true);
+    sb.conv_bn("joint_conv_layers.6", "joint_conv_layers.7", jd[1], jd[2], 3, true);
+    sb.conv("joint_final_layer", jd[2], h->dof, 1, true);
+  } else {
+    sb.linear("fc_pose_1", 2048 + h->dof, 1024);
+    sb.linear("fc_pose_2", 1024, 1024);
+    sb.linear("decpose", 1024, h->dof);
+  }
   if (h->cfg.direct_reg_rot) {                       // full_net.py:110-117
     sb.linear("fc_rot_1", 2048, 1024);
     for (int i = 2; i <= 6; ++i) sb.linear(S("fc_rot_%d", i), 1024, 1024);
@@ -669,7 +677,8 @@ struct GraphBuilder {
   // so iterate n is  s_n = G_n xf + P_n s_0 + g_n  with  P_n = (I+M)^n, S_n = sum_{j<n} (I+M)^j, G_n = S_n A, g_n = S_n c.
   // Composed here in fp64, evaluated by ONE launch for every iterate of both heads (heads_affine_kernel).
   void heads(const Tn& xf) {
-    const int dof = h->dof, F = 2048, Hd = 1024, nit = h->cfg.n_iter, R1 = dof + 6;
+    // reg_joint_map: the joint angles come from joint_map_head (below); the kernel then sees a rotation head only (dof = 0)
+    const int dof = h->cfg.reg_joint_map ? 0 : h->dof, F = 2048, Hd = 1024, nit = h->cfg.n_iter, R1 = dof + 6;
     const char* fc1[2] = {"fc_pose_1", "fc_rot_1"};
     const char* fc2[2] = {"fc_pose_2", "fc_rot_2"};
     const char* dec[2] = {"decpose", "decrot"};
@@ -678,6 +687,7 @@ struct GraphBuilder {
     std::vector<float> G((size_t)nit * R1 * F), P((size_t)nit * (dof * dof + 36)), gv((size_t)nit * R1), s0(R1);
     const bool direct = h->cfg.direct_reg_rot != 0, matmul = !direct && h->cfg.rot_iterative_matmul != 0;
     for (int k = 0; k < 2; ++k) {
+      if (k == 0 && dof == 0) continue;
       if (k == 1 && direct) { direct_rot(G, P, gv, s0); continue; }
       const int n = sd[k], in1 = F + n;
       const float* w1 = W(std::string(fc1[k]) + ".weight"); const float* b1 = W(std::string(fc1[k]) + ".bias");
@@ -761,7 +771,7 @@ struct GraphBuilder {
   // skip, no activation -> one affine map of xf, the same for every "iterate" and independent of init_rot. Row vectors of
   // decrot are pulled back through the layers in fp64.
   void direct_rot(std::vector<float>& G, std::vector<float>& P, std::vector<float>& gv, std::vector<float>& s0) {
-    const int dof = h->dof, F = 2048, Hd = 1024, nit = h->cfg.n_iter, R1 = dof + 6;
+    const int dof = h->cfg.reg_joint_map ? 0 : h->dof, F = 2048, Hd = 1024, nit = h->cfg.n_iter, R1 = dof + 6;
     const float* wd = W("decrot.weight"); const float* bd = W("decrot.bias");
     const float* w1 = W("fc_rot_1.weight"); const float* b1 = W("fc_rot_1.bias");
     const float* i0 = W("init_rot");
@@ -920,6 +930,20 @@ struct GraphBuilder {
       Tn x = resnet50(h->t_xreg, "reg_backbone.");
       cur_lane = head_lane;
       xf = avgpool(x);
+      if (h->cfg.reg_joint_map) {                // joint_conv_layers + joint_final_layer + HeatmapIntegralJoint, beside the deconv head
+        const int* jd = h->cfg.joint_conv_dim;
+        Tn j = conv(x, "joint_conv_layers.0", "joint_conv_layers.1", jd[0], 3, 1, 1, 1);
+        j = conv(j, "joint_conv_layers.3", "joint_conv_layers.4", jd[1], 3, 1, 1, 1);
+        j = conv(j, "joint_conv_layers.6", "joint_conv_layers.7", jd[2], 3, 1, 1, 1);
+        const float* w = W("joint_final_layer.weight"); const float* b = W("joint_final_layer.bias");
+        if (status != HRP_OK) return status;
+        OpDesc op{};
+        op.kind = OP_JOINTMAP; op.cls = CLS_HEADS; op.in = j.id; op.out = h->t_field[HRP_F_POSE]; op.Hi = j.H; op.Wi = j.W; op.Cin = j.C; op.dof = h->dof;
+        op.wptr = upload(std::vector<float>(w, w + (size_t)h->dof * j.C)); op.bptr = upload(std::vector<float>(b, b + h->dof));
+        op.same[0] = constant(upload(std::vector<float>(h->cfg.joint_bounds, h->cfg.joint_bounds + 2 * h->dof))); op.n_same = 1;
+        op.flops = 2.0 * j.H * j.W * j.C * h->dof;
+        push(op);
+      }
       cur_lane = kp_lane;
       phase_lane0 = head_lane + 1;           // lanes 6, 7, 8
       Tn d = deconv(x, 0, 256);
@@ -1305,7 +1329,9 @@ int run_ops(hrp_handle* h, Plan* p, const IoPtrs& io, cudaStream_t st, Profile* 
                                     static_cast<const float*>(ptr(o.in3)), static_cast<const int*>(ptr(o.in4)), static_cast<float*>(ptr(o.out3)),
                                     static_cast<float*>(ptr(o.out)), static_cast<float*>(ptr(o.out2)), B, o.Cin, o.dof, o.N, o.relu, st_op));
         break;
-      case OP_RESERVED:
+      case OP_JOINTMAP:
+        HRP_TRY(joint_map_head_launch(ptr(o.in), o.wptr, o.bptr, static_cast<const float*>(ptr(o.same[0])), static_cast<float*>(ptr(o.out)), B, o.Hi * o.Wi, o.Cin,
+                                      o.dof, bf16, st_op));
         break;
       case OP_SOFTARGMAX: {
         if (h->sa_fused) {       // the heatmap conv already wrote 32 partial states per (frame, keypoint)
@@ -1378,6 +1404,12 @@ extern "C" int hrp_create(const hrp_config* cfg, const hrp_fk_program* robot, in
     return fail(HRP_ERR_INVALID, "hrp_create: unknown precision %d (0 fp32, 1 tf32, 2 bf16, 3 tf32x3, 4 f16)", cfg->precision);
   if (cfg->n_iter < 1 || cfg->n_iter > 16) return fail(HRP_ERR_INVALID, "hrp_create: n_iter %d out of range", cfg->n_iter);
   if (cfg->image_size != 256.0f) return fail(HRP_ERR_INVALID, "hrp_create: only 256x256 inputs are supported (got %g)", cfg->image_size);
+  if (cfg->reg_joint_map) {
+    if (cfg->backbone != HRP_BACKBONE_RESNET50) return fail(HRP_ERR_INVALID, "hrp_create: reg_joint_map needs the ResNet keypoint backbone (full_net.py:377 reads x_out)");
+    if (robot->dof > 16) return fail(HRP_ERR_INVALID, "hrp_create: reg_joint_map supports up to 16 joints");
+    for (int i = 0; i < 3; ++i)
+      if (cfg->joint_conv_dim[i] <= 0 || cfg->joint_conv_dim[i] % 32) return fail(HRP_ERR_INVALID, "hrp_create: joint_conv_dim[%d] = %d must be a positive multiple of 32", i, cfg->joint_conv_dim[i]);
+  }
   if (cfg->depth_num < 0 || cfg->depth_num > HRP_FK_MAX_KP || cfg->depth_root < 0 || cfg->depth_root >= std::max(1, cfg->depth_num))
     return fail(HRP_ERR_INVALID, "hrp_create: depth_num %d / depth_root %d out of range", cfg->depth_num, cfg->depth_root);
   std::unique_ptr<hrp_handle> h(new hrp_handle());

@@ -14,8 +14,8 @@ import torch
 
 from . import arch, capi, consts, urdf
 
-UNSUPPORTED = {  # ctor variants of the reference that no shipped config enables and this path does not build -> explicit error
-    "reg_joint_map": False, "use_rpmg": False,
+UNSUPPORTED = {  # ctor switches of the reference that no shipped config enables and this path does not build -> explicit error
+    "use_rpmg": False,
 }
 
 
@@ -197,6 +197,13 @@ class HoliRobPoseB200(torch.nn.Module):
         if self.multi_kp and self.reference_keypoint_id not in self.kps_need_depth:
             raise ValueError("%d is not in list" % self.reference_keypoint_id)      # what kps_need_depth.index raises, full_net.py:328
         self.depth_num = len(self.kps_need_depth)
+        self.reg_joint_map = bool(cfg.get("reg_joint_map", False))
+        self.joint_conv_dim = [int(v) for v in (cfg.get("joint_conv_dim") or [])] if self.reg_joint_map else []
+        if self.reg_joint_map:
+            if self.backbone_name not in ("resnet", "resnet50"):
+                raise NotImplementedError("reg_joint_map reads the ResNet trunk's feature map (full_net.py:377); backbone_name=%r has none" % self.backbone_name)
+            if len(self.joint_conv_dim) != 3 or any(d <= 0 or d % 32 for d in self.joint_conv_dim):
+                raise NotImplementedError("joint_conv_dim=%r: three positive multiples of 32 are supported" % (self.joint_conv_dim,))
         self.dof, self.nkpt = spec["dof"], spec["nkpt"]
         self.num_joints = self.nkpt
         if device is None:
@@ -214,7 +221,9 @@ class HoliRobPoseB200(torch.nn.Module):
         self._cfg = capi.Config(capi.BACKBONE[self.backbone_name], capi.PREC[precision], self.n_iter, int(self.fix_root),
                                 self.image_size, depth_factor, int(self.direct_reg_rot), int(self.rot_iterative_matmul),
                                 int(self.add_fc), self.depth_num if self.multi_kp else 0,
-                                self.kps_need_depth.index(self.reference_keypoint_id) if self.multi_kp else 0)
+                                self.kps_need_depth.index(self.reference_keypoint_id) if self.multi_kp else 0,
+                                int(self.reg_joint_map), (C.c_int32 * 3)(*(self.joint_conv_dim or [0, 0, 0])),
+                                (C.c_float * 32)(*[float(v) for lo_hi in spec["bounds"] for v in lo_hi]))   # const.py:239-284
         h = C.c_void_p()
         capi.check(capi.lib().hrp_create(C.byref(self._cfg), C.byref(self._prog_struct), self.device.index, C.byref(h)))
         self._h = h
@@ -518,6 +527,6 @@ def get_rootNetwithRegInt_model(init_param_dict, args, device=None, precision="f
     """Factory with the reference's name and arguments (full_net.py:470-505); weights are loaded by the caller."""
     cfg = dict(args) if isinstance(args, dict) else {k: getattr(args, k) for k in dir(args) if not k.startswith("_")}
     keys = ("backbone_name", "rootnet_backbone_name", "n_iter", "rotation_dim", "reg_joint_map", "direct_reg_rot",
-            "rot_iterative_matmul", "add_fc", "multi_kp", "kps_need_depth", "use_rpmg", "fix_root", "bbox_3d_shape",
+            "rot_iterative_matmul", "add_fc", "multi_kp", "kps_need_depth", "joint_conv_dim", "use_rpmg", "fix_root", "bbox_3d_shape",
             "reference_keypoint_id", "other_image_size")
     return HoliRobPoseB200(init_param_dict["robot_type"], {k: cfg[k] for k in keys if k in cfg}, device, precision)

@@ -104,7 +104,7 @@ def make_state_dict(robot, backbone="resnet50", seed=1234, calibrated=True, reci
     sd = {}
     for name, shape, kind in arch.full_net(robot, backbone, ctor):
         t = _draw(name, shape, kind, seed, robot, damped=recipe == "damped")
-        if name.startswith("depth_bn.") and kind in ("bn_mean", "bn_var"):   # BatchNorm1d of the add_fc variant: drawn, not calibrated
+        if name.startswith(("depth_bn.", "joint_conv_layers.")) and kind in ("bn_mean", "bn_var"):   # variant-only BatchNorms: drawn, not calibrated
             g = _rng(seed, name)
             t = (g.standard_normal(shape) * 0.1 if kind == "bn_mean" else g.uniform(0.5, 1.5, shape)).astype(np.float32)
         elif z is not None and kind in ("bn_mean", "bn_var"):

@@ -139,6 +139,10 @@ typedef struct {
   int32_t add_fc;                /* DepthNet bottleneck MLP in front of depth_layer (full_net.py:156-163, 296-313) */
   int32_t depth_num;             /* multi_kp: len(kps_need_depth) depth outputs (>= 1), all returned in HRP_F_DEPTHS; 0 = single root depth */
   int32_t depth_root;            /* multi_kp: kps_need_depth.index(reference_keypoint_id) (full_net.py:328-329) */
+  int32_t reg_joint_map;         /* joint angles from per-joint maps over the trunk's 8x8 grid + a 1-D soft-argmax instead of the
+                                    refinement loop (ResNet keypoint backbone only; full_net.py:92-101, 376-379; integral.py:211-251) */
+  int32_t joint_conv_dim[3];     /* channels of the three 3x3 conv + BN + ReLU layers in front of it (multiples of 32) */
+  float joint_bounds[32];        /* dof x {lower, upper} (lib/dataset/const.py:239-284) */
 } hrp_config;
 
 typedef struct hrp_handle hrp_handle;

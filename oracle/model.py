@@ -1,7 +1,7 @@
 """Oracle: the full inference forward `model(x_reg, x_root, k_value, K)` + caller-side projections.
 
 Follows lib/models/full_net.py:262-466 (shipped configuration: n_iter=4, rotation_dim=6, fix_root=True; the
-constructor variants direct_reg_rot / rot_iterative_matmul / add_fc / multi_kp through `ctor`; no reg_joint_map) and lib/core/function.py:133-141.
+constructor variants direct_reg_rot / rot_iterative_matmul / add_fc / multi_kp / reg_joint_map through `ctor`) and lib/core/function.py:133-141.
 """
 import numpy as np
 import torch
@@ -27,7 +27,8 @@ class OracleModel:
                  fix_root=True, n_iter=4, ctor=None):
         # constructor switches outside the shipped configuration (full_net.py:107-131, 149-164, 293-330, 395-444):
         # direct_reg_rot, rot_iterative_matmul, add_fc, depth_num (= len(kps_need_depth)) + depth_root (index of the root keypoint in it)
-        self.ctor = dict(direct_reg_rot=False, rot_iterative_matmul=False, add_fc=False, depth_num=1, depth_root=0)
+        self.ctor = dict(direct_reg_rot=False, rot_iterative_matmul=False, add_fc=False, depth_num=1, depth_root=0, reg_joint_map=False,
+                         joint_bounds=None)     # reg_joint_map (resnet50 only): joint angles from joint_map_head; bounds const.py:239-284
         self.ctor.update(ctor or {})
         self.robot = robot
         self.dof, self.nkpt, self.ref, _ = ROBOTS[robot]
@@ -80,7 +81,10 @@ class OracleModel:
         tr = [] if trace is not None else None
         p0 = sd["init_pose"].expand(B, -1) if init_pose is None else init_pose        # full_net.py:268-272
         r0 = sd["init_rot"].expand(B, -1) if init_rot is None else init_rot
-        pose = network.iterative_head(xf, p0, sd, "fc_pose_1", "fc_pose_2", "decpose", self.n_iter, tp)
+        if self.ctor["reg_joint_map"]:
+            pose = network.joint_map_head(x_out, sd, self.ctor["joint_bounds"])
+        else:
+            pose = network.iterative_head(xf, p0, sd, "fc_pose_1", "fc_pose_2", "decpose", self.n_iter, tp)
         if self.ctor["direct_reg_rot"]:
             rot = network.direct_rot_head(xf, sd)
         elif self.ctor["rot_iterative_matmul"]:

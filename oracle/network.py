@@ -176,3 +176,21 @@ def depth_add_fc(feat, sd):
     mid = F.leaky_relu(mid, 0.01)
     f3 = 0.5 * (F.linear(mid, sd["depth_fc_u2.weight"], sd["depth_fc_u2.bias"]) + f1)
     return 0.5 * (F.linear(f3, sd["depth_fc_u1.weight"], sd["depth_fc_u1.bias"]) + feat)
+
+
+def joint_map_head(x_out, sd, bounds):
+    # full_net.py:240-258, 376-379 (reg_joint_map): three conv3x3(+bias) + BN + ReLU on the trunk's map, a 1x1 conv to one map per
+    # joint, then HeatmapIntegralJoint (lib/utils/integral.py:229-251): softmax over the positions, expected index / count, scaled
+    # into the joint's [lower, upper]
+    y = x_out
+    for i in (0, 3, 6):
+        y = F.conv2d(y, sd["joint_conv_layers.%d.weight" % i], sd["joint_conv_layers.%d.bias" % i], padding=1)
+        p = "joint_conv_layers.%d." % (i + 1)
+        y = F.relu(F.batch_norm(y, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, 1e-5))
+    y = F.conv2d(y, sd["joint_final_layer.weight"], sd["joint_final_layer.bias"])
+    hm = F.softmax(y.reshape(y.shape[0], y.shape[1], -1), 2)
+    hm = hm / hm.sum(dim=2, keepdim=True)
+    n = hm.shape[-1]
+    coord = (hm * torch.arange(n, dtype=torch.float32).reshape(1, 1, n)).sum(dim=2) / float(n)
+    b = torch.as_tensor(bounds, dtype=torch.float32)
+    return coord * (b[:, 1] - b[:, 0])[None] + b[:, 0][None]

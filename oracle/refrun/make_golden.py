@@ -36,6 +36,7 @@ UNDAMPED = [("panda", "resnet50", 2, 2031), ("panda", "hrnet32", 1, 2032)]
 LOGIT_STRIDES = (37, 5, 7)
 FK_N, FK_SEED = 512, 99
 METRICS_N, METRICS_SEED = 400, 2718
+JOINTMAP_GAIN = 6.0
 SA_CASES = [("resnet50", 7, "blobs", 2, 11), ("resnet50", 7, "extreme", 2, 12), ("resnet50", 17, "noise", 1, 13),
             ("hrnet32", 8, "blobs", 2, 14), ("hrnet32", 17, "extreme", 1, 15)]
 
@@ -192,6 +193,7 @@ def preprocess():
 VARIANTS = {
     "direct_addfc_multikp": dict(direct_reg_rot=True, add_fc=True, multi_kp=True, kps_need_depth=[0, 3, 6]),
     "rotmatmul": dict(rot_iterative_matmul=True),
+    "jointmap": dict(reg_joint_map=True, joint_conv_dim=[128, 64, 32]),
 }
 
 
@@ -199,7 +201,8 @@ def variant_ctor(over, ref_kp):
     """The same switches in the form synth / the oracle / the CUDA path take."""
     kps = over.get("kps_need_depth") if over.get("multi_kp") else None
     return dict(direct_reg_rot=bool(over.get("direct_reg_rot", False)), rot_iterative_matmul=bool(over.get("rot_iterative_matmul", False)),
-                add_fc=bool(over.get("add_fc", False)), depth_num=len(kps) if kps else 1, depth_root=kps.index(ref_kp) if kps else 0)
+                add_fc=bool(over.get("add_fc", False)), depth_num=len(kps) if kps else 1, depth_root=kps.index(ref_kp) if kps else 0,
+                reg_joint_map=bool(over.get("reg_joint_map", False)), joint_conv_dim=tuple(over.get("joint_conv_dim", ())))
 
 
 def variants():
@@ -207,6 +210,8 @@ def variants():
     for name, over in VARIANTS.items():
         ctor = variant_ctor(over, consts.ROBOTS[robot]["ref_kp"])
         sd = synth.make_state_dict(robot, bb, WEIGHT_SEED, ctor={k: v for k, v in ctor.items() if k != "depth_root"})
+        if ctor["reg_joint_map"]:            # as drawn, the joint maps are nearly flat (every angle mid-range): give them contrast
+            sd["joint_final_layer.weight"] = sd["joint_final_layer.weight"] * np.float32(JOINTMAP_GAIN)
         model, _ = harness.build_model(robot, bb, **over)
         model.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
         img, K, kv = synth.make_inputs(B, seed)

@@ -32,12 +32,18 @@ VARIANT_CASES = {
                              dict(direct_reg_rot=True, rot_iterative_matmul=False, add_fc=True, depth_num=3, depth_root=1)),
     "rotmatmul": (dict(rot_iterative_matmul=True),
                   dict(direct_reg_rot=False, rot_iterative_matmul=True, add_fc=False, depth_num=1, depth_root=0)),
+    "jointmap": (dict(reg_joint_map=True, joint_conv_dim=[128, 64, 32]),
+                 dict(reg_joint_map=True, joint_conv_dim=(128, 64, 32), joint_bounds=consts.ROBOTS["panda"]["bounds"])),
 }
+JOINTMAP_GAIN = 6.0        # oracle/refrun/make_golden.py: contrast of the joint maps in the fixture
 
 
 def variant_state_dict(name, seed=1234):
     ctor = VARIANT_CASES[name][1]
-    return synth.make_state_dict("panda", "resnet50", seed, ctor={k: v for k, v in ctor.items() if k != "depth_root"})
+    sd = synth.make_state_dict("panda", "resnet50", seed, ctor={k: v for k, v in ctor.items() if k not in ("depth_root", "joint_bounds")})
+    if ctor.get("reg_joint_map"):
+        sd["joint_final_layer.weight"] = sd["joint_final_layer.weight"] * np.float32(JOINTMAP_GAIN)
+    return sd
 
 
 def checkpoint_case():

@@ -42,7 +42,7 @@ def test_cxx_graph_builder_wants_the_variant_state_dicts(lib_built, name):
     from hrp_b200.model import HoliRobPoseB200
     cfg, ctor = helpers.VARIANT_CASES[name]
     m = HoliRobPoseB200("panda", dict(cfg))
-    mine = sorted((n, tuple(s)) for n, s, _ in arch.full_net("panda", "resnet50", {k: v for k, v in ctor.items() if k != "depth_root"}))
+    mine = sorted((n, tuple(s)) for n, s, _ in arch.full_net("panda", "resnet50", {k: v for k, v in ctor.items() if k not in ("depth_root", "joint_bounds")}))
     assert sorted(m.expected_tensors()) == mine
 
 
@@ -50,9 +50,12 @@ def test_unsupported_configs_fail_loudly(lib_built):
     from hrp_b200.model import HoliRobPoseB200
     with pytest.raises(ValueError):
         HoliRobPoseB200("owi535")
-    for k in ("reg_joint_map", "use_rpmg"):
-        with pytest.raises(NotImplementedError):
-            HoliRobPoseB200("panda", {k: True})
+    with pytest.raises(NotImplementedError):
+        HoliRobPoseB200("panda", {"use_rpmg": True})
+    with pytest.raises(NotImplementedError):                                  # full_net.py:377 reads the ResNet trunk's map
+        HoliRobPoseB200("panda", {"reg_joint_map": True, "joint_conv_dim": [64, 64, 64], "backbone_name": "hrnet32"})
+    with pytest.raises(NotImplementedError):
+        HoliRobPoseB200("panda", {"reg_joint_map": True, "joint_conv_dim": [100, 64, 64]})
     with pytest.raises(ValueError, match="not in list"):                      # kps_need_depth.index(reference_keypoint_id), full_net.py:328
         HoliRobPoseB200("panda", {"multi_kp": True, "kps_need_depth": [0, 1]})
     with pytest.raises(NotImplementedError):

@@ -156,8 +156,8 @@ def test_metrics_match_reference(robot):
 
 @pytest.mark.parametrize("name", list(helpers.VARIANT_CASES))
 def test_constructor_variants_match_reference(name):
-    """8f N4: direct_reg_rot + add_fc + multi_kp, and rot_iterative_matmul (full_net.py:107-131, 149-164, 293-330, 395-429),
-    against the reference constructed with those switches."""
+    """8f N4: direct_reg_rot + add_fc + multi_kp, rot_iterative_matmul, and reg_joint_map + HeatmapIntegralJoint
+    (full_net.py:92-131, 149-164, 293-330, 376-429; integral.py:211-251), against the reference constructed with those switches."""
     g = helpers.load_golden("variant_%s.npz" % name)
     wseed, seed, B = (int(v) for v in g["meta"])
     from oracle import model as omodel
@@ -174,4 +174,5 @@ def test_constructor_variants_match_reference(name):
         assert helpers.maxdiff(g["depths"][:, 1:2], g["root_depth"]) == 0.0
     shipped, _ = helpers.oracle_for("panda", "resnet50", wseed)
     base = shipped.forward_dict(img, img, kv, K)
-    assert helpers.maxdiff(base["rot6d"], g["rot6d"]) > 1e-2                       # the switch matters
+    changed = "joint_angles" if name == "jointmap" else "rot6d"
+    assert helpers.maxdiff(base[changed], g[changed]) > 1e-2                        # the switch matters
