@@ -43,7 +43,7 @@ if len(sys.argv) > 3:
     ks = sorted(agg, key=lambda k: -agg[k]["us"])
     json.dump({"dram_bytes_per_step": sum(a["dram"] for a in agg.values()), "l2_bytes_per_step": sum(a["l2"] for a in agg.values()),
                "launches": len(ids), "sum_of_launch_durations_us": round(tot, 3),
-               "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,... --clock-control none over scripts/one_step.py (bf16, batch 64), last forward (2 pre-graph launches + the graph's nodes); cold-cache (ncu flushes caches between launches), serialised launches, each launch at the graph's quarter-GPU cap: compare shares, not absolutes",
+               "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,... --clock-control none over scripts/one_step.py (f16, batch 64), last forward (2 pre-graph launches + the graph's nodes); cold-cache (ncu flushes caches between launches), serialised launches, each launch at the graph's quarter-GPU cap: compare shares, not absolutes",
                "by_kernel_l2_mb": {k: round(agg[k]["l2"] / 1e6, 1) for k in sorted(agg, key=lambda k: -agg[k]["us"])},
                "by_kernel_us": {k: round(agg[k]["us"], 1) for k in ks}, "by_kernel_launches": {k: int(agg[k]["n"]) for k in ks},
                "by_kernel_dram_mb": {k: round(agg[k]["dram"] / 1e6, 1) for k in ks}}, open(sys.argv[3], "w"), indent=1)
