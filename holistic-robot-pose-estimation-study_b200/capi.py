@@ -84,7 +84,7 @@ def lib():
         L.hrp_release_plans.argtypes = [vp]
         L.hrp_forward_u8.argtypes = [vp, f32p, f32p, f32p, f32p, i32, f32p, vp]
         L.hrp_crop_resize_u8.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
-        L.hrp_metrics_batch.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+        L.hrp_metrics_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
         L.hrp_summary_workspace.argtypes = [i64]
         L.hrp_summary_workspace.restype = C.c_size_t
         L.hrp_summary_add_pck.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]

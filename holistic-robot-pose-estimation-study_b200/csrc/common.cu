@@ -30,4 +30,4 @@ int sm_count() {
 }  // namespace hrp
 
 extern "C" const char* hrp_last_error(void) { return hrp::last_error().c_str(); }
-extern "C" const char* hrp_version(void) { return "hrp_b200 0.1 (sm_100a)"; }
+extern "C" const char* hrp_version(void) { return "hrp_b200 0.2 (sm_100a)"; }

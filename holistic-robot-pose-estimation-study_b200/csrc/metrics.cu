@@ -18,16 +18,26 @@ namespace {
 
 constexpr int MB_THREADS = 128;
 
+// predicted pixel of keypoint k of frame b: taken from puv, or (puv == null) projected here with the frame's camera matrix
+// exactly as point_projection_from_3d does (transforms.py:7-15: K @ p, divided by its last component)
+__device__ __forceinline__ void pred_pixel(const float* __restrict__ puv, const float* __restrict__ Kmat, const float* p3, int b, int nk, int k,
+                                           float* u, float* v) {
+  if (puv != nullptr) { *u = puv[((size_t)b * nk + k) * 2]; *v = puv[((size_t)b * nk + k) * 2 + 1]; return; }
+  const float* K = Kmat + (size_t)b * 9;
+  const float x = p3[0], y = p3[1], z = p3[2];
+  const float hx = K[0] * x + K[1] * y + K[2] * z, hy = K[3] * x + K[4] * y + K[5] * z, hz = K[6] * x + K[7] * y + K[8] * z;
+  *u = hx / hz; *v = hy / hz;
+}
+
 // one thread per frame: metrics.py:55-69 (error3d, error2d over in-frame keypoints), 83-94 (joint error), 98-116 (root depth,
 // root-relative depth, root-relative ADD)
-__global__ void metrics_frame_kernel(const float* __restrict__ pxyz, const float* __restrict__ puv, const float* __restrict__ pq,
+__global__ void metrics_frame_kernel(const float* __restrict__ pxyz, const float* __restrict__ puv, const float* __restrict__ Kmat, const float* __restrict__ pq,
                                      const float* __restrict__ gxyz, const float* __restrict__ guv, const float* __restrict__ gq,
                                      int B, int nk, int dof, int root, int joint_cols, float* __restrict__ out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float* p3 = pxyz + (size_t)b * nk * 3;
   const float* g3 = gxyz + (size_t)b * nk * 3;
-  const float* p2 = puv + (size_t)b * nk * 2;
   const float* g2 = guv + (size_t)b * nk * 2;
   const float pzr = p3[root * 3 + 2], gzr = g3[root * 3 + 2];
   float s3 = 0.f, s2 = 0.f, srel = 0.f, s3rel = 0.f;
@@ -35,7 +45,9 @@ __global__ void metrics_frame_kernel(const float* __restrict__ pxyz, const float
   for (int k = 0; k < nk; ++k) {
     const float dx = p3[k * 3] - g3[k * 3], dy = p3[k * 3 + 1] - g3[k * 3 + 1], dz = p3[k * 3 + 2] - g3[k * 3 + 2];
     s3 += sqrtf(dx * dx + dy * dy + dz * dz);
-    const float ux = p2[k * 2] - g2[k * 2], uy = p2[k * 2 + 1] - g2[k * 2 + 1];
+    float pu, pv;
+    pred_pixel(puv, Kmat, p3 + k * 3, b, nk, k, &pu, &pv);
+    const float ux = pu - g2[k * 2], uy = pv - g2[k * 2 + 1];
     const float gx = g2[k * 2], gy = g2[k * 2 + 1];
     const bool valid = gx <= 640.0f && gx >= 0.f && gy <= 480.0f && gy >= 0.f;     // metrics.py:63 (literal frame size)
     if (valid) { s2 += sqrtf(ux * ux + uy * uy); ++nvalid; }
@@ -56,7 +68,7 @@ __global__ void metrics_frame_kernel(const float* __restrict__ pxyz, const float
 }
 
 // one block per column (keypoint 0..nk-1: dis3d, dis2d; joint nk..nk+dof-1: l1_jointerror): batch means, metrics.py:72-76, 86
-__global__ void metrics_column_kernel(const float* __restrict__ pxyz, const float* __restrict__ puv, const float* __restrict__ pq,
+__global__ void metrics_column_kernel(const float* __restrict__ pxyz, const float* __restrict__ puv, const float* __restrict__ Kmat, const float* __restrict__ pq,
                                       const float* __restrict__ gxyz, const float* __restrict__ guv, const float* __restrict__ gq,
                                       int B, int nk, int dof, float* __restrict__ dis3d, float* __restrict__ dis2d,
                                       float* __restrict__ l1joint) {
@@ -69,10 +81,11 @@ __global__ void metrics_column_kernel(const float* __restrict__ pxyz, const floa
       const float* g3 = gxyz + ((size_t)b * nk + c) * 3;
       const float dx = p3[0] - g3[0], dy = p3[1] - g3[1], dz = p3[2] - g3[2];
       a0 += sqrtf(dx * dx + dy * dy + dz * dz);
-      const float* p2 = puv + ((size_t)b * nk + c) * 2;
       const float* g2 = guv + ((size_t)b * nk + c) * 2;
       if (g2[0] <= 640.0f && g2[0] >= 0.f && g2[1] <= 480.0f && g2[1] >= 0.f) {
-        const float ux = p2[0] - g2[0], uy = p2[1] - g2[1];
+        float pu, pv;
+        pred_pixel(puv, Kmat, p3, b, nk, c, &pu, &pv);
+        const float ux = pu - g2[0], uy = pv - g2[1];
         a1 += sqrtf(ux * ux + uy * uy);
         a2 += 1.f;
       }
@@ -191,19 +204,19 @@ __global__ void summary_final_kernel(const double* __restrict__ partial, int blo
 
 using namespace hrp;
 
-extern "C" int hrp_metrics_batch(const float* pred_xyz, const float* pred_uv, const float* pred_joint, const float* gt_xyz,
+extern "C" int hrp_metrics_batch(const float* pred_xyz, const float* pred_uv, const float* K_original, const float* pred_joint, const float* gt_xyz,
                                  const float* gt_uv, const float* gt_joint, int B, int nkpt, int dof, int root_kp, int joint_cols,
                                  float* per_frame, float* dis3d, float* dis2d, float* l1_joint, void* stream) {
   if (B < 0 || nkpt <= 0 || nkpt > HRP_FK_MAX_KP || dof <= 0 || root_kp < 0 || root_kp >= nkpt || joint_cols <= 0 || joint_cols > dof)
     return fail(HRP_ERR_INVALID, "hrp_metrics_batch: bad sizes (B=%d nkpt=%d dof=%d root=%d joint_cols=%d)", B, nkpt, dof, root_kp, joint_cols);
   if (B == 0) return HRP_OK;
-  if (!pred_xyz || !pred_uv || !gt_xyz || !gt_uv || !per_frame || !dis3d || !dis2d || !l1_joint || (pred_joint && !gt_joint))
+  if (!pred_xyz || (!pred_uv && !K_original) || !gt_xyz || !gt_uv || !per_frame || !dis3d || !dis2d || !l1_joint || (pred_joint && !gt_joint))
     return fail(HRP_ERR_INVALID, "hrp_metrics_batch: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  metrics_frame_kernel<<<(B + MB_THREADS - 1) / MB_THREADS, MB_THREADS, 0, st>>>(pred_xyz, pred_uv, pred_joint, gt_xyz, gt_uv, gt_joint, B, nkpt, dof,
+  metrics_frame_kernel<<<(B + MB_THREADS - 1) / MB_THREADS, MB_THREADS, 0, st>>>(pred_xyz, pred_uv, K_original, pred_joint, gt_xyz, gt_uv, gt_joint, B, nkpt, dof,
                                                                                 root_kp, joint_cols, per_frame);
   HRP_CHECK_LAUNCH("metrics_frame_kernel");
-  metrics_column_kernel<<<nkpt + dof, MB_THREADS, 0, st>>>(pred_xyz, pred_uv, pred_joint, gt_xyz, gt_uv, gt_joint, B, nkpt, dof, dis3d, dis2d, l1_joint);
+  metrics_column_kernel<<<nkpt + dof, MB_THREADS, 0, st>>>(pred_xyz, pred_uv, K_original, pred_joint, gt_xyz, gt_uv, gt_joint, B, nkpt, dof, dis3d, dis2d, l1_joint);
   HRP_CHECK_LAUNCH("metrics_column_kernel");
   if (!pred_joint) HRP_CUDA(cudaMemsetAsync(l1_joint, 0, (size_t)dof * 4, st));        // metrics.py:91-92
   return HRP_OK;

@@ -47,8 +47,7 @@ def metrics_batch_device(robot, gt_keypoints3d, gt_keypoints2d, K_original, gt_j
         if pred_xyz_integral is None:
             raise ValueError("either pred_joint / pred_rot / pred_trans or pred_xyz_integral is needed")
         p3 = _f32(pred_xyz_integral, dev, (B, nk, 3))
-        h = torch.einsum("bij,bkj->bki", Ko, p3)                                # point_projection_from_3d on given points
-        p2 = (h[..., :2] / h[..., 2:3]).contiguous()
+        p2 = None                                                               # projected inside the kernels with K_original
         pq = None
     else:
         pq = _f32(pred_joint, dev, (B, dof))
@@ -59,7 +58,8 @@ def metrics_batch_device(robot, gt_keypoints3d, gt_keypoints2d, K_original, gt_j
     l1 = torch.empty(dof, device=dev, dtype=torch.float32)
     joint_cols = dof - 1 if fk.robot_type == "panda" else dof                   # metrics.py:87-90
     st = torch.cuda.current_stream(dev).cuda_stream
-    capi.check(capi.lib().hrp_metrics_batch(_ptr(p3), _ptr(p2), _ptr(pq) if pq is not None else C.c_void_p(0), _ptr(g3), _ptr(g2),
+    null = C.c_void_p(0)
+    capi.check(capi.lib().hrp_metrics_batch(_ptr(p3), _ptr(p2) if p2 is not None else null, _ptr(Ko), _ptr(pq) if pq is not None else null, _ptr(g3), _ptr(g2),
                                             _ptr(gq), B, nk, dof, root, joint_cols, _ptr(per_frame), _ptr(dis3d), _ptr(dis2d),
                                             _ptr(l1), C.c_void_p(st)))
     return per_frame, dis3d, dis2d, l1

@@ -220,12 +220,13 @@ int hrp_crop_resize_u8(const uint8_t* frames, int B, int Hf, int Wf, const int32
 
 /* Evaluation tail on the device, replacing compute_metrics_batch (lib/utils/metrics.py:8-118; callers
  * lib/core/function.py:158-172, scripts/test.py:167-181). pred_xyz [B,nkpt,3] / pred_uv [B,nkpt,2]: the predicted pose through
- * hrp_fk_project with the ORIGINAL camera matrix (metrics.py:29-42); pred_joint [B,dof] or NULL (metrics.py:90-92: zeros);
+ * hrp_fk_project with the ORIGINAL camera matrix (metrics.py:29-42) -- or pred_uv NULL and K_original [B,3,3] given: the points are
+ * projected here (metrics.py:22-26, 42: predictions that are 3-D points, not a pose) --; pred_joint [B,dof] or NULL (metrics.py:90-92: zeros);
  * gt_xyz, gt_uv, gt_joint: ground truth of the batch. joint_cols: columns averaged per frame (dof, Panda dof-1:
  * metrics.py:87-88). Outputs (device): per_frame [B,6] = error3d, error2d (mean over keypoints with gt inside the 640x480 frame;
  * NaN when none is), mean_jointerror, error_depth, batch_error_relative, error3d_relative; dis3d [nkpt], dis2d [nkpt],
  * l1_joint [dof] = the batch means per keypoint / joint. */
-int hrp_metrics_batch(const float* pred_xyz, const float* pred_uv, const float* pred_joint, const float* gt_xyz,
+int hrp_metrics_batch(const float* pred_xyz, const float* pred_uv, const float* K_original, const float* pred_joint, const float* gt_xyz,
                       const float* gt_uv, const float* gt_joint, int B, int nkpt, int dof, int root_kp, int joint_cols,
                       float* per_frame, float* dis3d, float* dis2d, float* l1_joint, void* stream);
 
