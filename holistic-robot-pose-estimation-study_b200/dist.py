@@ -20,29 +20,32 @@ def shard_range(total, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def field_widths(dof, nkpt):
-    return (dof, 6, 3, 2, 1, nkpt * 3, nkpt * 3, nkpt * 3, nkpt * 2, nkpt * 2)
+def field_widths(dof, nkpt, depth_num=0):
+    """Floats per frame of every field of the output record (HRP_F_*); depth_num > 0: the multi_kp variant's HRP_F_DEPTHS."""
+    return (dof, 6, 3, 2, 1, nkpt * 3, nkpt * 3, nkpt * 3, nkpt * 2, nkpt * 2, depth_num)
 
 
-def record_offsets(batch, dof, nkpt):
+def record_offsets(batch, dof, nkpt, depth_num=0):
     """Mirror of hrp_output_offsets: struct-of-arrays record, every field 16-byte aligned."""
     offs, o = [], 0
-    for w in field_widths(dof, nkpt):
+    for w in field_widths(dof, nkpt, depth_num):
         offs.append(o)
         o = (o + batch * w + 3) & ~3
     offs.append(o)
     return offs
 
 
-def gather_records(rec, batch, dof, nkpt, group=None):
-    """All-gather equal-sized per-rank records and re-assemble global per-field tensors {name: [G*batch, ...]}."""
+def gather_records(rec, batch, dof, nkpt, group=None, depth_num=0):
+    """All-gather equal-sized per-rank records and re-assemble global per-field tensors {name: [G*batch, ...]}
+    (depth_num > 0: models built with multi_kp, whose record carries every regressed depth as `depths`)."""
     world = dist.get_world_size(group)
     out = torch.empty(world * rec.numel(), dtype=rec.dtype, device=rec.device)
     dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
     out = out.view(world, rec.numel())
-    offs = record_offsets(batch, dof, nkpt)
+    offs = record_offsets(batch, dof, nkpt, depth_num)
     res = {}
-    for f, (name, w) in enumerate(zip(capi.FIELD_NAMES, field_widths(dof, nkpt))):
+    names = tuple(capi.FIELD_NAMES) + (("depths",) if depth_num > 0 else ())
+    for f, (name, w) in enumerate(zip(names, field_widths(dof, nkpt, depth_num))):
         t = out[:, offs[f]:offs[f] + batch * w].reshape(world * batch, w)
         if f in (5, 6, 7):
             t = t.view(world * batch, nkpt, 3)

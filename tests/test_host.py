@@ -152,6 +152,14 @@ def _gloo_worker(rank, world, port, q):
     for r in range(world):
         ok = ok and float(out["trans"][r * B, 0]) == 2000 + 100000 * r
         ok = ok and float(out["kp3d_fk"][r * B + 1, 0, 0]) == 7000 + nkpt * 3 + 100000 * r
+    # the multi_kp variant's record carries one more field (every regressed depth)
+    offs = hd.record_offsets(B, dof, nkpt, depth_num=3)
+    rec = torch.zeros(offs[-1])
+    for f, w in enumerate(hd.field_widths(dof, nkpt, 3)):
+        rec[offs[f]:offs[f] + B * w] = torch.arange(B * w, dtype=torch.float32) + 1000 * f + 100000 * rank
+    out = hd.gather_records(rec, B, dof, nkpt, depth_num=3)
+    ok = ok and out["depths"].shape == (world * B, 3) and float(out["depths"][B, 1]) == 10001 + 100000 * 1
+    ok = ok and float(out["kp2d_fk"][B, 0, 0]) == 9000 + 100000 * 1
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
