@@ -144,6 +144,9 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="frames per GPU per step")
     ap.add_argument("--robot", default=ROBOT, choices=["panda", "kuka", "baxter"],
                     help="panda = the headline workload (BASELINE configs[1]); kuka / baxter with --batch 256 / 128 are configs[2] / [3]")
+    ap.add_argument("--gather", default=os.environ.get("HRP_GATHER", "nccl"), choices=["nccl", "p2p"],
+                    help="N > 1: output gather through NCCL (default; faster at 8 ranks, profiles/r02_p2p_gather_vs_nccl.jsonl) or as stores into "
+                         "the peers' HBM windows (hrp_p2p_all_gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-families", action="store_true", help="skip the tf32 / fp32 family lines")
     args = ap.parse_args()
@@ -215,9 +218,14 @@ def main():
     n_side = int(os.environ.get("HRP_SLOTS", "4"))
     state_dict = synth.make_state_dict(ROBOT, args.backbone, WEIGHT_SEED)
 
+    peer = None
+
     def gathered(rec):
+        nonlocal peer
         if world > 1:
-            hdist.gather_records(rec, B, spec["dof"], spec["nkpt"])
+            if args.gather == "p2p" and peer is None:
+                peer = hdist.PeerGather(rec.numel(), dev)
+            hdist.gather_records(rec, B, spec["dof"], spec["nkpt"], peer=peer)
         return rec
 
     def measure(model, steps, warm, sampler=None):
@@ -396,7 +404,7 @@ def main():
                            "batch_per_gpu": B, "global_batch": B * world, "gflop_per_frame": flops_frame / 1e9,
                            "l2": "inputs rotate over %d distinct batches (%d MB > L2); the %.1f GB activation workspace is rewritten every step" % (
                                NSETS, NSETS * B * 3 * 256 * 256 * 4 // 2 ** 20, ws_gb),
-                           "parallelism": "batch-sharded x%d, NCCL all-gather of output records" % world if world > 1 else "single GPU",
+                           "parallelism": ("batch-sharded x%d, %s of output records" % (world, "NCCL all-gather" if args.gather == "nccl" else "peer-memory all-gather (P2P stores)")) if world > 1 else "single GPU",
                            "pipelining": "consecutive steps are enqueued round-robin on %d streams (the library keeps one plan per stream), so the tail of step i overlaps the head of step i+1; every step is a complete forward of its own batch" % n_side,
                            "weights": "calibrated random init, seed %d" % WEIGHT_SEED},
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (3 * 256 * 256 + (9 + 1) * 4),

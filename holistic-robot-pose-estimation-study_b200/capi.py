@@ -20,6 +20,7 @@ EXPORTS = (
     "hrp_set_weight", "hrp_finalize_weights", "hrp_output_offsets", "hrp_workspace_bytes", "hrp_forward", "hrp_forward_ex",
     "hrp_forward_timed", "hrp_release_plans", "hrp_forward_u8", "hrp_crop_resize_u8",
     "hrp_metrics_batch", "hrp_summary_workspace", "hrp_summary_add_pck",
+    "hrp_p2p_create", "hrp_p2p_handle", "hrp_p2p_connect", "hrp_p2p_all_gather", "hrp_p2p_status", "hrp_p2p_destroy",
     "hrp_set_option", "hrp_launch_count", "hrp_debug_tensor", "hrp_forward_profile", "hrp_conv_bench", "hrp_last_error",
     "hrp_version",
 )
@@ -88,6 +89,13 @@ def lib():
         L.hrp_summary_workspace.argtypes = [i64]
         L.hrp_summary_workspace.restype = C.c_size_t
         L.hrp_summary_add_pck.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
+        L.hrp_p2p_create.argtypes = [i32, i32, C.c_size_t, i32, C.POINTER(vp)]
+        L.hrp_p2p_handle.argtypes = [vp, vp]
+        L.hrp_p2p_connect.argtypes = [vp, vp]
+        L.hrp_p2p_all_gather.argtypes = [vp, vp, C.c_size_t, vp, vp]
+        L.hrp_p2p_status.argtypes = [vp]
+        L.hrp_p2p_destroy.argtypes = [vp]
+        L.hrp_p2p_destroy.restype = None
         L.hrp_set_option.argtypes = [vp, C.c_char_p, i64]
         L.hrp_launch_count.argtypes = [vp]
         L.hrp_launch_count.restype = i64

@@ -35,13 +35,74 @@ def record_offsets(batch, dof, nkpt, depth_num=0):
     return offs
 
 
-def gather_records(rec, batch, dof, nkpt, group=None, depth_num=0):
+class PeerGather:
+    """All-gather of equal-sized fp32 records over peer memory (csrc/p2p_gather.cu): every rank stores its record straight into
+    windows its peers exposed through CUDA IPC. One instance per (record size, process group); the IPC handles are exchanged
+    once, here, with a torch.distributed all_gather. Every rank must call `all_gather` in the same order."""
+
+    def __init__(self, numel, device, group=None):
+        import ctypes as C
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.numel = int(numel)
+        self.padded = (self.numel * 4 + 15) // 16 * 4                  # floats per rank, record rounded up to 16 bytes
+        self.device = torch.device(device)
+        h = C.c_void_p()
+        capi.check(capi.lib().hrp_p2p_create(self.rank, self.world, self.padded * 4, self.device.index, C.byref(h)))
+        self._h = h
+        mine = (C.c_uint8 * 64)()
+        capi.check(capi.lib().hrp_p2p_handle(self._h, mine))
+        backend = dist.get_backend(group)
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device if backend == "nccl" else "cpu")
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(allh, t, group=group)
+        buf = (C.c_uint8 * (self.world * 64))(*allh.cpu().tolist())
+        capi.check(capi.lib().hrp_p2p_connect(self._h, buf))
+        dist.barrier(group)                                            # every window is mapped before the first store
+
+    def all_gather(self, rec):
+        """rec: CUDA fp32 [numel] -> [world, numel] on the current stream."""
+        import ctypes as C
+        if rec.numel() != self.numel or rec.dtype != torch.float32 or not rec.is_cuda:
+            raise ValueError("PeerGather.all_gather: expected a CUDA fp32 record of %d elements" % self.numel)
+        src = rec.contiguous()
+        if self.padded != self.numel or src.data_ptr() % 16:
+            pad = torch.zeros(self.padded, dtype=torch.float32, device=rec.device)
+            pad[:self.numel] = src
+            src = pad
+        out = torch.empty(self.world, self.padded, dtype=torch.float32, device=rec.device)
+        st = torch.cuda.current_stream(rec.device).cuda_stream
+        capi.check(capi.lib().hrp_p2p_all_gather(self._h, C.c_void_p(src.data_ptr()), self.padded * 4, C.c_void_p(out.data_ptr()), C.c_void_p(st)))
+        src.record_stream(torch.cuda.current_stream(rec.device))
+        return out[:, :self.numel]
+
+    def check(self):
+        """Synchronises; raises if a peer timed out in any gather so far."""
+        capi.check(capi.lib().hrp_p2p_status(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().hrp_p2p_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
+
+
+def gather_records(rec, batch, dof, nkpt, group=None, depth_num=0, peer=None):
     """All-gather equal-sized per-rank records and re-assemble global per-field tensors {name: [G*batch, ...]}
-    (depth_num > 0: models built with multi_kp, whose record carries every regressed depth as `depths`)."""
+    (depth_num > 0: models built with multi_kp, whose record carries every regressed depth as `depths`). peer: a PeerGather
+    for this record size -- the gather then runs as P2P stores over NVLink instead of an NCCL all-gather."""
     world = dist.get_world_size(group)
-    out = torch.empty(world * rec.numel(), dtype=rec.dtype, device=rec.device)
-    dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
-    out = out.view(world, rec.numel())
+    if peer is not None:                              # stores into the peers' windows over NVLink (PeerGather) instead of NCCL
+        out = peer.all_gather(rec)
+    else:
+        out = torch.empty(world * rec.numel(), dtype=rec.dtype, device=rec.device)
+        dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+        out = out.view(world, rec.numel())
     offs = record_offsets(batch, dof, nkpt, depth_num)
     res = {}
     names = tuple(capi.FIELD_NAMES) + (("depths",) if depth_num > 0 else ())

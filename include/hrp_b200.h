@@ -238,6 +238,23 @@ size_t hrp_summary_workspace(int64_t N);
 int hrp_summary_add_pck(const float* dis3d, const float* dis2d, int64_t N, double* out22, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* ---- output gather over peer memory (one box, one process per GPU) ---------------------------------------------
+ * The path's only exchange step: every rank's packed output record to every rank (the reference's counterpart is
+ * nn.DataParallel's gather, scripts/test.py:159). Each rank owns a window in its HBM that the peers map through CUDA IPC; an
+ * all-gather is two kernels on the caller's stream that store the record straight into the peers' windows over NVLink and
+ * copy the arrived records out -- no NCCL call, no host synchronisation (csrc/p2p_gather.cu).
+ * hrp_p2p_create (allocates the window for records of bytes_per_rank, rounded up to 16) -> hrp_p2p_handle (64 bytes to hand to
+ * every peer, e.g. with one torch.distributed all_gather at start-up) -> hrp_p2p_connect (all handles, rank order) ->
+ * hrp_p2p_all_gather (src: this rank's record, dst: world x bytes, both device, 16-byte aligned; every rank must call it the
+ * same number of times in the same order) -> hrp_p2p_status (synchronises; HRP_ERR_STATE if a peer timed out). */
+typedef struct hrp_p2p hrp_p2p;
+int hrp_p2p_create(int rank, int world, size_t bytes_per_rank, int device, hrp_p2p** out);
+int hrp_p2p_handle(hrp_p2p* g, void* handle64);
+int hrp_p2p_connect(hrp_p2p* g, const void* handles);
+int hrp_p2p_all_gather(hrp_p2p* g, const void* src, size_t bytes, void* dst, void* stream);
+int hrp_p2p_status(hrp_p2p* g);
+void hrp_p2p_destroy(hrp_p2p* g);
+
 /* Plans (workspace + CUDA graph) are cached per batch size: at most "max_cached_batches" distinct sizes (default 4, least
  * recently used dropped first), and a second / third plan of a size only when forwards of that size arrive on different
  * streams. hrp_release_plans frees every cached plan now (waits for the forwards that use them); the next forward

@@ -922,3 +922,26 @@ def test_constructor_variants_against_reference_golden(name, prec, dev):
             assert helpers.maxdiff(iters[:, n, model.dof:], trace["rot_iters"][n]) < t_rad * 2
             R = iters[:, n, model.dof:].reshape(5, 2, 3)
             assert float((R.norm(dim=2) - 1).abs().max()) < 1e-5 and float((R[:, 0] * R[:, 1]).sum(1).abs().max()) < 1e-5
+
+
+@pytest.mark.gpu
+def test_peer_memory_gather_single_rank(dev):
+    """hrp_p2p_* with a world of one (the multi-rank protocol is exercised by scripts/p2p_gather_test.py under torchrun: 64
+    overlapping steps on 2 and 8 GPUs bit-equal to NCCL's all-gather, profiles/r02_p2p_gather_vs_nccl.jsonl)."""
+    import ctypes as C
+    from hrp_b200 import capi
+    L = capi.lib()
+    h = C.c_void_p()
+    n = 7101                                                        # not a multiple of four floats: the window rounds up to 16 bytes
+    padded = (n * 4 + 15) // 16 * 4
+    capi.check(L.hrp_p2p_create(0, 1, n * 4, dev.index, C.byref(h)))
+    src = torch.zeros(padded, device=dev)
+    out = torch.empty(padded, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for step in range(5):
+        src[:n] = torch.arange(n, device=dev, dtype=torch.float32) + step
+        capi.check(L.hrp_p2p_all_gather(h, C.c_void_p(src.data_ptr()), padded * 4, C.c_void_p(out.data_ptr()), st))
+        assert torch.equal(out[:n], src[:n])
+    capi.check(L.hrp_p2p_status(h))
+    assert L.hrp_p2p_all_gather(h, C.c_void_p(src.data_ptr()), 64, C.c_void_p(out.data_ptr()), st) == -1          # HRP_ERR_INVALID: not the window's record size
+    L.hrp_p2p_destroy(h)
