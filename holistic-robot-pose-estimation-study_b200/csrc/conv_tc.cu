@@ -58,6 +58,8 @@ struct TcParams {
   int epi_tma;       // 1: the epilogue stages the tile in swizzled shared memory and moves it with TMA (residual in, result out)
   int chunk_bytes;   // epi_tma: bytes of one staged row chunk (128, or 64 when block_n*elem == 64)
   int n_chunks;      // epi_tma: block_n*elem / chunk_bytes
+  int epi_dual;      // epi_tma, TMA operand loads, EPI == 4, two staging buffers: warps 0-3 are a second epilogue group (odd tiles)
+  int epi_wide;      // epi_tma, 2-byte families: drain 32 columns per tcgen05.ld with the residual / bias loads in flight before the wait
   int res_prefetch;  // epi_tma, two staging buffers: request the residual of tile li+1 at the end of tile li
   int n_stg;         // epi_tma: staging buffers (2 when shared memory allows: the store of tile i overlaps tile i+1)
   ConvArgs a;
@@ -181,7 +183,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   if (p.pdl_early) pdl_trigger();
   if (warp != 4) pdl_wait();      // every warp that touches global memory (the MMA warp only reads shared memory / TMEM)
 
-  if (warp < 4) {
+  // TMA mode leaves warps 0-3 without a role (no gather, no 3xTF32 split); with the TMA epilogue and two staging buffers they
+  // become a SECOND EPILOGUE GROUP (p.epi_dual): group g drains accumulator buffer g into staging buffer g, i.e. the CTA's
+  // even / odd tiles, each group with its own named barrier and its own storing thread. The drain is a chain of
+  // fixed-latency instructions of in-order warps (ncu: issue slots 28 % busy, every epilogue warp ~80 % of its time inside
+  // the drain), so twice the warps per SM is what raises the rate; shared memory, TMEM and registers stay as they are.
+  const bool dual = p.epi_dual != 0;
+  if (warp < 4 && !dual) {
     if (!p.tma) {
     // ===== producers: im2col gather. One warp instruction covers 4 tile rows x 128 contiguous bytes (lane = 8*row + chunk),
     // so every request touches 4 cache lines instead of 32; a thread serves chunk `j` of 8 rows of its warp's 32.
@@ -355,7 +363,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     // ===== epilogue warps 6..: TMEM -> registers -> (+bias, +residual, ReLU) -> global ================================
     // a warp may only touch TMEM lanes 32*(warp%4)..+31; thread (et, eh) owns tile row `et`, column half `eh`
     constexpr int EPI_T = 32 * EPI, EPI_H = EPI / 4;
-    const int et = (warp & 3) * 32 + lane, eh = (warp - 6) >> 2, eid = eh * 128 + et;
+    const int grp = (dual && warp < 4) ? 1 : 0;                        // dual mode (EPI == 4): warps 6-9 = group 0, warps 0-3 = group 1
+    const int et = (warp & 3) * 32 + lane, eh = dual ? 0 : (warp - 6) >> 2, eid = eh * 128 + et;
+    const int tile_inc = dual ? 2 : 1;
+    auto epi_bar = [&]() {
+      if (dual) asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      else epi_barrier<EPI>();
+    };
     const int c_lo = (p.block_n / EPI_H) * eh, c_hi = c_lo + p.block_n / EPI_H;   // block_n / EPI_H is a multiple of 16 (block_n >= 32)
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t pitch = (uint32_t)p.block_n * ESZ + 16u;            // odd multiple of 16 B: conflict-free both ways
@@ -370,17 +384,26 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + i);
       asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_bias + 16u * (uint32_t)i), "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w) : "memory");
     }
-    epi_barrier<EPI>();
-    int li = 0;
-    for (int u = unit0; u < p.total_units; u += unit_step, ++li) {
+    epi_bar();
+    int li = grp;
+    for (int u = unit0 + grp * unit_step; u < p.total_units; u += tile_inc * unit_step, li += tile_inc) {
       const int buf = li & 1;
       const int m0 = HRP_TILE_M(u) * TC_BLOCK_M, n0 = HRP_TILE_N(u) * p.block_n;
-      const int m = m0 + et;
-      const bool row_ok = m < p.M;
-      const int mm = row_ok ? m : 0;
-      const int ox = mm % a.Wo, t1 = mm / a.Wo, oy = t1 % a.Ho, b = t1 / a.Ho;
-      const int y = oy * a.out_sy + a.out_oy, x = ox * a.out_sx + a.out_ox;
-      const size_t pix = ((size_t)b * a.Ho_full + y) * a.Wo_full + x;
+      // the row's pixel coordinates: three integer divisions per tile that only the register / cp.async epilogues need (the TMA
+      // epilogue addresses the [M][Cout] matrix by m0 / n0 alone; they were 16 % of its instructions)
+      bool row_ok = true;
+      int ox = 0, oy = 0, b = 0, y = 0, x = 0;
+      size_t pix = 0;
+      if (!p.epi_tma || a.sa_partial != nullptr || a.out_nchw) {
+        const int m = m0 + et;
+        row_ok = m < p.M;
+        const int mm = row_ok ? m : 0;
+        ox = mm % a.Wo;
+        const int t1 = mm / a.Wo;
+        oy = t1 % a.Ho; b = t1 / a.Ho;
+        y = oy * a.out_sy + a.out_oy; x = ox * a.out_sx + a.out_ox;
+        pix = ((size_t)b * a.Ho_full + y) * a.Wo_full + x;
+      }
       const uint32_t t_row = t_lane + (uint32_t)(buf * p.block_n);
       if (a.sa_partial != nullptr) {
         // The heatmap head without the heatmap: this tile is 128 pixels x the 64 depth bins of ONE keypoint. Every thread
@@ -415,12 +438,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) { SaState o = sa_shfl_xor(st, off); sa_merge(st, o); }
-        const uint32_t sa_smem = s_rowoff;                         // 4 warps x 5 floats (the row-offset table is idle in this mode)
+        const uint32_t sa_smem = s_rowoff + 256u * (uint32_t)grp;  // 4 warps x 5 floats per epilogue group (the row-offset table is idle in this mode)
         if (lane == 0) {
           asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sa_smem + 32u * (uint32_t)(warp & 3)), "f"(st.m), "f"(st.l), "f"(st.sx), "f"(st.sy) : "memory");
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa_smem + 32u * (uint32_t)(warp & 3) + 16u), "f"(st.sz) : "memory");
         }
-        epi_barrier<EPI>();
+        epi_bar();
         if (eid == 0) {
           mbar_arrive(bar_acce + 8u * buf);
           SaState t{-INFINITY, 0.f, 0.f, 0.f, 0.f};
@@ -435,7 +458,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           float* dst = a.sa_partial + ((size_t)(bb * (a.Cout >> 6) + kp) * chunks + tile_in_img) * 5;
           dst[0] = t.m; dst[1] = t.l; dst[2] = t.sx; dst[3] = t.sy; dst[4] = t.sz;
         }
-        epi_barrier<EPI>();                                        // the shared-memory hop is reused by the next tile
+        epi_bar();                                        // the shared-memory hop is reused by the next tile
         continue;
       }
       if (a.out_nchw) {
@@ -461,7 +484,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           }
         }
         tc_fence_before();
-        epi_barrier<EPI>();
+        epi_bar();
         if (eid == 0) mbar_arrive(bar_acce + 8u * buf);
         continue;
       }
@@ -482,7 +505,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const bool prefetch = has_res && p.res_prefetch != 0;
         const bool early = prefetch && p.res_prefetch == 2;
         if (eid == 0) {                                        // the store that last read this buffer has finished reading
-          if (p.n_stg == 2 && !early) bulk_wait_read1(); else bulk_wait_read0();
+          // (dual mode: a group's storing thread has only its own stores in flight, all from this one buffer)
+          if (p.n_stg == 2 && !early && !dual) bulk_wait_read1(); else bulk_wait_read0();
           if (has_res && (!prefetch || li == 0)) {
             mbar_arrive_expect_tx(bar_res, (uint32_t)p.n_chunks * chunk_sz);
             for (int k = 0; k < p.n_chunks; ++k)
@@ -498,11 +522,84 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               tma_load_2d(stg1 + (uint32_t)k * chunk_sz, p.tmap_res, a.out_coff + n1 + k * (int)(cbytes / ESZ), m1, bar1);
           }
         }
-        epi_barrier<EPI>();
+        epi_bar();
         mbar_wait(bar_accf + 8u * buf, (li >> 1) & 1);
         tc_fence_after();
         if (has_res) mbar_wait(bar_res, p.n_stg == 2 ? ((li >> 1) & 1) : (li & 1));
-        for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+        bool drained = false;
+        if constexpr (!TF32) {
+          // 2-byte families, 32 columns per TMEM load: the drain is a chain of latencies for an in-order warp (tcgen05.ld,
+          // the bias vector, one residual load per 16-byte unit, each waited for in turn: ~250 clk per 16 columns for ~90
+          // issue slots). Here one tcgen05.ld.x32, the four residual units and the first half of the bias are all in
+          // flight before the single wait, and there are half as many round trips. Same arithmetic per element.
+          if (p.epi_wide) {
+            drained = true;
+            const uint32_t cb_log = cbytes == 128 ? 7u : 6u;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+              uint32_t v[32];
+              tmem_ld32(t_row + (uint32_t)c0, v);
+              const uint32_t byte0 = (uint32_t)c0 * 2u, ck = byte0 >> cb_log, u0 = (byte0 & (cbytes - 1u)) >> 4;
+              const uint32_t rowp = tile_stg + ck * chunk_sz + (uint32_t)et * cbytes;
+              uint32_t addr[4], w[4][4];
+#pragma unroll
+              for (int uu = 0; uu < 4; ++uu) addr[uu] = rowp + (((u0 + (uint32_t)uu) ^ swz) << 4);
+              if (has_res) {
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu)
+                  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[uu][0]), "=r"(w[uu][1]), "=r"(w[uu][2]), "=r"(w[uu][3]) : "r"(addr[uu]));
+              }
+              const uint32_t bp = s_bias + 4u * (uint32_t)(n0 + c0);
+              float4 bq[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) bq[q] = lds_f4(bp + 16u * (uint32_t)q);
+              tmem_ld_wait();
+              float f[32];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                f[q * 4 + 0] = __uint_as_float(v[q * 4 + 0]) + bq[q].x; f[q * 4 + 1] = __uint_as_float(v[q * 4 + 1]) + bq[q].y;
+                f[q * 4 + 2] = __uint_as_float(v[q * 4 + 2]) + bq[q].z; f[q * 4 + 3] = __uint_as_float(v[q * 4 + 3]) + bq[q].w;
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) bq[q] = lds_f4(bp + 64u + 16u * (uint32_t)q);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                f[16 + q * 4 + 0] = __uint_as_float(v[16 + q * 4 + 0]) + bq[q].x; f[16 + q * 4 + 1] = __uint_as_float(v[16 + q * 4 + 1]) + bq[q].y;
+                f[16 + q * 4 + 2] = __uint_as_float(v[16 + q * 4 + 2]) + bq[q].z; f[16 + q * 4 + 3] = __uint_as_float(v[16 + q * 4 + 3]) + bq[q].w;
+              }
+#pragma unroll
+              for (int uu = 0; uu < 4; ++uu) {
+                float* ff = f + uu * 8;
+                if (has_res) {
+                  float r[8];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 t2 = unpack2<F16>(w[uu][e]);
+                    r[2 * e] = t2.x; r[2 * e + 1] = t2.y;
+                  }
+                  if (!a.res_after_act) {                        // uniform branches, not per-element predicates
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ff[e] += r[e];
+                    if (a.relu) {
+#pragma unroll
+                      for (int e = 0; e < 8; ++e) ff[e] = fmaxf(ff[e], 0.f);
+                    }
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ff[e] = (a.relu ? fmaxf(ff[e], 0.f) : ff[e]) + r[e];
+                  }
+                } else if (a.relu) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) ff[e] = fmaxf(ff[e], 0.f);
+                }
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = pack2<F16>(ff[2 * e], ff[2 * e + 1]);
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr[uu]), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+              }
+            }
+          }
+        }
+        for (int c0 = c_lo; c0 < c_hi && !drained; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(t_row + (uint32_t)c0, v);
           tmem_ld_wait();
@@ -565,7 +662,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         }
         fence_proxy_async();                                   // generic-proxy writes -> visible to the TMA store
         tc_fence_before();
-        epi_barrier<EPI>();
+        epi_bar();
         if (eid == 0) {
           mbar_arrive(bar_acce + 8u * buf);                    // accumulator buffer may be overwritten by tile li+2
           for (int k = 0; k < p.n_chunks; ++k)
@@ -590,7 +687,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const long long off = row_ok ? (long long)(pix * a.ld_out + a.out_coff + n0) : -1ll;
         asm volatile("st.shared.b64 [%0], %1;" ::"r"(s_rowoff + 8u * et), "l"(off) : "memory");
       }
-      epi_barrier<EPI>();
+      epi_bar();
       if (has_res) {
         const uint8_t* res8 = static_cast<const uint8_t*>(a.res);
         for (uint32_t idx = eid; idx < (128u << cpr_log); idx += EPI_T) {
@@ -601,7 +698,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         }
         cp_async_commit();
         cp_async_wait<0>();
-        epi_barrier<EPI>();
+        epi_bar();
       }
       mbar_wait(bar_accf + 8u * buf, (li >> 1) & 1);
       tc_fence_after();
@@ -666,7 +763,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         }
       }
       tc_fence_before();
-      epi_barrier<EPI>();
+      epi_bar();
       if (eid == 0) mbar_arrive(bar_acce + 8u * buf);         // accumulator buffer may be overwritten by tile li+2
       uint8_t* out8 = static_cast<uint8_t*>(a.out);
       for (uint32_t idx = eid; idx < (128u << cpr_log); idx += EPI_T) {
@@ -679,7 +776,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           *reinterpret_cast<uint4*>(out8 + (size_t)off * ESZ + (ch << 4)) = t;
         }
       }
-      epi_barrier<EPI>();                                           // staging tile and row offsets are reused by the next tile
+      epi_bar();                                           // staging tile and row offsets are reused by the next tile
     }
     // the storing thread: its TMA stores have finished READING shared memory (the writes themselves are ordered before
     // the end of the grid like any other store; waiting for their completion here would only lengthen every CTA's tail)
@@ -841,6 +938,19 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   // (measured: 64->256 @64x64 with residual 81 -> 75 us, without 60 -> 47 us)
   const bool short_k = p.Ktot <= 128 && bn > 128 && a.Cout % 128 == 0 && a.sa_partial == nullptr;
   if (short_k) bn = 128;
+  // Epilogue-heavy layers in general (K <= 256 and 128 columns or more per tile; 2-byte families): the drain of a tile is a
+  // latency chain of in-order warps, so what counts is how many tiles an SM drains at once. Two co-resident CTAs with 128-wide
+  // tiles and four epilogue warps each (eight with the second epilogue group, epi_dual) beat one CTA with eight warps on one
+  // 128- or 256-wide tile wherever there are enough tiles for two CTAs per SM (quarter-GPU cap, batch 64: 32->128 @64x64 with
+  // residual 129 -> 100 us, 256->128 @64x64 104 -> 80 us, 256->1024 @16x16 with residual 67 -> 52 us, 512->2048 @8x8 with
+  // residual 44 -> 32 us; profiles/r02_epilogue_groups.txt). HRP_TC_EPI_HEAVY=0 restores the old choice.
+  static const int epi_heavy_on = env_int("HRP_TC_EPI_HEAVY", 1);
+  bool epi_heavy = false;
+  if (epi_heavy_on && !tf32 && !x3 && a.sa_partial == nullptr && !a.out_nchw && a.Cout % 128 == 0 && bn >= 128 &&
+      (p.Ktot <= 256 || (p.Ktot <= 512 && a.res != nullptr && a.KH == 1)) && (long long)mtiles * (a.Cout / 128) >= 2LL * sms) {
+    epi_heavy = true;
+    bn = 128;
+  }
   if (a.sa_partial != nullptr) {
     if (a.Cout % 64 || (a.Ho * a.Wo) % TC_BLOCK_M || a.out_sy != 1 || a.out_sx != 1 || a.Ho_full != a.Ho || a.Wo_full != a.Wo || a.res != nullptr)
       return fail(HRP_ERR_INVALID, "conv_tc: fused soft-argmax needs Cout %% 64 == 0 and whole 128-pixel tiles per frame (Cout=%d, %dx%d)", a.Cout, a.Ho, a.Wo);
@@ -855,7 +965,7 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   p.tmem_cols = tm;
   // epilogue-heavy tiles (wide N, short K) get eight epilogue warps and the SM to themselves
   static const int force_epi = env_int("HRP_TC_EPI", 0);
-  int epi = (bn >= 128 && p.Ktot <= 256 && !short_k) ? 8 : 4;
+  int epi = (bn >= 128 && p.Ktot <= 256 && !short_k && !epi_heavy) ? 8 : 4;
   if (force_epi == 4 || force_epi == 8) epi = force_epi;
   if (a.sa_partial != nullptr) epi = 4;
   static const int ctas_share = env_int("HRP_TC_CTAS_SHARE", 0);
@@ -877,12 +987,23 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     // anyway) trade operand stages for the second buffer, which lets the residual of tile li+1 load during tile li and
     // the store of tile li drain under tile li+1 (64->256 @64x64: 78 -> 70.5 us with residual, 46.8 -> 39.1 us without).
     static const int no_short_stg = env_int("HRP_TC_NO_SHORT_STG2", 0);
-    const int min_stages = (short_k && !no_short_stg) ? 1 : 3;
+    // (epilogue-heavy layers with one or two k-blocks per tile likewise; with more k-blocks a single stage would serialise
+    // every load with its MMAs, so those keep two stages and one staging buffer)
+    const int min_stages = ((short_k || (epi_heavy && p.num_kb <= 2)) && !no_short_stg) ? 1 : 3;
     p.n_stg = (2048 + 2 * one + tc_tail_bytes() + (size_t)a.Cout * 4 + min_stages * opnd * tc_stage_bytes(bn, p.row_bytes) <= budget) ? 2 : 1;
     staging = (p.n_stg * one + 1023) / 1024 * 1024;
     static const int no_prefetch = env_int("HRP_TC_NO_RES_PREFETCH", 0);
     static const int early = env_int("HRP_TC_RES_EARLY", 1);
     p.res_prefetch = (p.n_stg == 2 && a.res != nullptr && !no_prefetch) ? (early ? 2 : 1) : 0;
+    static const int epi_dual = env_int("HRP_TC_EPI_DUAL", 1);
+    p.epi_dual = (epi_dual && epi == 4 && p.tma && !x3 && p.n_stg == 2 && a.sa_partial == nullptr && !a.out_nchw) ? 1 : 0;
+    if (p.epi_dual) p.res_prefetch = 0;                       // one staging buffer per group: the residual is requested when the tile starts
+    static const int epi_wide = env_int("HRP_TC_EPI_WIDE", 1);
+    p.epi_wide = (epi_wide && !tf32 && (bn / (epi / 4)) % 32 == 0) ? 1 : 0;
+  }
+  if (a.sa_partial != nullptr) {                              // the fused heatmap head: 64 exponentials per thread and tile, no staging at all
+    static const int sa_dual = env_int("HRP_TC_SA_DUAL", 1);
+    p.epi_dual = (sa_dual && epi == 4 && p.tma && !x3) ? 1 : 0;
   }
   const size_t fixed = 2048 + staging + tc_tail_bytes() + (size_t)a.Cout * 4;
   int smax = (int)((budget - fixed) / (opnd * tc_stage_bytes(bn, p.row_bytes)));
