@@ -58,6 +58,8 @@ struct TcParams {
   int epi_tma;       // 1: the epilogue stages the tile in swizzled shared memory and moves it with TMA (residual in, result out)
   int chunk_bytes;   // epi_tma: bytes of one staged row chunk (128, or 64 when block_n*elem == 64)
   int n_chunks;      // epi_tma: block_n*elem / chunk_bytes
+  int a_res;         // activation-resident walk (1x1, TMA mode, one CTA = whole M tiles): the num_kb activation k-blocks of an M tile are loaded
+                     // ONCE into the A halves of stages 0..num_kb-1 and every N tile of that M tile multiplies them; the ring carries weights only
   int epi_dual;      // epi_tma, TMA operand loads, EPI == 4, two staging buffers: warps 0-3 are a second epilogue group (odd tiles)
   int epi_wide;      // epi_tma, 2-byte families: drain 32 columns per tcgen05.ld with the residual / bias loads in flight before the wait
   int res_prefetch;  // epi_tma, two staging buffers: request the residual of tile li+1 at the end of tile li
@@ -158,7 +160,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   // M tile group*cluster + r. Without clusters a unit is a tile and a "cluster" is one CTA.
   const int CS = p.cluster;
   const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
-  const int unit0 = (int)blockIdx.x / CS, unit_step = (int)gridDim.x / CS;
+  // activation-resident walk: a CTA takes whole M tiles (blockIdx.x, + gridDim.x, ...) and visits their N tiles in turn; in unit
+  // numbering (u = m * tiles_n + n) that is u+1 inside an M tile and a jump of (gridDim.x - 1) M tiles after its last N tile
+  const bool a_res = p.a_res != 0;
+  const int unit0 = a_res ? (int)blockIdx.x * p.tiles_n : (int)blockIdx.x / CS, unit_step = (int)gridDim.x / CS;
+  const int res_jump = ((int)gridDim.x - 1) * p.tiles_n;
+  auto next_unit = [&](int u) { return a_res ? (u + 1 + (((u + 1) % p.tiles_n == 0) ? res_jump : 0)) : u + unit_step; };
   const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
 #define HRP_TILE_M(u) (((u) / p.tiles_n) * CS + crank)
 #define HRP_TILE_N(u) ((u) % p.tiles_n)
@@ -167,7 +174,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8u * s, p.tma ? 1 : TC_PRODUCERS + 1);
       mbar_init(bar_empty + 8u * s, (uint32_t)p.cluster);     // one tcgen05.commit per CTA that received the stage's weight tile
-      mbar_init(bar_split + 8u * s, TC_PRODUCERS);
+      mbar_init(bar_split + 8u * s, p.a_res ? 1u : (uint32_t)TC_PRODUCERS);   // a_res: [0] = activations landed, [1] = activations consumed
     }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_accf + 8u * i, 1); mbar_init(bar_acce + 8u * i, 1); }
     for (int i = 0; i < 2; ++i) mbar_init(sBar + 16u * TC_MAX_STAGES + 48u + 16u * TC_BLOCK_M + 8u * i, 1);   // residual boxes landed (epi_tma)
@@ -206,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     int it = 0;
     int s = 0, as = 0;                                         // ring slot being filled / slot whose copies are awaited (lag behind)
     uint32_t ph = 1;                                           // parity to wait on for empty[s] (first pass: slots start free)
-    for (int u = unit0; u < p.total_units; u += unit_step) {
+    for (int u = unit0; u < p.total_units; u = next_unit(u)) {
       const int m0 = HRP_TILE_M(u) * TC_BLOCK_M;
       const int b0 = m0 / hw_o;                                // first image this tile touches
       const uint8_t* tile_base = in8 + (size_t)b0 * a.Hi * a.Wi * a.Cin * ESZ;
@@ -272,7 +279,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const uint32_t n16 = (uint32_t)a_half >> 4;
       int s = 0;
       uint32_t ph = 0;
-      for (int u = unit0; u < p.total_units; u += unit_step)
+      for (int u = unit0; u < p.total_units; u = next_unit(u))
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(bar_full + 8u * s, ph);
           const uint32_t base = sA + (uint32_t)(s * a_stage);
@@ -293,17 +300,20 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     int li = 0, s = 0;
     uint32_t ph = 0;
     const int num_kb = p.num_kb;
-    for (int u = unit0; u < p.total_units; u += unit_step, ++li) {
+    int mj = 0;                                                  // a_res: M tiles this CTA has started
+    for (int u = unit0; u < p.total_units; u = next_unit(u), ++li) {
       const int buf = li & 1;
       if (li >= 2) mbar_wait(bar_acce + 8u * buf, ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.block_n);
+      const bool first_n = a_res && (u % p.tiles_n) == 0, last_n = a_res && ((u + 1) % p.tiles_n) == 0;
+      if (first_n) { mbar_wait(bar_split, (uint32_t)(mj & 1)); ++mj; }     // this M tile's activation k-blocks have landed
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(((x3 && p.tma) ? bar_split : bar_full) + 8u * s, ph);
         tc_fence_after();
         const int kleft = p.Ktot - kb * kbe;
         const int nk = (kleft >= kbe ? kbe : kleft) / UK;
-        const uint32_t aa = sA + (uint32_t)(s * a_stage), bb = sB + (uint32_t)(s * b_stage);
+        const uint32_t aa = sA + (uint32_t)((a_res ? kb : s) * a_stage), bb = sB + (uint32_t)(s * b_stage);
         if (x3) {
           for (int kk = 0; kk < nk; ++kk)
             if (leader) {                                        // small terms first, the leading product last
@@ -318,6 +328,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           if (CS > 1) umma_commit_mc(bar_empty + 8u * s, cmask);    // ... in every CTA whose loader writes into this CTA's stage
           else umma_commit(bar_empty + 8u * s);                  // frees the stage once these MMAs have read it
           if (kb == num_kb - 1) umma_commit(bar_accf + 8u * buf);   // accumulator complete
+          if (last_n && kb == num_kb - 1) umma_commit(bar_split + 8u);   // a_res: the resident activations may be replaced
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1u; }
@@ -335,18 +346,28 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       int it = 0, s = 0;
       uint32_t ph = 1;
       const uint32_t part = (uint32_t)b_half / (uint32_t)CS;     // this CTA's share of the rows of a multicast weight tile
-      for (int u = unit0; u < p.total_units; u += unit_step) {
+      int mj = 0;
+      for (int u = unit0; u < p.total_units; u = next_unit(u)) {
         const int n0 = HRP_TILE_N(u) * p.block_n;
         const int m0 = HRP_TILE_M(u) * TC_BLOCK_M;
         const int x0 = (m0 % a.Wo) * a.stride - a.pad_w, t1 = m0 / a.Wo, y0 = (t1 % a.Ho) * a.stride - a.pad_h, b0 = t1 / a.Ho;
         const uint8_t* wsrc = static_cast<const uint8_t*>(a.w) + (size_t)n0 * p.row_bytes;
         int c = 0, fr = 0, fs = 0;
+        if (a_res && HRP_TILE_N(u) == 0) {
+          // all k-blocks of this M tile's activations, once, into the A halves of stages 0..num_kb-1 (1x1 conv: one tap)
+          if (mj >= 1) mbar_wait(bar_split + 8u, (uint32_t)((mj - 1) & 1));     // the previous M tile's last MMA has read them
+          if (leader) {
+            mbar_arrive_expect_tx(bar_split, (uint32_t)(p.num_kb * a_half));
+            for (int kb = 0; kb < p.num_kb; ++kb) tma_load_4d(sA + (uint32_t)(kb * a_stage), p.tmap, kb * kbe, x0, y0, b0, bar_split);
+          }
+          ++mj;
+        }
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           if (it >= S) mbar_wait(bar_empty + 8u * s, ph);
           const uint32_t bar = bar_full + 8u * s;
           if (leader) {
-            mbar_arrive_expect_tx(bar, tx);
-            if (p.tma) tma_load_4d(sA + (uint32_t)(s * a_stage), p.tmap, c, x0 + fs, y0 + fr, b0, bar);
+            mbar_arrive_expect_tx(bar, a_res ? (uint32_t)b_stage : tx);
+            if (p.tma && !a_res) tma_load_4d(sA + (uint32_t)(s * a_stage), p.tmap, c, x0 + fs, y0 + fr, b0, bar);
             if (CS > 1) bulk_g2s_mc(sB + (uint32_t)(s * b_stage) + (uint32_t)crank * part, wsrc + kb * kb_stride + (size_t)crank * part, part, bar, cmask);
             else bulk_g2s(sB + (uint32_t)(s * b_stage), wsrc + kb * kb_stride, (uint32_t)b_half, bar);
             if (x3) bulk_g2s(sB + (uint32_t)(s * b_stage + b_half), wsrc + kb * kb_stride + (size_t)a.Cout * p.row_bytes, (uint32_t)b_half, bar);
@@ -386,7 +407,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     }
     epi_bar();
     int li = grp;
-    for (int u = unit0 + grp * unit_step; u < p.total_units; u += tile_inc * unit_step, li += tile_inc) {
+    for (int u = grp ? next_unit(unit0) : unit0; u < p.total_units; u = dual ? next_unit(next_unit(u)) : next_unit(u), li += tile_inc) {
       const int buf = li & 1;
       const int m0 = HRP_TILE_M(u) * TC_BLOCK_M, n0 = HRP_TILE_N(u) * p.block_n;
       // the row's pixel coordinates: three integer divisions per tile that only the register / cp.async epilogues need (the TMA
@@ -512,7 +533,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             for (int k = 0; k < p.n_chunks; ++k)
               tma_load_2d(tile_stg + (uint32_t)k * chunk_sz, p.tmap_res, a.out_coff + n0 + k * (int)(cbytes / ESZ), m0, bar_res);
           }
-          const int next = u + unit_step;
+          const int next = next_unit(u);
           if (early && next < p.total_units) {
             const int m1 = HRP_TILE_M(next) * TC_BLOCK_M, n1 = HRP_TILE_N(next) * p.block_n;
             const uint32_t stg1 = stg + (uint32_t)(sb ^ 1) * (uint32_t)(p.n_chunks * TC_BLOCK_M * p.chunk_bytes);
@@ -668,7 +689,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           for (int k = 0; k < p.n_chunks; ++k)
             tma_store_2d(p.tmap_out, a.out_coff + n0 + k * (int)(cbytes / ESZ), m0, tile_stg + (uint32_t)k * chunk_sz);
           bulk_commit();
-          const int next = u + unit_step;
+          const int next = next_unit(u);
           if (prefetch && !early && next < p.total_units) {
             bulk_wait_read1();                                 // the store of tile li-1 has finished reading the other buffer
             const int m1 = HRP_TILE_M(next) * TC_BLOCK_M, n1 = HRP_TILE_N(next) * p.block_n;
@@ -1004,6 +1025,7 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   if (a.sa_partial != nullptr) {                              // the fused heatmap head: 64 exponentials per thread and tile, no staging at all
     static const int sa_dual = env_int("HRP_TC_SA_DUAL", 1);
     p.epi_dual = (sa_dual && epi == 4 && p.tma && !x3) ? 1 : 0;
+    staging = 0;
   }
   const size_t fixed = 2048 + staging + tc_tail_bytes() + (size_t)a.Cout * 4;
   int smax = (int)((budget - fixed) / (opnd * tc_stage_bytes(bn, p.row_bytes)));
@@ -1012,6 +1034,16 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   p.stages = smax;                                          // the ring runs across tiles, so depth is not tied to num_kb
   const long long kb_per_cta = (long long)p.num_kb * ceil_div(p.total_tiles, sms * ctas);
   if (kb_per_cta < p.stages) p.stages = (int)std::max(1LL, kb_per_cta);
+  // Activation-resident walk for the fused heatmap head (HRP_TC_A_RES): its N tiles are the keypoints, and walking tiles N-fastest
+  // across CTAs made every keypoint's tile fetch the same 128 x 256-channel activation block again -- 1.5 GB of L2 requests per
+  // 64 frames, ~63 B/clk per SM, which is what the layer ran at. A CTA now owns whole M tiles: the block's k-blocks land once in
+  // the A halves of stages 0..num_kb-1 and the ring streams the keypoints' weight tiles (672 -> 288 KB per M tile).
+  // Measured (scripts/experiments/a_res.sh): results identical, the layer alone on the whole GPU 126 -> 142 us (the single resident
+  // block leaves the MMA warp idle while the next M tile's activations load, and alone the layer is not L2-bound), the network
+  // 13.85k vs 13.90k frames/s with and without (two interleaved runs each): kept as a switch, off by default.
+  static const int a_res_on = env_int("HRP_TC_A_RES", 0);   // off: correct (tests pass with it) but not faster, see the comment above
+  p.a_res = (a_res_on && a.sa_partial != nullptr && p.tma && !x3 && !tf32 && a.KH == 1 && a.KW == 1 && a.stride == 1 && p.tiles_n >= 2 &&
+             p.stages >= p.num_kb && p.num_kb <= TC_MAX_STAGES) ? 1 : 0;
   p.lag = std::min(TC_MAX_LAG, p.stages - 1);
   p.round_tf32 = x3 ? 0 : round_tf32;                       // 3xTF32 layers exchange full fp32 activations
   p.stg_off = (int)((p.stages * opnd * tc_stage_bytes(bn, p.row_bytes) + 1023) / 1024 * 1024);
@@ -1064,8 +1096,10 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
   p.cluster = cs;
   p.total_units = (mtiles / cs) * p.tiles_n;
   if (cs == 1) p.total_units = p.total_tiles;
+  if (cs > 1) p.a_res = 0;
   int grid = std::min(p.total_units * cs, cap);
   grid -= grid % cs;
+  if (p.a_res) grid = std::min(mtiles, cap);                 // one unit of work = an M tile with all its N tiles
   size_t smem_req = smem;
   if (cs > 1) {
     // A cluster CTA that holds TMEM may wait for a peer that is still waiting for TMEM on another SM, so cluster CTAs must
@@ -1075,8 +1109,8 @@ int conv_tc_launch(const ConvArgs& a, int tf32, int round_tf32, cudaStream_t st)
     smem_req = std::min((size_t)TC_SMEM_LIMIT, std::max(smem, share > 1024 ? share - 1024 : 0));
   }
   static const int dbg = env_int("HRP_TC_DEBUG", 0);
-  if (dbg) fprintf(stderr, "conv_tc %dx%d %d->%d k%d s%d res%d: bn %d epi %d ctas %d grid %d stages %d n_stg %d smem %zu tiles %d\n", a.Hi, a.Wi, a.Cin, a.Cout, a.KH,
-                   a.stride, a.res != nullptr, bn, epi, ctas, grid, p.stages, p.n_stg, smem_req, p.total_tiles);
+  if (dbg) fprintf(stderr, "conv_tc %dx%d %d->%d k%d s%d res%d: bn %d epi %d ctas %d grid %d stages %d n_stg %d smem %zu tiles %d dual %d a_res %d\n", a.Hi, a.Wi, a.Cin, a.Cout, a.KH,
+                   a.stride, a.res != nullptr, bn, epi, ctas, grid, p.stages, p.n_stg, smem_req, p.total_tiles, p.epi_dual, p.a_res);
   static const int pdl_early = env_int("HRP_PDL_EARLY", 0);
   p.pdl_early = pdl_early;
   cudaError_t le;
