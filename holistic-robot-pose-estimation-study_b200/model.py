@@ -475,38 +475,43 @@ class HostPipeline:
         # one compute stream per slot: the library keeps two plans (workspace + graph) per batch size and uses them
         # round-robin, so forwards enqueued on different streams overlap (the tail of batch i with the head of batch i+1)
         self.compute = [torch.cuda.Stream(dev) for _ in range(depth)]
-        self.img = [None] * depth             # device staging, allocated on first use in the dtype the caller submits (fp32 or uint8)
-        self.K = [torch.empty(self.B, 3, 3, device=dev) for _ in range(depth)]
-        self.kv = [torch.empty(self.B, device=dev) for _ in range(depth)]
+        # device staging: TWO input sets per slot, used alternately, so the upload of batch n never waits for the forward of
+        # batch n - depth (which still reads the slot's other set while 'depth' forwards are in flight); allocated on first
+        # use in the dtype the caller submits (fp32 or uint8)
+        self.nstage = 2 * depth
+        self.img = [None] * self.nstage
+        self.K = [torch.empty(self.B, 3, 3, device=dev) for _ in range(self.nstage)]
+        self.kv = [torch.empty(self.B, device=dev) for _ in range(self.nstage)]
         self.offs = model._record(self.B, dev)
         # pinned result buffers up front: a cudaHostAlloc inside the stream of submits synchronises the whole device
         self.host = [torch.empty(self.offs[-1], dtype=torch.float32).pin_memory() for _ in range(depth)]
-        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
-        self.ev_free = [None] * depth          # forward of the batch that last used this slot's inputs has finished
+        self.ev_in = [torch.cuda.Event() for _ in range(self.nstage)]
+        self.ev_free = [None] * self.nstage    # forward of the batch that last used this input set has finished
         self.ev_done = [None] * depth
         self.n = 0
 
     def submit(self, images, K, k_value=None):
-        s = self.n % self.depth
+        s = self.n % self.depth               # compute stream, plan and result buffer
+        g = self.n % self.nstage              # input staging set
         self.n += 1
         if k_value is None:
             k_value = torch.sqrt(K[:, 0, 0] * K[:, 1, 1] * 1000.0 * 1000.0 / (self.model.image_size * self.model.image_size))
         compute = self.compute[s]
         compute.wait_stream(torch.cuda.current_stream(self.model.device))
         with torch.cuda.stream(self.copy_stream):
-            if self.ev_free[s] is not None:
-                self.copy_stream.wait_event(self.ev_free[s])
-            if self.img[s] is None or self.img[s].dtype != images.dtype:
-                self.img[s] = torch.empty(self.B, 3, 256, 256, device=self.model.device, dtype=images.dtype)
-            self.img[s].copy_(images, non_blocking=True)
-            self.K[s].copy_(K, non_blocking=True)
-            self.kv[s].copy_(k_value, non_blocking=True)
-            self.ev_in[s].record(self.copy_stream)
-        compute.wait_event(self.ev_in[s])
+            if self.ev_free[g] is not None:
+                self.copy_stream.wait_event(self.ev_free[g])
+            if self.img[g] is None or self.img[g].dtype != images.dtype:
+                self.img[g] = torch.empty(self.B, 3, 256, 256, device=self.model.device, dtype=images.dtype)
+            self.img[g].copy_(images, non_blocking=True)
+            self.K[g].copy_(K, non_blocking=True)
+            self.kv[g].copy_(k_value, non_blocking=True)
+            self.ev_in[g].record(self.copy_stream)
+        compute.wait_event(self.ev_in[g])
         with torch.cuda.stream(compute):
-            rec, _ = self.model.forward_record(self.img[s], self.img[s], self.kv[s], self.K[s])
-            self.ev_free[s] = torch.cuda.Event()
-            self.ev_free[s].record(compute)
+            rec, _ = self.model.forward_record(self.img[g], self.img[g], self.kv[g], self.K[g])
+            self.ev_free[g] = torch.cuda.Event()
+            self.ev_free[g].record(compute)
             if self.post is not None:
                 rec = self.post(rec)             # e.g. the multi-GPU gather of the packed records
             if self.host[s] is None or self.host[s].numel() != rec.numel():
