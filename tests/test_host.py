@@ -183,3 +183,21 @@ def test_generated_fk_chains_are_current():
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_fk_programs.py"), "--check"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_committed_launch_list_reproduces_the_committed_traffic_summary(tmp_path):
+    """profiles/r02_dram_traffic_per_step.json (read by bench.py for roofline.traffic) is what scripts/ncu_launches.py
+    makes of the committed ncu launch list -- the evidence chain stays reproducible without a GPU."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv_path = os.path.join(root, "profiles", "r02_launches_f16_b64_one_forward.csv")
+    committed = json.load(open(os.path.join(root, "profiles", "r02_dram_traffic_per_step.json")))
+    out = tmp_path / "t.json"
+    subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_launches.py"), csv_path, str(committed["launches"]), str(out)],
+                   check=True, capture_output=True)
+    again = json.load(open(out))
+    assert again["launches"] == committed["launches"]
+    assert abs(again["dram_bytes_per_step"] - committed["dram_bytes_per_step"]) < 1.0
+    assert abs(again["l2_bytes_per_step"] - committed["l2_bytes_per_step"]) < 1.0
+    conv = sum(v for k, v in again["by_kernel_dram_mb"].items() if k.startswith("conv_"))
+    assert conv > 0.9 * again["dram_bytes_per_step"] / 1e6        # the conv family is what moves the bytes
